@@ -1,0 +1,182 @@
+"""TEST INFRASTRUCTURE ONLY -- regenerates tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (``python oracle/make_golden.py``); needs /root/reference,
+which does not exist on the GPU box -- hence the committed fixtures.  The reference is
+imported with the two shims of SURVEY.md appendix B (gym stub, np.float/np.long) and
+driven through its own public surface: ``SharedMAC``, ``QLearner.train`` /
+``QTRANLearner.train``, ``TwoAgentsMatrixGame``.  Each fixture stores inputs (batch,
+initial weights), the loss returned by every ``train()`` call, the clipped gradients
+left in ``p.grad`` after the first step, the final eval/target weights, and the
+step-0 intermediates obtained by replaying the reference's own methods in the order
+``train()`` calls them (q_learner.py:95-114).
+"""
+import copy
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+import numpy as np
+import torch as th
+
+REF = os.environ.get("MARL_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.modules.setdefault("gym", types.SimpleNamespace(Env=object))
+np.float = float
+np.long = np.int64
+
+from common.arguments import get_mixer_args  # noqa: E402
+from controller.share_params import SharedMAC  # noqa: E402
+from algorithm.q_learner import QLearner  # noqa: E402
+from algorithm.qtran_learner import QTRANLearner  # noqa: E402
+from env.single_state_matrix_game import TwoAgentsMatrixGame  # noqa: E402
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from marl_b200.synthetic import synthetic_batch  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
+PAYOFF1 = [[8, -12, -12], [-12, 0, 0], [-12, 0, 0]]          # matrix_game_test.py:43-45
+
+
+def ref_args(alg, N, A, O, S, T, **kw):
+    a = SimpleNamespace(RTW=False, alg=alg, map="synthetic", last_action=True, reuse_network=True,
+                        gamma=0.99, optimizer="RMS", model_dir="/tmp/marl_golden_model", result_dir="/tmp",
+                        cuda=False, load_model=False, evaluate=False, evaluate_epoch=0, replay_dir="", n_episodes=1)
+    get_mixer_args(a)
+    a.n_agents, a.n_actions, a.obs_shape, a.state_shape, a.episode_limit = N, A, O, S, T
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def dump_sd(prefix, sd, out):
+    for k, v in sd.items():
+        out[f"{prefix}/{k}"] = v.detach().cpu().numpy().copy()
+
+
+def run_case(name, alg, batch, N, A, O, S, T, n_steps=3, seed=0, **kw):
+    th.manual_seed(seed)
+    args = ref_args(alg, N, A, O, S, T, **kw)
+    mac = SharedMAC(args)
+    learner = QTRANLearner(mac, args) if alg == "qtran_base" else QLearner(mac, args)
+    out = {"meta/alg": np.array(alg), "meta/optimizer": np.array(args.optimizer),
+           "meta/dims": np.array([N, A, O, S, T]), "meta/n_steps": np.array(n_steps),
+           "meta/double_q": np.array(int(args.double_q)), "meta/lr": np.array(args.lr),
+           "meta/target_update_cycle": np.array(args.target_update_cycle)}
+    for k in ("num_kernel", "adv_hypernet_embed", "hypernet_embed", "qtran_hidden_dim"):
+        out[f"meta/{k}"] = np.array(getattr(args, k))
+    for k, v in batch.items():
+        out[f"batch/{k}"] = np.asarray(v)
+    dump_sd("init/agent", mac.agent.state_dict(), out)
+    dump_sd("init/mixer", learner.mixer.state_dict(), out)
+    if alg == "qtran_base":
+        dump_sd("init/v", learner.v.state_dict(), out)
+        dump_sd("init/q_sum_mixer", learner.q_sum_mixer.state_dict(), out)
+
+    # --- step-0 intermediates, replaying q_learner.py:95-114 / qtran_learner.py:95-114 on a deep copy
+    probe = copy.deepcopy(learner)
+    b = {k: np.array(v) for k, v in batch.items()}
+    b, L = probe.get_max_episode_len(b)
+    for k in b:
+        b[k] = th.tensor(b[k], dtype=th.long if k == "u" else th.float32)
+    B = b["o"].shape[0]
+    with th.no_grad():
+        probe.eval_net.init_hidden(B)
+        q_evals, hid = probe.eval_net.get_current_q_values(b, L)
+        probe.target_net.init_hidden(B)
+        q_targets, hid_t = probe.target_net.get_next_q_values(b, L)
+        q_targets[b["avail_u_next"] == 0.0] = -9999999
+        out["step0/L"] = np.array(L)
+        out["step0/q_evals"] = q_evals.numpy().copy()
+        out["step0/hidden_evals"] = hid.numpy().copy()
+        out["step0/q_targets"] = q_targets.numpy().copy()
+        if alg != "qtran_base" and args.double_q:
+            q_en, _ = probe.eval_net.get_next_q_values(b, L)      # no init_hidden: carried hidden
+            q_en[b["avail_u_next"] == 0] = -9999999
+            out["step0/q_evals_next"] = q_en.numpy().copy()
+            out["step0/cur_max_actions"] = th.argmax(q_en, dim=3).numpy().copy()
+        if alg in ("vdn", "qmix"):
+            qc = th.gather(q_evals, 3, b["u"]).squeeze(3)
+            out["step0/q_tot"] = probe.mixer(qc, b["s"]).numpy().copy()
+        if alg == "qtran_base":
+            out["step0/hidden_targets"] = hid_t.numpy().copy()
+
+    # --- the real thing
+    losses = []
+    for step in range(n_steps):
+        losses.append(learner.train({k: np.array(v) for k, v in batch.items()}, step))
+        if step == 0:
+            names = [("agent", k) for k, _ in mac.agent.named_parameters()]
+            names += [("mixer", k) for k, _ in learner.mixer.named_parameters()]
+            if alg == "qtran_base":
+                names += [("v", k) for k, _ in learner.v.named_parameters()]
+                names += [("q_sum_mixer", k) for k, _ in learner.q_sum_mixer.named_parameters()]
+            assert len(names) == len(learner.params)
+            for (g, k), p in zip(names, learner.params):
+                if p.grad is not None:
+                    out[f"clipped_grad/{g}/{k}"] = p.grad.detach().numpy().copy()
+    out["loss"] = np.array(losses, dtype=np.float64)
+    dump_sd("final/agent", mac.agent.state_dict(), out)
+    dump_sd("final/mixer", learner.mixer.state_dict(), out)
+    dump_sd("final_target/agent", learner.target_net.agent.state_dict(), out)
+    dump_sd("final_target/mixer", learner.target_mixer.state_dict(), out)
+    if alg == "qtran_base":
+        dump_sd("final/v", learner.v.state_dict(), out)
+    if N == 2 and A == 3 and O == 1 and S == 1 and alg != "qtran_base":
+        qt, qi, qj = learner.get_q_and_q_tot_table()                 # q_learner.py:211-262
+        out["table/q_tot"], out["table/q_i"], out["table/q_j"] = qt, qi, qj
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: losses={losses} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def env_case():
+    """TwoAgentsMatrixGame golden: get_episodes() + step() for all joint actions, 3 payoff tables."""
+    tables = [PAYOFF1, [[8, -12, -12], [-12, 6, 0], [-12, 0, 6]], [[8, 3, 2], [-12, -13, -14], [-12, -13, -14]]]
+    out = {}
+    for i, tab in enumerate(tables):
+        env = TwoAgentsMatrixGame(tab)
+        for k, v in env.get_episodes().items():
+            out[f"t{i}/episodes/{k}"] = np.asarray(v)
+        rew = np.zeros((3, 3))
+        for a0 in range(3):
+            for a1 in range(3):
+                env.reset()
+                r, term, info = env.step([a0, a1])
+                assert term is True and info == {}
+                rew[a0, a1] = r
+        out[f"t{i}/step_reward"] = rew
+        out[f"t{i}/payoff"] = np.array(tab, dtype=np.float64)
+        out[f"t{i}/obs"] = np.array(env.get_obs())
+        out[f"t{i}/state"] = np.array(env.get_state())
+        out[f"t{i}/avail"] = np.array(env.get_avail_actions())
+        out[f"t{i}/replay_len"] = np.array(len(env.replay))
+        info = env.get_env_info()
+        out[f"t{i}/env_info"] = np.array([info[k] for k in ("n_actions", "n_agents", "state_shape", "obs_shape", "episode_limit")])
+    np.savez_compressed(os.path.join(OUT, "matrix_game_env.npz"), **out)
+    print("matrix_game_env ok")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    env_case()
+    tiny = dict(N=3, A=4, O=5, S=6, T=6)
+    tb = synthetic_batch(0, 4, tiny["T"], tiny["N"], tiny["A"], tiny["O"], tiny["S"])
+    small_qplex = dict(num_kernel=2, adv_hypernet_embed=8, hypernet_embed=8)
+    run_case("tiny_vdn_rms", "vdn", tb, **tiny, target_update_cycle=2)
+    run_case("tiny_qmix_rms", "qmix", tb, **tiny, target_update_cycle=2)
+    run_case("tiny_qmix_adam", "qmix", tb, **tiny, optimizer="Adam", target_update_cycle=2)
+    run_case("tiny_qmix_nodouble", "qmix", tb, **tiny, double_q=False, n_steps=2)
+    run_case("tiny_qplex_rms", "qplex", tb, **tiny, target_update_cycle=2, **small_qplex)
+    run_case("tiny_qtran_rms", "qtran_base", tb, **tiny, target_update_cycle=2, qtran_hidden_dim=16)
+    # config 1: QMIX on the matrix game's fixed 9-episode batch (matrix_game_test.py:77-93)
+    mg = TwoAgentsMatrixGame(PAYOFF1).get_episodes()
+    run_case("matrix_qmix_rms", "qmix", mg, N=2, A=3, O=1, S=1, T=1, n_steps=5, lr=1e-3)
+    run_case("matrix_vdn_rms", "vdn", mg, N=2, A=3, O=1, S=1, T=1, n_steps=3, lr=1e-3)
+    # one ragged mid-size case: first episode shorter than the limit -> truncation L < T
+    rb = synthetic_batch(3, 5, 9, 2, 5, 7, 4, full_length_first=False, min_len=2)
+    run_case("ragged_qmix_rms", "qmix", rb, N=2, A=5, O=7, S=4, T=9, n_steps=2)
+
+
+if __name__ == "__main__":
+    main()
