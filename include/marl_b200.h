@@ -1,0 +1,189 @@
+/*
+ * libmarl_b200 -- C ABI of the B200-native (sm_100a) value-factorisation learner hot path.
+ *
+ * The reference (Skylarking/MARL) is pure Python/PyTorch and has no FFI of its own; the
+ * entry points below are what a binding for its hot path attaches to.  Each one names the
+ * reference code it replaces (paths relative to the reference root).  Conventions:
+ *   - every function returns int: 0 = ok, <0 = argument error (MARL_EINVAL), >0 = cudaError_t;
+ *   - all data pointers are DEVICE pointers unless the name ends in _host;
+ *   - nothing is allocated or freed on behalf of the caller; workspaces are caller-owned;
+ *   - `stream` is a cudaStream_t; every call is asynchronous with respect to the host;
+ *   - tensors are dense, row-major fp32 in the reference's episode-major layout
+ *     (common/replaybuffer.py:19-30), rows of the folded agent batch are (b, n) with n minor
+ *     (controller/share_params.py:110); action ids are int64.
+ *   - H = rnn_hidden_dim = 64 and E = qmix_hidden_dim = 32 are compile-time constants
+ *     (common/arguments.py:88-89); everything else is a run-time size.
+ */
+#ifndef MARL_B200_H
+#define MARL_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MARL_B200_VERSION 100
+#define MARL_HIDDEN 64
+#define MARL_QMIX_EMBED 32
+
+int marl_version(void);
+/* Runtime probe: fills sm count / compute capability of the current device. */
+int marl_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* B episodes, L = max_episode_len after truncation (algorithm/q_learner.py:49-66),
+ * N agents, A actions, O obs dim, S state dim. */
+typedef struct marl_dims { int B, L, N, A, O, S; } marl_dims;
+
+/* One episode batch on the device, fp32, the 11 ReplayBuffer keys (common/replaybuffer.py:19-30):
+ * o,o_next [B,L,N,O]  s,s_next [B,L,S]  u [B,L,N] (int64)  r,padded,terminated [B,L]
+ * avail_u,avail_u_next,u_onehot [B,L,N,A]. */
+typedef struct marl_episode_f32 {
+    float* o; float* s; long long* u; float* r; float* o_next; float* s_next;
+    float* avail_u; float* avail_u_next; float* u_onehot; float* padded; float* terminated;
+} marl_episode_f32;
+
+/* The same 11 keys as the reference hands them to train(): float64, [B, T_src, ...]
+ * (u may be float64 or int64: u_is_int64). */
+typedef struct marl_episode_f64 {
+    const double* o; const void* u; const double* s; const double* r; const double* o_next;
+    const double* s_next; const double* avail_u; const double* avail_u_next; const double* u_onehot;
+    const double* padded; const double* terminated;
+    int u_is_int64;
+} marl_episode_f64;
+
+/* ---- environment: env/single_state_matrix_game.py:27-40 (step), :81-120 (episode layout) ----
+ * Steps n_envs independent TwoAgentsMatrixGame instances: reward = payoff[a0, a1], terminated = 1,
+ * and writes one T=1 episode record per env.  actions: [n_envs, 2] int32 or int64 (action_bytes 4|8).
+ * obs_value: 0 reproduces get_obs()/get_state() (what a rollout records), 1 reproduces get_episodes().
+ * r64 (nullable): the float64 reward exactly as the reference returns it. */
+int marl_matrix_game_step(const double* payoff_host /*[9]*/, const void* actions, int action_bytes,
+                          long long n_envs, float obs_value, const marl_episode_f32* out,
+                          double* r64, void* stream);
+/* Sets *bad_flag_device to 1 if any action is outside {0,1,2} (reference: IndexError). */
+int marl_matrix_game_validate_actions(const void* actions, int action_bytes, long long n_envs,
+                                      int* bad_flag_device, void* stream);
+
+/* ---- batch ingest: algorithm/q_learner.py:63-78,83 ----
+ * float64 [B, T_src, ...] -> fp32 [B, L, ...] (truncation to L and the dtype casts of train(); u is
+ * truncated toward zero like th.tensor(..., dtype=th.long)). */
+int marl_ingest_f64(const marl_episode_f64* src, int T_src, const marl_dims* d,
+                    const marl_episode_f32* dst, void* stream);
+
+/* ---- agent: network/q_network.py:6-21 unrolled by controller/share_params.py:125-168 ---- */
+typedef struct marl_agent_params {
+    const float* fc1_w;  /* [H, O+A+N] */  const float* fc1_b;  /* [H] */
+    const float* w_ih;   /* [3H, H]   */  const float* w_hh;   /* [3H, H] */
+    const float* b_ih;   /* [3H]      */  const float* b_hh;   /* [3H] */
+    const float* fc2_w;  /* [A, H]    */  const float* fc2_b;  /* [A] */
+} marl_agent_params;
+
+typedef struct marl_agent_grads {
+    float* fc1_w; float* fc1_b; float* w_ih; float* w_hh; float* b_ih; float* b_hh; float* fc2_w; float* fc2_b;
+} marl_agent_grads;
+
+/* One T-step unroll ("stream") of the shared agent over an episode batch.
+ * Input row at step t = [obs[b,t,n] | onehot[b,t-shift,n] (zeros when t < shift) | eye(N)[n]]
+ * (share_params.py:84-112; shift_onehot=1 is get_current_q_values, 0 is get_next_q_values).
+ * Hidden state starts from zeros (init_hidden, :74-76), from h0, or -- h0_from >= 0 -- from the
+ * final hidden of an earlier stream of the same call (the carried hidden of q_learner.py:110). */
+typedef struct marl_unroll_stream {
+    const float* obs;        /* [B,L,N,O] */
+    const float* onehot;     /* [B,L,N,A] */
+    int shift_onehot;
+    int full_input;          /* 1: `obs` already holds the full [O+A+N]-wide input rows (RNNQNet.forward /
+                                choose_action, share_params.py:37-61); onehot is ignored */
+    int h0_from;             /* -1, or index of an earlier stream in the same call */
+    const float* h0;         /* [B*N,H] or NULL */
+    marl_agent_params params;
+    float* q;                /* out [B,L,N,A] */
+    float* hidden;           /* out [B,L,N,H], h after each step */
+    float* h_last;           /* out [B*N,H] or NULL */
+    float* x;                /* workspace/out [B,L,N,H]: relu(fc1) (needed by the backward) */
+    float* gi;               /* workspace [B,L,N,3H] */
+    float* gates;            /* out [B,L,N,4H] (r, z, n, W_hn h + b_hn) for the backward, or NULL */
+} marl_unroll_stream;
+
+int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_stream* streams, int n_streams, void* stream);
+
+/* BPTT of one unroll (autograd of share_params.py:125-146 as triggered by
+ * loss.backward(), q_learner.py:171).  dq [B,L,N,A] and dhidden [B,L,N,H] (either may be NULL) are
+ * dL/dq and an external dL/dhidden (QTRAN, qtran_learner.py:119,136).  Gradients are ACCUMULATED
+ * into `grads` (caller zeroes).  Workspaces: dhext [B,L,N,H], dgi [B,L,N,3H], dgh [B,L,N,3H],
+ * dx [B,L,N,H]. */
+typedef struct marl_unroll_bwd {
+    const float* obs; const float* onehot; int shift_onehot; int full_input;
+    marl_agent_params params;
+    const float* hidden; const float* x; const float* gates;
+    const float* h0;         /* [B*N,H] initial hidden of the forward, or NULL (zeros) */
+    const float* dq; const float* dhidden;
+    float* dhext; float* dgi; float* dgh; float* dx;
+    float* dh0;              /* out [B*N,H] dL/dh0, or NULL */
+    marl_agent_grads grads;
+} marl_unroll_bwd;
+
+int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* a, void* stream);
+
+/* ---- action-value selection: algorithm/q_learner.py:100,105,108-117,126-127 ----
+ * q_chosen = q_evals.gather(u); q_targets[avail_u_next==0] = -9999999 (IN PLACE, as the reference);
+ * double-Q (q_evals_next != NULL): a* = argmax_a of the masked q_evals_next (first max wins),
+ * q_targets_chosen = q_targets.gather(a*); else q_targets_chosen = max_a q_targets.
+ * Optional (QPLEX): max_q_evals = max_a of q_evals masked by avail_u; q_targets_max = max_a q_targets. */
+int marl_q_select(const marl_dims* d, const float* q_evals, const long long* u, const float* q_evals_next,
+                  float* q_targets, const float* avail_u_next, const float* avail_u /*nullable*/,
+                  float* q_chosen, long long* a_star /*nullable*/, float* q_targets_chosen,
+                  float* max_q_evals /*nullable*/, float* q_targets_max /*nullable*/, void* stream);
+
+/* ---- TD target + masked MSE: algorithm/q_learner.py:165-168 ----
+ * y = r + gamma*q_tot_target*(1-terminated); d = (1-padded)*(y - q_tot);
+ * scalars[0] += sum d^2, scalars[1] += sum (1-padded); dq_tot = -2*(1-padded)*d  (UN-normalised:
+ * the 1/sum(mask) factor is applied by the optimiser step, after the data-parallel all-reduce). */
+int marl_td_loss(int M, const float* q_tot, const float* q_tot_target, const float* r, const float* terminated,
+                 const float* padded, float gamma, float* dq_tot, float* scalars, void* stream);
+
+/* ---- VDN: network/mixer.py:15-16 fused with the TD loss and its gradient ----
+ * dq [B,L,N,A] receives dL/dq_evals (dense: dq_tot at the chosen action, 0 elsewhere). */
+int marl_vdn_td_fwd_bwd(const marl_dims* d, const float* q_chosen, const float* q_targets_chosen,
+                        const long long* u, const float* r, const float* terminated, const float* padded,
+                        float gamma, float* q_tot, float* q_tot_target, float* dq, float* scalars, void* stream);
+
+/* ---- QMIX: network/mixer.py:57-80 ----
+ * Hyper-network weights are passed concatenated (the host lays the parameters out that way):
+ *   wcat [C, S], bcat [C] with C = N*E + 3E rows in the order
+ *   hyper_w1 (N*E) | hyper_b1 (E) | hyper_w2 (E) | hyper_b2.0 (E);  wb2 [E], bb2 [1] = hyper_b2.2. */
+typedef struct marl_qmix_params { const float* wcat; const float* bcat; const float* wb2; const float* bb2; } marl_qmix_params;
+typedef struct marl_qmix_grads { float* wcat; float* bcat; float* wb2; float* bb2; } marl_qmix_grads;
+
+/* q_tot[M] = QMixMixer(q[M,N], s[M,S]);  hy [M,C] workspace keeps the hyper-network outputs for the backward. */
+int marl_qmix_fwd(int M, int N, int S, const marl_qmix_params* p, const float* q, const float* s,
+                  float* hy, float* q_tot, void* stream);
+/* Given dq_tot[M]: dq[M,N] and accumulated parameter gradients. dhy [M,C] workspace. */
+int marl_qmix_bwd(int M, int N, int S, const marl_qmix_params* p, const float* q, const float* s,
+                  const float* hy, const float* dq_tot, float* dhy, float* dq, const marl_qmix_grads* g, void* stream);
+/* Learner fusion (q_learner.py:161-168 + backward): eval mixer on (q_chosen, s), target mixer on
+ * (q_targets_chosen, s_next), TD loss, gradient to the eval mixer parameters and dense dq [B,L,N,A]. */
+int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* p, const marl_qmix_params* p_target,
+                         const float* s, const float* s_next, const float* q_chosen, const float* q_targets_chosen,
+                         const long long* u, const float* r, const float* terminated, const float* padded, float gamma,
+                         float* hy, float* hy_target, float* dhy, float* q_tot, float* q_tot_target,
+                         float* dq, const marl_qmix_grads* g, float* scalars, void* stream);
+
+/* ---- clip_grad_norm_ + optimiser: algorithm/q_learner.py:172-173 ----
+ * grads holds d/dtheta of the UN-normalised loss sum; scalars = {loss_sum, mask_sum} (after the
+ * all-reduce in data-parallel runs).  g = grads/mask_sum; total_norm = ||g||_2;
+ * g *= min(1, max_norm/(total_norm+1e-6)) (torch/nn/utils/clip_grad.py); grads is overwritten with the
+ * clipped g (what p.grad holds after the reference's train()); loss_out[0] = loss_sum/mask_sum,
+ * loss_out[1] = total_norm.  partials: workspace of marl_optim_partials() floats.
+ * Adam: the step count is `step` (>= 1), or -- when step_counter is non-NULL -- a device int32 that the
+ * call itself pre-increments (so a captured CUDA graph can be replayed). */
+int marl_optim_partials(void);
+int marl_clip_rmsprop_step(float* params, float* grads, float* square_avg, long long n, const float* scalars,
+                           float max_norm, float lr, float alpha, float eps, float* partials, float* loss_out,
+                           void* stream);
+int marl_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                        const float* scalars, float max_norm, float lr, float beta1, float beta2, float eps,
+                        int step, int* step_counter /*nullable, device*/, float* partials, float* loss_out,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARL_B200_H */

@@ -1,0 +1,141 @@
+"""ctypes binding of libmarl_b200.so (the C ABI declared in include/marl_b200.h).
+
+There is no CPU fallback: if the library is missing, or a kernel is called without a CUDA
+device, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmarl_b200.so")
+
+c_float_p = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
+c_ptr = C.c_void_p
+
+
+class Dims(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("B", "L", "N", "A", "O", "S")]
+
+
+EPISODE_KEYS = ("o", "s", "u", "r", "o_next", "s_next", "avail_u", "avail_u_next", "u_onehot", "padded", "terminated")
+
+
+class EpisodeF32(C.Structure):
+    _fields_ = [(k, c_ptr) for k in EPISODE_KEYS]
+
+
+class EpisodeF64(C.Structure):
+    _fields_ = [(k, c_ptr) for k in ("o", "u", "s", "r", "o_next", "s_next", "avail_u", "avail_u_next", "u_onehot",
+                                     "padded", "terminated")] + [("u_is_int64", C.c_int)]
+
+
+AGENT_KEYS = ("fc1_w", "fc1_b", "w_ih", "w_hh", "b_ih", "b_hh", "fc2_w", "fc2_b")
+
+
+class AgentParams(C.Structure):
+    _fields_ = [(k, c_ptr) for k in AGENT_KEYS]
+
+
+class AgentGrads(C.Structure):
+    _fields_ = [(k, c_ptr) for k in AGENT_KEYS]
+
+
+class UnrollStream(C.Structure):
+    _fields_ = [("obs", c_ptr), ("onehot", c_ptr), ("shift_onehot", C.c_int), ("full_input", C.c_int),
+                ("h0_from", C.c_int), ("h0", c_ptr),
+                ("params", AgentParams), ("q", c_ptr), ("hidden", c_ptr), ("h_last", c_ptr), ("x", c_ptr),
+                ("gi", c_ptr), ("gates", c_ptr)]
+
+
+class UnrollBwd(C.Structure):
+    _fields_ = [("obs", c_ptr), ("onehot", c_ptr), ("shift_onehot", C.c_int), ("full_input", C.c_int),
+                ("params", AgentParams), ("hidden", c_ptr), ("x", c_ptr), ("gates", c_ptr), ("h0", c_ptr), ("dq", c_ptr),
+                ("dhidden", c_ptr), ("dhext", c_ptr), ("dgi", c_ptr), ("dgh", c_ptr), ("dx", c_ptr), ("dh0", c_ptr),
+                ("grads", AgentGrads)]
+
+
+class QmixParams(C.Structure):
+    _fields_ = [(k, c_ptr) for k in ("wcat", "bcat", "wb2", "bb2")]
+
+
+class QmixGrads(C.Structure):
+    _fields_ = [(k, c_ptr) for k in ("wcat", "bcat", "wb2", "bb2")]
+
+
+_P = C.POINTER
+_SIGNATURES = {
+    "marl_version": ([], C.c_int),
+    "marl_device_info": ([_P(C.c_int)] * 3, C.c_int),
+    "marl_matrix_game_step": ([_P(C.c_double), c_ptr, C.c_int, C.c_longlong, C.c_float, _P(EpisodeF32), c_ptr, c_ptr], C.c_int),
+    "marl_matrix_game_validate_actions": ([c_ptr, C.c_int, C.c_longlong, c_ptr, c_ptr], C.c_int),
+    "marl_ingest_f64": ([_P(EpisodeF64), C.c_int, _P(Dims), _P(EpisodeF32), c_ptr], C.c_int),
+    "marl_agent_unroll_fwd": ([_P(Dims), _P(UnrollStream), C.c_int, c_ptr], C.c_int),
+    "marl_agent_unroll_bwd": ([_P(Dims), _P(UnrollBwd), c_ptr], C.c_int),
+    "marl_q_select": ([_P(Dims)] + [c_ptr] * 11 + [c_ptr], C.c_int),
+    "marl_td_loss": ([C.c_int] + [c_ptr] * 5 + [C.c_float, c_ptr, c_ptr, c_ptr], C.c_int),
+    "marl_vdn_td_fwd_bwd": ([_P(Dims)] + [c_ptr] * 6 + [C.c_float] + [c_ptr] * 4 + [c_ptr], C.c_int),
+    "marl_qmix_fwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
+    "marl_qmix_bwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams)] + [c_ptr] * 6 + [_P(QmixGrads), c_ptr], C.c_int),
+    "marl_qmix_td_fwd_bwd": ([_P(Dims), _P(QmixParams), _P(QmixParams)] + [c_ptr] * 8 + [C.c_float] + [c_ptr] * 6
+                             + [_P(QmixGrads), c_ptr, c_ptr], C.c_int),
+    "marl_optim_partials": ([], C.c_int),
+    "marl_clip_rmsprop_step": ([c_ptr, c_ptr, c_ptr, C.c_longlong, c_ptr] + [C.c_float] * 4 + [c_ptr, c_ptr, c_ptr], C.c_int),
+    "marl_clip_adam_step": ([c_ptr] * 4 + [C.c_longlong, c_ptr] + [C.c_float] * 5 + [C.c_int, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
+}
+
+_lib = None
+
+
+class MarlLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the .so is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MarlLibraryError(
+            f"{LIB_PATH} is missing: run `python -m marl_b200.build` (needs nvcc); marl_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (argtypes, restype) in _SIGNATURES.items():
+        fn = getattr(lib, name)     # AttributeError if the .so does not export a declared symbol
+        fn.argtypes, fn.restype = argtypes, restype
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise ValueError(f"{what}: invalid argument (MARL_EINVAL)")
+    raise MarlLibraryError(f"{what}: CUDA error {rc}")
+
+
+def require_cuda(t: torch.Tensor, name="tensor"):
+    if not t.is_cuda:
+        raise MarlLibraryError(f"{name} must live on a CUDA device: marl_b200 has no CPU path")
+    return t
+
+
+def ptr(t):
+    """Device address of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)

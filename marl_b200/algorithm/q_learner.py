@@ -1,0 +1,453 @@
+"""VDN / QMIX / QPLEX learner on sm_100a kernels, drop-in for ``algorithm/q_learner.py:10-262``.
+
+``QLearner(mac, args).train(batch, train_step) -> float`` keeps the reference's contract (same
+batch dict in the ReplayBuffer layout, same loss value, same parameter update, same target-sync
+cadence, ``mac.hidden_states`` left as the reference leaves it) but executes as a short fixed
+sequence of libmarl_b200 calls, captured in a CUDA graph per (B, L):
+
+    ingest (f64 -> f32)                      marl_ingest_f64            q_learner.py:63-91
+    3 agent unrolls (eval/o, eval/o_next     marl_agent_unroll_fwd      :96-97, :103-104, :110
+      chained to it, target/o_next)
+    gather / masked argmax / target gather   marl_q_select              :100, :105, :111-117
+    mixer + TD loss + their gradient         marl_{vdn,qmix}_td_fwd_bwd :161-168, :171
+    BPTT through the eval/o unroll           marl_agent_unroll_bwd      :171
+    [data parallel: one NCCL all-reduce of the flat gradient + (loss_sum, mask_sum)]
+    clip_grad_norm_ + RMSprop/Adam           marl_clip_{rmsprop,adam}_step   :172-173
+    target sync = one D2D copy               :176-177, :181-184
+
+No autograd, no PyTorch arithmetic and no CPU fallback on this path.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+import os
+
+import numpy as np
+import torch as th
+
+from .. import _lib as L
+from ..flat import FlatBuffer
+from ..network.mixer import VDNMixer, QMixMixer, qmix_struct
+from ..network.q_network import agent_param_struct, AGENT_FLAT_ORDER
+
+H = 64
+BATCH_KEYS = ("o", "u", "s", "r", "o_next", "s_next", "avail_u", "avail_u_next", "u_onehot", "padded", "terminated")
+
+
+def host_max_episode_len(terminated, episode_limit):
+    """q_learner.py:49-61 vectorised: 1 + the largest first-terminated index, limit if none."""
+    term = np.asarray(terminated)[:, :episode_limit, 0] == 1
+    has = term.any(axis=1)
+    if not has.any():
+        return int(episode_limit)
+    return int(term.argmax(axis=1)[has].max()) + 1
+
+
+class _FlatOptimizer:
+    """Facade with the torch.optim surface the reference touches (zero_grad / state)."""
+
+    def __init__(self, kind, lr, flat, device):
+        self.kind, self.lr = kind, lr
+        self.defaults = dict(lr=lr, alpha=0.99, eps=1e-8, betas=(0.9, 0.999))
+        n = flat.numel
+        z = lambda: th.zeros(n, dtype=th.float32, device=device)
+        if kind == "RMS":
+            self.square_avg = z()
+        else:
+            self.exp_avg, self.exp_avg_sq = z(), z()
+            self.step_counter = th.zeros(1, dtype=th.int32, device=device)
+        self._flat = flat
+
+    def zero_grad(self, set_to_none=False):
+        self._flat.grad_full.zero_()
+
+    def state_dict(self):
+        if self.kind == "RMS":
+            return {"square_avg": self.square_avg}
+        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_counter}
+
+
+class QLearner:
+    def __init__(self, mac, args):
+        self.max_episode_len = args.episode_limit
+        self.gamma = args.gamma
+        self.lr = args.lr
+        self.model_dir = args.model_dir + '/' + args.alg + '/' + args.map
+        self.args = args
+
+        self.eval_net = mac
+        self.target_net = copy.deepcopy(mac)
+        self.params = list(mac.parameters())
+        self.mixer = self._make_mixer(args)
+        self.target_mixer = copy.deepcopy(self.mixer)
+        self.params += list(self.mixer.parameters())
+        if args.optimizer not in ("RMS", "Adam"):
+            raise ValueError("optimizer {} not recognised.".format(args.optimizer))
+
+        self._dev = th.device("cuda") if th.cuda.is_available() else th.device("cpu")
+        self._pack()
+        self._ws = {}
+        self._graphs = {}
+        self._use_graph = bool(getattr(args, "cuda_graph", True))
+        self._dist = None
+        self.last = {}
+        self.launches_per_step = 0
+
+    # ---- construction helpers ---------------------------------------------------------------------
+    def _make_mixer(self, args):
+        if args.alg == 'vdn':
+            return VDNMixer(args)
+        if args.alg == 'qmix':
+            return QMixMixer(args)
+        if args.alg == 'qplex':
+            from ..network.qplex import DMAQer
+            return DMAQer(args)
+        raise ValueError("Mixer {} not recognised.".format(args.alg))
+
+    def _pack(self):
+        """All optimised tensors into one flat buffer (+grad +2 tail scalars); targets mirror it."""
+        dev = self._dev
+        named = [("agent." + n, p) for n, p in self.eval_net.agent.flat_named_parameters()]
+        named += [("mixer." + n, p) for n, p in self.mixer.flat_named_parameters()]
+        self._flat = FlatBuffer(named, device=dev, with_grad=True, extra_tail=2)
+        tnamed = [("agent." + n, p) for n, p in self.target_net.agent.flat_named_parameters()]
+        tnamed += [("mixer." + n, p) for n, p in self.target_mixer.flat_named_parameters()]
+        self._tflat = FlatBuffer(tnamed, device=dev, with_grad=False)
+        self.eval_net.agent.adopt(self._flat)
+        self.target_net.agent.adopt(self._tflat)
+        if hasattr(self.mixer, "adopt"):
+            self.mixer.adopt(self._flat)
+            self.target_mixer.adopt(self._tflat)
+        self.optimizer = _FlatOptimizer(self.args.optimizer, self.lr, self._flat, dev)
+        self._partials = th.zeros(L.load().marl_optim_partials() if os.path.exists(L.LIB_PATH) else 148,
+                                  dtype=th.float32, device=dev)
+        self._loss_out = th.zeros(2, dtype=th.float32, device=dev)
+        self._loss_host = th.zeros(2, dtype=th.float32).pin_memory() if dev.type == "cuda" else th.zeros(2)
+        self._ws, self._graphs = {}, {}
+
+    def cuda(self):
+        self._dev = th.device("cuda")
+        self._pack()
+
+    def enable_data_parallel(self, group=None):
+        """Shard every batch along the episode axis over the ranks of `group` and all-reduce the
+        flat [grad | loss_sum | mask_sum] buffer once per step."""
+        import torch.distributed as dist
+        self._dist = (dist, group)
+        self._graphs = {}
+
+    # ---- reference surface: episode-length cut ------------------------------------------------------
+    def get_max_episode_len(self, batch):
+        L_ = host_max_episode_len(_to_numpy(batch["terminated"]), self.args.episode_limit)
+        for key in batch.keys():
+            batch[key] = batch[key][:, :L_]
+        return batch, L_
+
+    # ---- staging -------------------------------------------------------------------------------------
+    def _dims(self, B, Lq):
+        a = self.args
+        return L.Dims(B, Lq, a.n_agents, a.n_actions, a.obs_shape, a.state_shape)
+
+    def _workspace(self, B, Lq):
+        key = (B, Lq)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        a, dev = self.args, self._dev
+        N, A, O, S = a.n_agents, a.n_actions, a.obs_shape, a.state_shape
+        rows, M = B * Lq * N, B * Lq
+        f = lambda *shape: th.empty(*shape, dtype=th.float32, device=dev)
+        ws = dict(
+            batch=dict(o=f(B, Lq, N, O), s=f(B, Lq, S), u=th.empty(B, Lq, N, dtype=th.int64, device=dev), r=f(B, Lq),
+                       o_next=f(B, Lq, N, O), s_next=f(B, Lq, S), avail_u=f(B, Lq, N, A), avail_u_next=f(B, Lq, N, A),
+                       u_onehot=f(B, Lq, N, A), padded=f(B, Lq), terminated=f(B, Lq)),
+            x=[f(rows, H) for _ in range(3)], gi=[f(rows, 3 * H) for _ in range(3)],
+            hidden=[f(B, Lq, N, H) for _ in range(3)], q=[f(B, Lq, N, A) for _ in range(3)],
+            h_last=[f(B * N, H) for _ in range(3)], gates=f(rows, 4 * H),
+            q_chosen=f(B, Lq, N), q_tc=f(B, Lq, N), a_star=th.empty(B, Lq, N, dtype=th.int64, device=dev),
+            q_tot=f(B, Lq, 1), q_tot_t=f(B, Lq, 1), dq=f(B, Lq, N, A),
+            dhext=f(rows, H), dgi=f(rows, 3 * H), dgh=f(rows, 3 * H), dx=f(rows, H),
+        )
+        if a.alg == "qmix":
+            Ccols = N * 32 + 96
+            ws.update(hy=f(M, Ccols), hy_t=f(M, Ccols), dhy=f(M, Ccols))
+        self._ws[key] = ws
+        return ws
+
+    def _stage_host_batch(self, batch):
+        """numpy (float64, [B, T_src, ...]) -> pinned/pageable H2D -> marl_ingest_f64 -> fp32 working set."""
+        a, dev = self.args, self._dev
+        Lq = host_max_episode_len(_to_numpy(batch["terminated"]), a.episode_limit)
+        arrs = {k: _to_numpy(batch[k]) for k in BATCH_KEYS}
+        B_glob, T_src = arrs["o"].shape[0], arrs["o"].shape[1]
+        lo, hi = self._shard(B_glob)
+        B = hi - lo
+        ws = self._workspace(B, Lq)
+        key = ("stage", B, T_src)
+        st = self._ws.get(key)
+        if st is None:
+            st = {}
+            for k in BATCH_KEYS:
+                shape = (B,) + arrs[k].shape[1:]
+                dt = th.int64 if (k == "u" and arrs[k].dtype.kind in "iu") else th.float64
+                st[k] = th.empty(shape, dtype=dt, device=dev)
+            self._ws[key] = st
+        h2d = 0
+        for k in BATCH_KEYS:
+            src = arrs[k][lo:hi]
+            want = np.int64 if st[k].dtype == th.int64 else np.float64
+            if src.dtype != want or not src.flags.c_contiguous:
+                src = np.ascontiguousarray(src, dtype=want)
+            st[k].copy_(th.from_numpy(src), non_blocking=True)
+            h2d += src.nbytes
+        self.h2d_bytes_last = h2d
+        e64 = L.EpisodeF64()
+        for k in BATCH_KEYS:
+            setattr(e64, k, st[k].data_ptr())
+        e64.u_is_int64 = int(st["u"].dtype == th.int64)
+        d = self._dims(B, Lq)
+        e32 = _episode_struct(ws["batch"])
+        L.call("marl_ingest_f64", C.byref(e64), T_src, C.byref(d), C.byref(e32), L.stream_ptr())
+        return ws["batch"], B, Lq, 1
+
+    def _stage_device_batch(self, batch):
+        """Dict of CUDA tensors already in the device layout (fp32, u int64)."""
+        a = self.args
+        Lq = batch.get("max_episode_len") if isinstance(batch, dict) else None
+        if Lq is None:
+            term = batch["terminated"].reshape(batch["terminated"].shape[0], -1)[:, :a.episode_limit] == 1
+            has = term.any(dim=1)
+            first = term.to(th.int32).argmax(dim=1)
+            Lq = int((first[has].max() + 1).item()) if bool(has.any()) else int(a.episode_limit)
+        B_glob = batch["o"].shape[0]
+        lo, hi = self._shard(B_glob)
+        out = {}
+        for k in BATCH_KEYS:
+            t = batch[k][lo:hi, :Lq]
+            t = t.to(th.int64) if k == "u" else t.to(th.float32)
+            out[k] = t.contiguous()
+        return out, hi - lo, int(Lq), 0
+
+    def _shard(self, B_glob):
+        if self._dist is None:
+            return 0, B_glob
+        dist, group = self._dist
+        g, r = dist.get_world_size(group), dist.get_rank(group)
+        per = B_glob // g
+        if per * g != B_glob:
+            raise ValueError("data-parallel training needs the batch size to be a multiple of the world size")
+        return r * per, (r + 1) * per
+
+    # ---- the device step -----------------------------------------------------------------------------
+    def _agent_structs(self, flat, prefix="agent."):
+        return agent_param_struct({n: flat.ptr(prefix + n) for n in AGENT_FLAT_ORDER})
+
+    def _launch_forward_backward(self, bt, ws, B, Lq):
+        """Everything between the staged batch and the flat un-normalised gradient."""
+        a = self.args
+        d = self._dims(B, Lq)
+        sp = L.stream_ptr()
+        self._flat.grad_full.zero_()
+        n_launch = 1
+        pe, pt = self._agent_structs(self._flat), self._agent_structs(self._tflat)
+        double_q = bool(a.double_q)
+        n_streams = 3 if double_q else 2
+        arr = (L.UnrollStream * 3)()
+
+        def fill(i, obs, shift, params, h0_from, gates):
+            s = arr[i]
+            s.obs, s.onehot, s.shift_onehot, s.full_input = obs.data_ptr(), bt["u_onehot"].data_ptr(), shift, 0
+            s.h0_from, s.h0, s.params = h0_from, None, params
+            s.q, s.hidden, s.h_last = ws["q"][i].data_ptr(), ws["hidden"][i].data_ptr(), ws["h_last"][i].data_ptr()
+            s.x, s.gi, s.gates = ws["x"][i].data_ptr(), ws["gi"][i].data_ptr(), gates
+
+        fill(0, bt["o"], 1, pe, -1, ws["gates"].data_ptr())          # eval net on o          (q_learner.py:96-97)
+        fill(1, bt["o_next"], 0, pt, -1, None)                        # target net on o_next   (:103-104)
+        if double_q:
+            fill(2, bt["o_next"], 0, pe, 0, None)                     # eval net on o_next, hidden carried (:110)
+        L.call("marl_agent_unroll_fwd", C.byref(d), arr, n_streams, sp)
+        n_launch += 3 * n_streams + 1
+        L.call("marl_q_select", C.byref(d), ws["q"][0].data_ptr(), bt["u"].data_ptr(),
+               ws["q"][2].data_ptr() if double_q else None, ws["q"][1].data_ptr(), bt["avail_u_next"].data_ptr(), None,
+               ws["q_chosen"].data_ptr(), ws["a_star"].data_ptr(), ws["q_tc"].data_ptr(), None, None, sp)
+        n_launch += 1
+        scalars = self._flat.tail.data_ptr()
+        if a.alg == "vdn":
+            L.call("marl_vdn_td_fwd_bwd", C.byref(d), ws["q_chosen"].data_ptr(), ws["q_tc"].data_ptr(), bt["u"].data_ptr(),
+                   bt["r"].data_ptr(), bt["terminated"].data_ptr(), bt["padded"].data_ptr(), float(self.gamma),
+                   ws["q_tot"].data_ptr(), ws["q_tot_t"].data_ptr(), ws["dq"].data_ptr(), scalars, sp)
+            n_launch += 1
+        elif a.alg == "qmix":
+            p = qmix_struct({n: self._flat.ptr("mixer." + n) for n in ("hyper_w1.weight", "hyper_w1.bias",
+                                                                       "hyper_b2.2.weight", "hyper_b2.2.bias")})
+            ptg = qmix_struct({n: self._tflat.ptr("mixer." + n) for n in ("hyper_w1.weight", "hyper_w1.bias",
+                                                                          "hyper_b2.2.weight", "hyper_b2.2.bias")})
+            g = qmix_struct({n: self._flat.ptr("mixer." + n, self._flat.grad) for n in
+                             ("hyper_w1.weight", "hyper_w1.bias", "hyper_b2.2.weight", "hyper_b2.2.bias")}, L.QmixGrads)
+            L.call("marl_qmix_td_fwd_bwd", C.byref(d), C.byref(p), C.byref(ptg), bt["s"].data_ptr(), bt["s_next"].data_ptr(),
+                   ws["q_chosen"].data_ptr(), ws["q_tc"].data_ptr(), bt["u"].data_ptr(), bt["r"].data_ptr(),
+                   bt["terminated"].data_ptr(), bt["padded"].data_ptr(), float(self.gamma), ws["hy"].data_ptr(),
+                   ws["hy_t"].data_ptr(), ws["dhy"].data_ptr(), ws["q_tot"].data_ptr(), ws["q_tot_t"].data_ptr(),
+                   ws["dq"].data_ptr(), C.byref(g), scalars, sp)
+            n_launch += 4
+        else:
+            raise NotImplementedError(a.alg)
+        bw = L.UnrollBwd()
+        bw.obs, bw.onehot, bw.shift_onehot, bw.full_input = bt["o"].data_ptr(), bt["u_onehot"].data_ptr(), 1, 0
+        bw.params = pe
+        bw.hidden, bw.x, bw.gates = ws["hidden"][0].data_ptr(), ws["x"][0].data_ptr(), ws["gates"].data_ptr()
+        bw.h0, bw.dq, bw.dhidden = None, ws["dq"].data_ptr(), None
+        bw.dhext, bw.dgi, bw.dgh, bw.dx = (ws[k].data_ptr() for k in ("dhext", "dgi", "dgh", "dx"))
+        bw.dh0 = None
+        bw.grads = agent_param_struct({n: self._flat.ptr("agent." + n, self._flat.grad) for n in AGENT_FLAT_ORDER},
+                                      L.AgentGrads)
+        L.call("marl_agent_unroll_bwd", C.byref(d), C.byref(bw), sp)
+        n_launch += 7
+        return n_launch
+
+    def _launch_optimizer(self):
+        a, fl, opt, sp = self.args, self._flat, self.optimizer, L.stream_ptr()
+        if opt.kind == "RMS":
+            L.call("marl_clip_rmsprop_step", fl.data.data_ptr(), fl.grad.data_ptr(), opt.square_avg.data_ptr(), fl.numel,
+                   fl.tail.data_ptr(), float(a.grad_norm_clip), float(self.lr), 0.99, 1e-8, self._partials.data_ptr(),
+                   self._loss_out.data_ptr(), sp)
+        else:
+            L.call("marl_clip_adam_step", fl.data.data_ptr(), fl.grad.data_ptr(), opt.exp_avg.data_ptr(),
+                   opt.exp_avg_sq.data_ptr(), fl.numel, fl.tail.data_ptr(), float(a.grad_norm_clip), float(self.lr),
+                   0.9, 0.999, 1e-8, 0, opt.step_counter.data_ptr(), self._partials.data_ptr(),
+                   self._loss_out.data_ptr(), sp)
+        return 2
+
+    def _device_step(self, bt, ws, B, Lq):
+        if self._dist is not None:
+            n = self._launch_forward_backward(bt, ws, B, Lq)
+            dist, group = self._dist
+            dist.all_reduce(self._flat.grad_full, group=group)
+            return n + self._launch_optimizer()
+        return self._launch_forward_backward(bt, ws, B, Lq) + self._launch_optimizer()
+
+    def _run(self, bt, ws, B, Lq):
+        if not self._use_graph:
+            self.launches_per_step = self._device_step(bt, ws, B, Lq)
+            return
+        key = (B, Lq) + tuple(bt[k].data_ptr() for k in BATCH_KEYS)
+        entry = self._graphs.get(key)
+        if entry is None:
+            # first call with this shape runs eagerly (lazy CUDA/NCCL init must not happen in capture)
+            self.launches_per_step = self._device_step(bt, ws, B, Lq)
+            self._graphs[key] = "warm"
+            return
+        if entry == "warm":
+            if self._dist is None:
+                g = th.cuda.CUDAGraph()
+                with th.cuda.graph(g):
+                    self._device_step(bt, ws, B, Lq)
+                entry = (g,)
+            else:
+                g1, g2 = th.cuda.CUDAGraph(), th.cuda.CUDAGraph()
+                with th.cuda.graph(g1):
+                    self._launch_forward_backward(bt, ws, B, Lq)
+                with th.cuda.graph(g2):
+                    self._launch_optimizer()
+                entry = (g1, g2)
+            self._graphs[key] = entry
+        if len(entry) == 1:
+            entry[0].replay()
+        else:
+            dist, group = self._dist
+            entry[0].replay()
+            dist.all_reduce(self._flat.grad_full, group=group)
+            entry[1].replay()
+
+    # ---- reference surface: the train step -------------------------------------------------------------
+    def train(self, batch, train_step, episode_num=None):
+        """One learner step; returns the loss as a Python float (q_learner.py:68-179).
+
+        `batch`: the ReplayBuffer dict (numpy float64, host) or a dict of CUDA tensors in the device
+        layout.  pymarl-style ``train(batch, t_env, episode_num)`` is accepted; the second argument
+        drives the target sync exactly like the reference's ``train_step``."""
+        if self._dev.type != "cuda":
+            raise L.MarlLibraryError("QLearner.train needs a CUDA device: marl_b200 has no CPU path")
+        on_device = th.is_tensor(batch["o"]) and batch["o"].is_cuda
+        if on_device:
+            bt, B, Lq, _ = self._stage_device_batch(batch)
+            ws = self._workspace(B, Lq)
+        else:
+            bt, B, Lq, _ = self._stage_host_batch(batch)
+            ws = self._workspace(B, Lq)
+        self.max_episode_len = Lq
+        self._run(bt, ws, B, Lq)
+        if train_step > 0 and train_step % self.args.target_update_cycle == 0:
+            self._update_targets()
+        self._loss_host.copy_(self._loss_out, non_blocking=True)
+        th.cuda.current_stream().synchronize()
+        # hidden states as the reference leaves them ([B*N, H], q_learner.py:96-110)
+        self.eval_net.hidden_states = ws["h_last"][2 if self.args.double_q else 0]
+        self.target_net.hidden_states = ws["h_last"][1]
+        self.last = dict(B=B, L=Lq, ws=ws, batch=bt, grad_norm=float(self._loss_host[1]))
+        return float(self._loss_host[0])
+
+    def _update_targets(self):
+        self._tflat.data.copy_(self._flat.data)
+
+    # ---- checkpoints -------------------------------------------------------------------------------------
+    def save_models(self, train_step):
+        num = str(train_step // self.args.save_cycle)
+        if not os.path.exists(self.model_dir):
+            os.makedirs(self.model_dir)
+        self.eval_net.save_models(self.model_dir + '/' + num + '_rnn_net_params.pkl')
+        th.save(self.mixer.state_dict(), self.model_dir + '/' + num + '_mixer_net_params.pkl')
+
+    def load_models(self):
+        if os.path.exists(self.model_dir + '/rnn_net_params.pkl'):
+            path_rnn = self.model_dir + '/rnn_net_params.pkl'
+            path_mix = self.model_dir + '/mixer_net_params.pkl'
+            self.eval_net.load_models(path_rnn)
+            self.mixer.load_state_dict(th.load(path_mix, map_location=self._dev))
+            print('Successfully load the model: {} and {}'.format(path_rnn, path_mix))
+        else:
+            raise Exception("No model!")
+
+    # ---- matrix-game tables (q_learner.py:211-262) ----------------------------------------------------------
+    def get_q_and_q_tot_table(self):
+        """3x3 Q_tot table and the two per-agent Q rows at o = s = 1 (matrix game only)."""
+        with th.no_grad():
+            dev = self._dev
+            one = {'o': th.ones(1, 1, 2, 1, device=dev), 's': th.ones(1, 1, 1, device=dev),
+                   'o_next': th.ones(1, 1, 2, 1, device=dev), 'u_onehot': th.zeros(1, 1, 2, 3, device=dev),
+                   'avail_u': th.ones(1, 1, 2, 3, device=dev)}
+            self.eval_net.init_hidden(episode_num=1)
+            q_values, _ = self.eval_net.get_current_q_values(one, max_episode_len=1)     # (1,1,2,3)
+            q_table_i = q_values[0, 0, 0].cpu().numpy()
+            q_table_j = q_values[0, 0, 1].cpu().numpy()
+            q_tot_table = np.zeros((3, 3))
+            for i in range(3):
+                for j in range(3):
+                    chosen = th.stack((q_values[:, :, 0, i], q_values[:, :, 1, j]), dim=2)   # (1,1,2)
+                    if self.args.alg == 'qplex':
+                        v_tot = self.mixer(chosen, one['s'], is_v=True)
+                        max_q = q_values.max(dim=3)[0]
+                        oh = th.zeros_like(q_values)
+                        oh[0, 0, 0, i] = 1
+                        oh[0, 0, 1, j] = 1
+                        a_tot = self.mixer(chosen, one['s'], actions=oh, max_q_i=max_q, is_v=False)
+                        q_tot_table[i, j] = (v_tot + a_tot).item()
+                    else:
+                        q_tot_table[i, j] = self.mixer(chosen, one['s']).item()
+            return q_tot_table, q_table_i, q_table_j
+
+
+def _to_numpy(x):
+    if isinstance(x, np.ndarray):
+        return x
+    if th.is_tensor(x):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+def _episode_struct(bt):
+    e = L.EpisodeF32()
+    for k in L.EPISODE_KEYS:
+        setattr(e, k, bt[k].data_ptr())
+    return e

@@ -1,0 +1,87 @@
+// Shared device helpers for libmarl_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MARL_H 64            // rnn_hidden_dim  (common/arguments.py:88)
+#define MARL_G (3 * MARL_H)  // GRU gate width (r,z,n)
+
+#define MARL_OK 0
+#define MARL_EINVAL (-1)
+
+#define MARL_LAUNCH_CHECK()                                   \
+    do {                                                      \
+        cudaError_t e__ = cudaGetLastError();                 \
+        if (e__ != cudaSuccess) return (int)e__;              \
+    } while (0)
+
+namespace marl {
+
+constexpr int kNumSMs = 148;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ------------------------------------------------------------------------------------------
+// Linear-layer operand description shared by the forward / data-gradient / weight-gradient
+// GEMM kernels.  The logical input row is the K-wide concatenation
+//     [ x (K1 cols) | x2 (K2 cols, optionally shifted by `x2_shift` rows within a period) |
+//       one-hot(m % onehot_mod) (onehot_mod cols) ]
+// which is how the agent input [obs | last_action | agent_id] (share_params.py:84-112) and the
+// QTRAN [hidden | action] / [state | encoding] concatenations are consumed without ever being
+// materialised.
+// ------------------------------------------------------------------------------------------
+struct LinOperand {
+    const float* x;   int ldx;  int K1;
+    const float* x2;  int ldx2; int K2;
+    int x2_shift;     // rows; element (m, K1+k) reads x2[m - shift] and is 0 when (m % x2_period) < shift
+    int x2_period;
+    int onehot_mod;   // 0 = none
+    long long x_bs, x2_bs;   // blockIdx.z strides (batched problems)
+};
+
+__device__ __forceinline__ float lin_load(const LinOperand& a, int z, int m, int k) {
+    if (k < a.K1) return __ldg(a.x + (long long)z * a.x_bs + (long long)m * a.ldx + k);
+    k -= a.K1;
+    if (k < a.K2) {
+        int mm = m;
+        if (a.x2_shift) {
+            if ((m % a.x2_period) < a.x2_shift) return 0.0f;
+            mm = m - a.x2_shift;
+        }
+        return __ldg(a.x2 + (long long)z * a.x2_bs + (long long)mm * a.ldx2 + k);
+    }
+    k -= a.K2;
+    return (m % a.onehot_mod) == k ? 1.0f : 0.0f;
+}
+
+__host__ __device__ __forceinline__ int lin_width(const LinOperand& a) { return a.K1 + a.K2 + a.onehot_mod; }
+
+// 64x64x16 register-tiled FP32 GEMM micro-kernel state (256 threads, 4x4 outputs per thread).
+constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4, GEMM_THREADS = 256;
+
+struct TileSmem {
+    float a[BK][BM + 4];
+    float b[BK][BN + 4];
+};
+
+__device__ __forceinline__ void tile_fma(const TileSmem& s, float (&acc)[TM][TN], int ty, int tx) {
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+        float4 av = *reinterpret_cast<const float4*>(&s.a[k][ty * TM]);
+        float4 bv = *reinterpret_cast<const float4*>(&s.b[k][tx * TN]);
+        float a_[4] = {av.x, av.y, av.z, av.w};
+        float b_[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a_[i], b_[j], acc[i][j]);
+    }
+}
+
+}  // namespace marl

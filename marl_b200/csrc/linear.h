@@ -1,0 +1,51 @@
+// Internal (non-ABI) dense-layer primitives used by the operator files.
+#pragma once
+#include "common.cuh"
+
+namespace marl {
+
+// y[M,N] (+)= act( in[M,K] . w[N,K]^T + bias[N] )        (nn.Linear convention: w is [out, in])
+struct LinearFwd {
+    LinOperand in;
+    const float* w;    int ldw;  long long w_bs;
+    const float* bias;           long long b_bs;   // nullable
+    float* y;          int ldy;  long long y_bs;
+    int M, N;
+    int relu;         // apply max(0, .) in the epilogue
+    int accumulate;   // y += result instead of y = result
+    int batch;        // independent problems over blockIdx.z (operands advance by *_bs)
+};
+
+// dx[M,K] (+)= ( dy[M,N] . w[N, col0:col0+K] ) * (relu_src[M,K] > 0)
+struct LinearDgrad {
+    const float* dy;   int lddy; long long dy_bs;
+    const float* w;    int ldw;  long long w_bs;  int w_col0;
+    float* dx;         int lddx; long long dx_bs;
+    const float* relu_src; int ldrs; long long rs_bs;   // nullable
+    int M, N, K;
+    int accumulate;
+    int batch;
+};
+
+// dw[N, 0:K] += dy[M,N]^T . in[M,K] ;  db[N] += colsum(dy)   (atomic split over M)
+struct LinearWgrad {
+    const float* dy;   int lddy; long long dy_bs;
+    LinOperand in;
+    float* dw;         int ldw;  long long dw_bs;
+    float* db;                   long long db_bs;   // nullable
+    int M, N;
+    int batch;
+};
+
+int linear_fwd(const LinearFwd& a, cudaStream_t st);
+int linear_dgrad(const LinearDgrad& a, cudaStream_t st);
+int linear_wgrad(const LinearWgrad& a, cudaStream_t st);
+
+inline LinOperand plain_operand(const float* x, int ldx, int K, long long bs = 0) {
+    LinOperand o{};
+    o.x = x; o.ldx = ldx; o.K1 = K; o.x_bs = bs;
+    o.x2 = nullptr; o.ldx2 = 0; o.K2 = 0; o.x2_shift = 0; o.x2_period = 1; o.onehot_mod = 0; o.x2_bs = 0;
+    return o;
+}
+
+}  // namespace marl

@@ -1,0 +1,123 @@
+// Global-norm gradient clipping fused with the RMSprop / Adam update over ONE flat parameter
+// buffer.  Replaces th.nn.utils.clip_grad_norm_ + optimizer.step() (algorithm/q_learner.py:172-173),
+// i.e. torch/nn/utils/clip_grad.py and torch/optim/{rmsprop,adam}.py with default hyper-parameters.
+// Two launches, deterministic: (1) per-block partial sums of squares, (2) every block reduces the
+// partials in the same fixed order, then updates its slice.
+#include "common.cuh"
+#include "../../include/marl_b200.h"
+
+namespace marl {
+
+constexpr int kOptBlocks = kNumSMs;
+constexpr int kOptThreads = 256;
+
+__global__ void __launch_bounds__(kOptThreads) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ partials,
+                                                            int* step_counter) {
+    __shared__ float sw[kOptThreads / 32];
+    if (step_counter && blockIdx.x == 0 && threadIdx.x == 0) *step_counter += 1;   // graph-replayable Adam step count
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * kOptThreads + threadIdx.x; i < n; i += (long long)kOptBlocks * kOptThreads) {
+        const float v = g[i];
+        acc = fmaf(v, v, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < kOptThreads / 32; ++w) t += sw[w];
+        partials[blockIdx.x] = t;
+    }
+}
+
+// returns scale = (1/mask_sum) * min(1, max_norm/(total_norm+1e-6)); writes loss/norm from block 0
+__device__ __forceinline__ float clip_scale(const float* partials, const float* scalars, float max_norm, float* loss_out) {
+    __shared__ float s_scale;
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int b = 0; b < kOptBlocks; ++b) t += partials[b];
+        const float inv = 1.0f / scalars[1];
+        const float total_norm = sqrtf(t) * inv;
+        float coef = max_norm / (total_norm + 1e-6f);
+        coef = coef > 1.0f ? 1.0f : coef;              // torch.clamp(clip_coef, max=1.0)
+        s_scale = inv * coef;
+        if (blockIdx.x == 0 && loss_out) { loss_out[0] = scalars[0] * inv; loss_out[1] = total_norm; }
+    }
+    __syncthreads();
+    return s_scale;
+}
+
+__global__ void __launch_bounds__(kOptThreads) clip_rmsprop_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                                   float* __restrict__ sq, long long n,
+                                                                   const float* __restrict__ partials,
+                                                                   const float* __restrict__ scalars, float max_norm,
+                                                                   float lr, float alpha, float eps, float* loss_out) {
+    const float scale = clip_scale(partials, scalars, max_norm, loss_out);
+    for (long long i = (long long)blockIdx.x * kOptThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kOptThreads) {
+        const float gr = g[i] * scale;
+        g[i] = gr;
+        const float v = alpha * sq[i] + (1.0f - alpha) * gr * gr;   // square_avg.mul_(alpha).addcmul_(g, g, 1-alpha)
+        sq[i] = v;
+        p[i] = p[i] - lr * (gr / (sqrtf(v) + eps));                 // p.addcdiv_(g, sqrt(v)+eps, -lr)
+    }
+}
+
+__global__ void __launch_bounds__(kOptThreads) clip_adam_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                                float* __restrict__ m1, float* __restrict__ m2, long long n,
+                                                                const float* __restrict__ partials,
+                                                                const float* __restrict__ scalars, float max_norm,
+                                                                float lr, float beta1, float beta2, float eps, int step,
+                                                                const int* step_counter, float* loss_out) {
+    const float scale = clip_scale(partials, scalars, max_norm, loss_out);
+    // bias corrections in double, as torch does with python floats (torch/optim/adam.py)
+    const int stp = step_counter ? *step_counter : step;
+    const float step_size = (float)((double)lr / (1.0 - pow((double)beta1, (double)stp)));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)stp));
+    for (long long i = (long long)blockIdx.x * kOptThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kOptThreads) {
+        const float gr = g[i] * scale;
+        g[i] = gr;
+        const float a = m1[i] + (1.0f - beta1) * (gr - m1[i]);      // exp_avg.lerp_(grad, 1-beta1)
+        const float b = beta2 * m2[i] + (1.0f - beta2) * gr * gr;   // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
+        m1[i] = a; m2[i] = b;
+        const float denom = sqrtf(b) / bc2_sqrt + eps;
+        p[i] = p[i] - step_size * (a / denom);
+    }
+}
+
+}  // namespace marl
+
+using namespace marl;
+
+extern "C" int marl_optim_partials(void) { return kOptBlocks; }
+
+static int opt_grid(long long n) {
+    long long b = (n + kOptThreads - 1) / kOptThreads;
+    return (int)(b < 1 ? 1 : (b > kOptBlocks ? kOptBlocks : b));
+}
+
+extern "C" int marl_clip_rmsprop_step(float* params, float* grads, float* square_avg, long long n, const float* scalars,
+                                      float max_norm, float lr, float alpha, float eps, float* partials, float* loss_out,
+                                      void* stream) {
+    if (!params || !grads || !square_avg || n <= 0 || !scalars || !partials) return MARL_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    sumsq_kernel<<<kOptBlocks, kOptThreads, 0, st>>>(grads, n, partials, nullptr);
+    MARL_LAUNCH_CHECK();
+    clip_rmsprop_kernel<<<opt_grid(n), kOptThreads, 0, st>>>(params, grads, square_avg, n, partials, scalars, max_norm, lr,
+                                                             alpha, eps, loss_out);
+    MARL_LAUNCH_CHECK();
+    return MARL_OK;
+}
+
+extern "C" int marl_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                                   const float* scalars, float max_norm, float lr, float beta1, float beta2, float eps,
+                                   int step, int* step_counter, float* partials, float* loss_out, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || !scalars || !partials) return MARL_EINVAL;
+    if (!step_counter && step < 1) return MARL_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    sumsq_kernel<<<kOptBlocks, kOptThreads, 0, st>>>(grads, n, partials, step_counter);
+    MARL_LAUNCH_CHECK();
+    clip_adam_kernel<<<opt_grid(n), kOptThreads, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, partials, scalars,
+                                                          max_norm, lr, beta1, beta2, eps, step, step_counter, loss_out);
+    MARL_LAUNCH_CHECK();
+    return MARL_OK;
+}

@@ -1,0 +1,187 @@
+// Action-value selection (gather / masked argmax / target gather), TD loss, VDN, batch ingest.
+#include "common.cuh"
+#include "../../include/marl_b200.h"
+
+namespace marl {
+
+constexpr float kNegBig = -9999999.0f;   // algorithm/q_learner.py:105,112,126
+
+__global__ void __launch_bounds__(256) q_select_kernel(
+    int rows, int A, const float* __restrict__ q_evals, const long long* __restrict__ u,
+    const float* __restrict__ q_evals_next, float* __restrict__ q_targets,
+    const float* __restrict__ avail_next, const float* __restrict__ avail,
+    float* __restrict__ q_chosen, long long* __restrict__ a_star, float* __restrict__ q_tc,
+    float* __restrict__ max_q_evals, float* __restrict__ q_targets_max) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const long long o = (long long)i * A;
+    if (q_chosen) q_chosen[i] = q_evals[o + u[i]];                     // q_learner.py:100
+    int best = 0;
+    float tmax = 0.f, tsel = 0.f;
+    if (q_evals_next) {                                                // double-Q, q_learner.py:110-114
+        float bv = 0.f;
+        for (int a = 0; a < A; ++a) {
+            float v = (avail_next[o + a] == 0.0f) ? kNegBig : q_evals_next[o + a];
+            if (a == 0 || v > bv) { bv = v; best = a; }                // first maximum wins (th.argmax on CPU)
+        }
+    }
+    for (int a = 0; a < A; ++a) {
+        float v = q_targets[o + a];
+        if (avail_next[o + a] == 0.0f) { v = kNegBig; q_targets[o + a] = v; }   // in place, q_learner.py:105
+        if (a == 0 || v > tmax) tmax = v;
+        if (a == best) tsel = v;
+    }
+    q_tc[i] = q_evals_next ? tsel : tmax;                              // q_learner.py:114 / :117
+    if (a_star) a_star[i] = q_evals_next ? best : -1;
+    if (q_targets_max) q_targets_max[i] = tmax;                        // q_learner.py:150
+    if (max_q_evals) {                                                 // q_learner.py:125-127
+        float m = 0.f;
+        for (int a = 0; a < A; ++a) {
+            float v = (avail[o + a] == 0.0f) ? kNegBig : q_evals[o + a];
+            if (a == 0 || v > m) m = v;
+        }
+        max_q_evals[i] = m;
+    }
+}
+
+// Block-wide sum of two values; thread 0 of the block adds them to out[0], out[1].
+__device__ __forceinline__ void block_accumulate2(float a, float b, float* out) {
+    __shared__ float sa[32], sb[32];
+    a = warp_sum(a); b = warp_sum(b);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    if (l == 0) { sa[w] = a; sb[w] = b; }
+    __syncthreads();
+    if (w == 0) {
+        a = l < nw ? sa[l] : 0.f; b = l < nw ? sb[l] : 0.f;
+        a = warp_sum(a); b = warp_sum(b);
+        if (l == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); }
+    }
+}
+
+__device__ __forceinline__ float td_grad(float q_tot, float q_tot_t, float r, float term, float padded, float gamma,
+                                         float& sq, float& msk) {
+    const float mask = 1.0f - padded;                                  // q_learner.py:83
+    const float y = r + gamma * q_tot_t * (1.0f - term);               // :165
+    const float d = mask * (y - q_tot);                                // :166-167
+    sq = d * d; msk = mask;
+    return -2.0f * mask * d;                                           // d(sum d^2)/d q_tot
+}
+
+__global__ void __launch_bounds__(256) td_loss_kernel(int M, const float* q_tot, const float* q_tot_t, const float* r,
+                                                      const float* term, const float* padded, float gamma,
+                                                      float* dq_tot, float* scalars) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    float sq = 0.f, msk = 0.f;
+    if (m < M) {
+        float g = td_grad(q_tot[m], q_tot_t[m], r[m], term[m], padded[m], gamma, sq, msk);
+        if (dq_tot) dq_tot[m] = g;
+    }
+    block_accumulate2(sq, msk, scalars);
+}
+
+__global__ void __launch_bounds__(256) vdn_td_kernel(int M, int N, int A, const float* q_chosen, const float* q_tc,
+                                                     const long long* u, const float* r, const float* term,
+                                                     const float* padded, float gamma, float* q_tot, float* q_tot_t,
+                                                     float* dq, float* scalars) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    float sq = 0.f, msk = 0.f;
+    if (m < M) {
+        float a = 0.f, b = 0.f;
+        for (int n = 0; n < N; ++n) { a += q_chosen[m * N + n]; b += q_tc[m * N + n]; }   // mixer.py:16
+        q_tot[m] = a; q_tot_t[m] = b;
+        const float g = td_grad(a, b, r[m], term[m], padded[m], gamma, sq, msk);
+        if (dq)
+            for (int n = 0; n < N; ++n) {
+                const long long o = ((long long)m * N + n) * A;
+                const int ua = (int)u[m * N + n];
+                for (int c = 0; c < A; ++c) dq[o + c] = (c == ua) ? g : 0.0f;
+            }
+    }
+    block_accumulate2(sq, msk, scalars);
+}
+
+struct IngestKey { const void* src; void* dst; int inner; int kind; };   // kind 0: f64->f32, 1: f64->i64, 2: i64->i64
+struct IngestArgs { IngestKey k[11]; int B, L, T_src; };
+
+__global__ void __launch_bounds__(256) ingest_kernel(IngestArgs a) {
+    const IngestKey key = a.k[blockIdx.y];
+    const long long per_b = (long long)a.L * key.inner, total = (long long)a.B * per_b;
+    const long long src_b = (long long)a.T_src * key.inner;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / per_b, rem = i - b * per_b, si = b * src_b + rem;
+        if (key.kind == 0) ((float*)key.dst)[i] = (float)((const double*)key.src)[si];
+        else if (key.kind == 1) ((long long*)key.dst)[i] = (long long)((const double*)key.src)[si];   // trunc toward zero
+        else ((long long*)key.dst)[i] = ((const long long*)key.src)[si];
+    }
+}
+
+}  // namespace marl
+
+using namespace marl;
+
+extern "C" int marl_q_select(const marl_dims* d, const float* q_evals, const long long* u, const float* q_evals_next,
+                             float* q_targets, const float* avail_u_next, const float* avail_u, float* q_chosen,
+                             long long* a_star, float* q_targets_chosen, float* max_q_evals, float* q_targets_max,
+                             void* stream) {
+    if (!d || !q_targets || !avail_u_next || !q_targets_chosen) return MARL_EINVAL;
+    if (q_chosen && (!q_evals || !u)) return MARL_EINVAL;
+    if (max_q_evals && (!avail_u || !q_evals)) return MARL_EINVAL;
+    const int rows = d->B * d->L * d->N;
+    if (rows <= 0) return MARL_OK;
+    q_select_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, d->A, q_evals, u, q_evals_next, q_targets,
+        avail_u_next, avail_u, q_chosen, a_star, q_targets_chosen, max_q_evals, q_targets_max);
+    MARL_LAUNCH_CHECK();
+    return MARL_OK;
+}
+
+extern "C" int marl_td_loss(int M, const float* q_tot, const float* q_tot_target, const float* r, const float* terminated,
+                            const float* padded, float gamma, float* dq_tot, float* scalars, void* stream) {
+    if (M < 0 || !q_tot || !q_tot_target || !r || !terminated || !padded || !scalars) return MARL_EINVAL;
+    if (M == 0) return MARL_OK;
+    td_loss_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(M, q_tot, q_tot_target, r, terminated, padded, gamma,
+                                                                     dq_tot, scalars);
+    MARL_LAUNCH_CHECK();
+    return MARL_OK;
+}
+
+extern "C" int marl_vdn_td_fwd_bwd(const marl_dims* d, const float* q_chosen, const float* q_targets_chosen,
+                                   const long long* u, const float* r, const float* terminated, const float* padded,
+                                   float gamma, float* q_tot, float* q_tot_target, float* dq, float* scalars, void* stream) {
+    if (!d || !q_chosen || !q_targets_chosen || !r || !terminated || !padded || !q_tot || !q_tot_target || !scalars)
+        return MARL_EINVAL;
+    if (dq && !u) return MARL_EINVAL;
+    const int M = d->B * d->L;
+    if (M <= 0) return MARL_OK;
+    vdn_td_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(M, d->N, d->A, q_chosen, q_targets_chosen, u, r,
+        terminated, padded, gamma, q_tot, q_tot_target, dq, scalars);
+    MARL_LAUNCH_CHECK();
+    return MARL_OK;
+}
+
+extern "C" int marl_ingest_f64(const marl_episode_f64* s, int T_src, const marl_dims* d, const marl_episode_f32* o,
+                               void* stream) {
+    if (!s || !d || !o || T_src < d->L || d->B <= 0 || d->L <= 0) return MARL_EINVAL;
+    IngestArgs a{};
+    a.B = d->B; a.L = d->L; a.T_src = T_src;
+    const int NO = d->N * d->O, NA = d->N * d->A;
+    a.k[0] = {s->o, o->o, NO, 0};
+    a.k[1] = {s->u, o->u, d->N, s->u_is_int64 ? 2 : 1};
+    a.k[2] = {s->s, o->s, d->S, 0};
+    a.k[3] = {s->r, o->r, 1, 0};
+    a.k[4] = {s->o_next, o->o_next, NO, 0};
+    a.k[5] = {s->s_next, o->s_next, d->S, 0};
+    a.k[6] = {s->avail_u, o->avail_u, NA, 0};
+    a.k[7] = {s->avail_u_next, o->avail_u_next, NA, 0};
+    a.k[8] = {s->u_onehot, o->u_onehot, NA, 0};
+    a.k[9] = {s->padded, o->padded, 1, 0};
+    a.k[10] = {s->terminated, o->terminated, 1, 0};
+    for (int i = 0; i < 11; ++i)
+        if (!a.k[i].src || !a.k[i].dst) return MARL_EINVAL;
+    long long biggest = (long long)d->B * d->L * (NO > NA ? NO : NA);
+    int bx = (int)((biggest + 1023) / 1024);
+    if (bx < 1) bx = 1;
+    if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;
+    ingest_kernel<<<dim3(bx, 11), 256, 0, (cudaStream_t)stream>>>(a);
+    MARL_LAUNCH_CHECK();
+    return MARL_OK;
+}

@@ -1,0 +1,61 @@
+"""Flat fp32 parameter / gradient storage with nn.Parameter views.
+
+All trainable tensors of a learner live in ONE contiguous device buffer so that the clip +
+optimiser kernels, the target sync (one D2D copy) and the data-parallel all-reduce (one NCCL
+call over [grads | loss_sum | mask_sum]) touch a single allocation.  The nn.Parameters of the
+modules are re-pointed to views of that buffer, so ``state_dict()`` keeps the reference's key
+names (fc1.weight, rnn.weight_ih, hyper_w1.weight, ...) and its checkpoints load unchanged.
+"""
+from __future__ import annotations
+
+import torch
+
+ALIGN = 4   # floats; every tensor starts 16-byte aligned (float4 loads in the kernels)
+
+
+def _round_up(n, a=ALIGN):
+    return (n + a - 1) // a * a
+
+
+class FlatBuffer:
+    """Packs ``[(name, parameter)]`` into one buffer, in the given order."""
+
+    def __init__(self, named_params, device=None, with_grad=True, extra_tail=0):
+        named_params = list(named_params)
+        self.names = [n for n, _ in named_params]
+        self.params = [p for _, p in named_params]
+        device = device if device is not None else (self.params[0].device if self.params else torch.device("cpu"))
+        self.offsets, off = {}, 0
+        for n, p in named_params:
+            self.offsets[n] = off
+            off += _round_up(p.numel())
+        self.numel = off
+        self.data = torch.zeros(off, dtype=torch.float32, device=device)
+        # gradient buffer carries `extra_tail` trailing floats (loss_sum, mask_sum) for the all-reduce
+        self.grad_full = torch.zeros(off + extra_tail, dtype=torch.float32, device=device) if with_grad else None
+        self.grad = self.grad_full[:off] if with_grad else None
+        self.tail = self.grad_full[off:] if with_grad else None
+        with torch.no_grad():
+            for n, p in named_params:
+                o = self.offsets[n]
+                view = self.data[o:o + p.numel()].view(p.shape)
+                view.copy_(p.detach().to(device=device, dtype=torch.float32))
+                p.data = view
+                if with_grad:
+                    p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def view(self, name, source=None):
+        src = self.data if source is None else source
+        i = self.names.index(name)
+        o = self.offsets[name]
+        return src[o:o + self.params[i].numel()].view(self.params[i].shape)
+
+    def ptr(self, name, source=None):
+        src = self.data if source is None else source
+        return src.data_ptr() + 4 * self.offsets[name]
+
+    def rebind_grads(self):
+        """Re-attach p.grad views (optimizer.zero_grad(set_to_none=True) style resets drop them)."""
+        for n, p in zip(self.names, self.params):
+            o = self.offsets[n]
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)

@@ -315,7 +315,7 @@ def q_learner_forward(st, batch_np):
             a_star = torch.argmax(q_en, dim=3, keepdim=True)
             q_tc = torch.gather(q_targets, 3, a_star).squeeze(3)
         else:
-            a_star = None
+            a_star, q_en = None, None
             q_tc = q_targets.max(dim=3)[0]
     if cfg.alg == "qplex":
         v_tot = qplex_mix(P["mixer"], q_chosen, b["s"], cfg, is_v=True)
@@ -346,7 +346,7 @@ def q_learner_forward(st, batch_np):
     loss = ((mask * td) ** 2).sum() / mask.sum()
     return dict(loss=loss, L=L, q_evals=q_evals, hidden_evals=hid_evals, q_targets=q_targets,
                 a_star=a_star, q_chosen=q_chosen, q_targets_chosen=q_tc, q_tot=q_tot,
-                q_tot_target=q_tot_t, h_last=h_last)
+                q_tot_target=q_tot_t, h_last=h_last, q_evals_next=q_en)
 
 
 def qtran_forward(st, batch_np):

@@ -1,0 +1,98 @@
+"""Shared helpers for the GPU parity tests: build the CUDA learner and the CPU oracle on the same
+weights / batch and compare named tensors."""
+import copy
+
+import numpy as np
+import torch
+
+from marl_b200.common.arguments import default_args
+from oracle import marl_oracle as MO
+
+
+def rel_err(x, y):
+    x = np.asarray(x.detach().cpu() if torch.is_tensor(x) else x, dtype=np.float64)
+    y = np.asarray(y.detach().cpu() if torch.is_tensor(y) else y, dtype=np.float64)
+    if x.size == 0:
+        return 0.0
+    return float(np.max(np.abs(x - y)) / max(float(np.max(np.abs(y))), 1e-30))
+
+
+def make_args(alg, N, A, O, S, T, **kw):
+    a = default_args(alg=alg, n_agents=N, n_actions=A, obs_shape=O, state_shape=S, episode_limit=T,
+                     map="synthetic", model_dir="/tmp/marl_b200_model")
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def oracle_cfg(args):
+    return MO.make_cfg(**{k: getattr(args, k) for k in (
+        "alg", "optimizer", "n_agents", "n_actions", "obs_shape", "state_shape", "episode_limit", "double_q", "lr",
+        "target_update_cycle", "num_kernel", "adv_hypernet_embed", "hypernet_embed", "qtran_hidden_dim", "gamma",
+        "grad_norm_clip", "lambda_opt", "lambda_nopt", "weighted_head", "is_minus_one", "rnn_hidden_dim",
+        "qmix_hidden_dim")})
+
+
+def build_pair(args, params=None, seed=0, dtype=torch.float32):
+    """Returns (cuda learner, oracle LearnerState) holding identical weights."""
+    from marl_b200.controller.share_params import SharedMAC
+    from marl_b200.algorithm.q_learner import QLearner
+    torch.manual_seed(seed)
+    mac = SharedMAC(args)
+    if args.alg == "qtran_base":
+        from marl_b200.algorithm.qtran_learner import QTRANLearner
+        learner = QTRANLearner(mac, args)
+    else:
+        learner = QLearner(mac, args)
+    if params is not None:
+        load_params(learner, params)
+    st = MO.LearnerState(oracle_cfg(args), export_params(learner), dtype=dtype)
+    return learner, st
+
+
+def module_groups(learner):
+    g = {"agent": learner.eval_net.agent, "mixer": learner.mixer}
+    if hasattr(learner, "v"):
+        g["v"] = learner.v
+        g["q_sum_mixer"] = learner.q_sum_mixer
+    return g
+
+
+def export_params(learner):
+    return {g: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()} for g, m in module_groups(learner).items()}
+
+
+def load_params(learner, params):
+    """params: {group: state_dict}. Loads eval nets and mirrors them into the targets (fresh learner)."""
+    groups = module_groups(learner)
+    for g, sd in params.items():
+        if g in groups and len(sd):
+            groups[g].load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    learner._update_targets()
+
+
+def compare_named(mine, theirs, tol, what, report):
+    worst = 0.0
+    for k, v in theirs.items():
+        if v is None:
+            continue
+        e = rel_err(mine[k], v)
+        worst = max(worst, e)
+        if e > tol:
+            report.append(f"{what}[{k}] rel err {e:.3e} > {tol:g}")
+    return worst
+
+
+def argmax_mismatches(a_star_mine, q_masked_oracle, a_star_oracle, noise=1e-5):
+    """Index mismatches whose oracle top-2 gap exceeds fp32 noise."""
+    mine = np.asarray(a_star_mine.cpu()).reshape(-1)
+    ref = np.asarray(a_star_oracle).reshape(-1)
+    q = np.asarray(q_masked_oracle, dtype=np.float64).reshape(len(ref), -1)
+    bad = np.nonzero(mine != ref)[0]
+    hard = 0
+    for i in bad:
+        gap = abs(q[i, ref[i]] - q[i, mine[i]])
+        scale = max(1.0, abs(q[i, ref[i]]))
+        if gap > noise * scale:
+            hard += 1
+    return len(bad), hard

@@ -1,0 +1,253 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+from marl_b200.synthetic import synthetic_batch
+from oracle import marl_oracle as MO
+from oracle import matrix_game as MG
+from tests import golden_util as GU
+from tests import parity_util as PU
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5            # north_star: loss, Q_tot, gradients within 1e-5 relative (fp32)
+TOL_MULTI = 5e-5      # after several optimiser steps fp32 noise compounds (both sides vs fp64 differ by this much)
+
+PAYOFF1 = [[8, -12, -12], [-12, 0, 0], [-12, 0, 0]]
+
+
+# ------------------------------------------------------------------------------------------ env
+@pytest.mark.parametrize("n_envs", [1, 3, 9, 4096, 100003])
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
+def test_matrix_game_step_bit_exact(n_envs, dtype):
+    from marl_b200.env.single_state_matrix_game import BatchedMatrixGame
+    rng = np.random.RandomState(n_envs)
+    acts = rng.randint(0, 3, size=(n_envs, 2))
+    for obs_value in (0.0, 1.0):
+        env = BatchedMatrixGame(PAYOFF1, n_envs, obs_value=obs_value, keep_r64=True, validate=True)
+        out = env.step(torch.as_tensor(acts, dtype=dtype, device="cuda"))
+        ref = MG.step(PAYOFF1, acts, obs_value)
+        for k in BatchedMatrixGame.KEYS:
+            assert np.array_equal(out[k].cpu().numpy(), ref[k]), k
+        assert np.array_equal(env.r64.cpu().numpy(), ref["r64"])
+
+
+def test_matrix_game_reproduces_get_episodes_golden():
+    from marl_b200.env.single_state_matrix_game import BatchedMatrixGame
+    z = np.load(GU.GOLDEN_DIR + "/matrix_game_env.npz")
+    acts = np.array([[i, j] for i in range(3) for j in range(3)])
+    for t in range(3):
+        env = BatchedMatrixGame(z[f"t{t}/payoff"], 9, obs_value=1.0, keep_r64=True)
+        out = env.step(torch.as_tensor(acts, device="cuda"))
+        for k in BatchedMatrixGame.KEYS:
+            assert np.array_equal(out[k].cpu().numpy().astype(np.float64), z[f"t{t}/episodes/{k}"].astype(np.float64)), k
+        assert np.array_equal(env.r64.cpu().numpy().reshape(3, 3), z[f"t{t}/step_reward"])
+
+
+def test_matrix_game_rejects_bad_action():
+    from marl_b200.env.single_state_matrix_game import BatchedMatrixGame
+    env = BatchedMatrixGame(PAYOFF1, 8, validate=True)
+    a = torch.zeros(8, 2, dtype=torch.int64, device="cuda")
+    a[5, 1] = 3
+    with pytest.raises(IndexError):
+        env.step(a)
+
+
+# ------------------------------------------------------------------------------------------ agent
+def _agent_pair(N, A, O, S, T, seed=0):
+    args = PU.make_args("vdn", N, A, O, S, T)
+    learner, st = PU.build_pair(args, seed=seed)
+    return args, learner, st
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 2, 3, 4, 5), (4, 7, 5, 11, 80, 120), (33, 3, 2, 3, 1, 1)])
+def test_unroll_forward_and_carry(shape):
+    B, T, N, A, O, S = shape
+    args, learner, st = _agent_pair(N, A, O, S, T)
+    batch = synthetic_batch(1, B, T, N, A, O, S)
+    mac = learner.eval_net
+    mac.init_hidden(B)
+    with torch.no_grad():
+        q, hid = mac.get_current_q_values(batch, T)
+        q2, hid2 = mac.get_next_q_values(batch, T)       # no init_hidden: hidden carried (share_params.py:135,158)
+    b = MO.to_tensors(batch, T, torch.float32)
+    p = st.params["agent"]
+    h0 = torch.zeros(B * N, 64)
+    with torch.no_grad():
+        oq, oh, hl = MO.unroll(p, b["o"], MO.shift_onehot(b["u_onehot"]), h0, st.cfg)
+        oq2, oh2, hl2 = MO.unroll(p, b["o_next"], b["u_onehot"], hl, st.cfg)
+    assert PU.rel_err(q, oq) < TOL and PU.rel_err(hid, oh) < TOL
+    assert PU.rel_err(q2, oq2) < TOL and PU.rel_err(hid2, oh2) < TOL
+    assert tuple(mac.hidden_states.shape) == (B * N, 64)
+    assert PU.rel_err(mac.hidden_states, hl2) < TOL
+
+
+def test_single_step_module_forward_and_autograd():
+    """RNNQNet.forward(obs, hidden) one step, looped like the reference's controller, under autograd."""
+    args, learner, st = _agent_pair(2, 3, 4, 5, 4)
+    agent = learner.eval_net.agent
+    torch.manual_seed(3)
+    R, I, T = 6, 4 + 3 + 2, 4
+    xs = torch.randn(T, R, I)
+    h = torch.zeros(R, 64, device="cuda")
+    tot = 0
+    for t in range(T):
+        q, h = agent(xs[t].cuda(), h)
+        tot = tot + (q * q).sum() + h.sum()
+    grads = torch.autograd.grad(tot, list(agent.parameters()))
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in st.params["agent"].items()}
+    ho = torch.zeros(R, 64)
+    tot_o = 0
+    for t in range(T):
+        qo, ho = MO.agent_step(p, xs[t], ho)
+        tot_o = tot_o + (qo * qo).sum() + ho.sum()
+    go = torch.autograd.grad(tot_o, [p[k] for k, _ in agent.named_parameters()])
+    assert abs(float(tot) - float(tot_o)) / abs(float(tot_o)) < TOL
+    for (k, _), a, b in zip(agent.named_parameters(), grads, go):
+        assert PU.rel_err(a, b) < 2e-5, k
+
+
+# ------------------------------------------------------------------------------------------ mixer
+def test_qmix_module_forward_backward():
+    from marl_b200.network.mixer import QMixMixer
+    args = PU.make_args("qmix", 5, 11, 80, 120, 10)
+    torch.manual_seed(0)
+    mixer = QMixMixer(args)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in mixer.state_dict().items()}
+    q = torch.randn(6, 10, 5)
+    s = torch.randn(6, 10, 120)
+    qc = q.cuda().requires_grad_(True)
+    out = mixer(qc, s.cuda())
+    w = torch.randn(6, 10, 1)
+    (out * w.cuda()).sum().backward()
+    qo = q.clone().requires_grad_(True)
+    oo = MO.qmix_mix(sd, qo, s, PU.oracle_cfg(args))
+    (oo * w).sum().backward()
+    assert out.shape == (6, 10, 1)
+    assert PU.rel_err(out, oo) < TOL
+    assert PU.rel_err(qc.grad, qo.grad) < TOL
+    for k, p in mixer.named_parameters():
+        assert PU.rel_err(p.grad, sd[k].grad) < TOL, k
+
+
+# ------------------------------------------------------------------------------------------ learner vs goldens
+@pytest.mark.parametrize("name", [n for n in GU.learner_cases() if "qplex" not in n and "qtran" not in n])
+def test_learner_reproduces_reference_goldens(name):
+    z = GU.load(name)
+    cfg = GU.cfg_from(z)
+    args = PU.make_args(cfg.alg, cfg.n_agents, cfg.n_actions, cfg.obs_shape, cfg.state_shape, cfg.episode_limit,
+                        optimizer=cfg.optimizer, double_q=cfg.double_q, lr=cfg.lr, target_update_cycle=cfg.target_update_cycle)
+    learner, _ = PU.build_pair(args, GU.init_params(z))
+    batch = GU.batch_of(z)
+    losses = []
+    for step in range(int(z["meta/n_steps"])):
+        losses.append(learner.train({k: v.copy() for k, v in batch.items()}, step))
+        if step == 0:
+            ws = learner.last["ws"]
+            assert learner.last["L"] == int(z["step0/L"])
+            assert PU.rel_err(ws["q"][0], z["step0/q_evals"]) < TOL
+            assert PU.rel_err(ws["hidden"][0], z["step0/hidden_evals"]) < TOL
+            assert PU.rel_err(ws["q"][1], z["step0/q_targets"]) < TOL
+            if "step0/cur_max_actions" in z:
+                n_bad, hard = PU.argmax_mismatches(ws["a_star"], z["step0/q_evals_next"], z["step0/cur_max_actions"])
+                assert hard == 0, (n_bad, hard)
+            if "step0/q_tot" in z:
+                assert PU.rel_err(ws["q_tot"], z["step0/q_tot"]) < TOL
+            for g, m in PU.module_groups(learner).items():
+                for k, p in m.named_parameters():
+                    assert PU.rel_err(p.grad, z[f"clipped_grad/{g}/{k}"]) < 2e-5, (g, k)
+    assert np.allclose(losses, z["loss"], rtol=TOL_MULTI, atol=0), (losses, z["loss"])
+    for g, m in PU.module_groups(learner).items():
+        for k, v in m.state_dict().items():
+            assert PU.rel_err(v, z[f"final/{g}/{k}"]) < TOL_MULTI, (g, k)
+    for k, v in learner.target_net.agent.state_dict().items():
+        assert PU.rel_err(v, z[f"final_target/agent/{k}"]) < TOL_MULTI, k
+
+
+def test_matrix_game_q_table_golden():
+    z = GU.load("matrix_qmix_rms")
+    cfg = GU.cfg_from(z)
+    args = PU.make_args("qmix", 2, 3, 1, 1, 1, lr=cfg.lr)
+    learner, _ = PU.build_pair(args, GU.init_params(z))
+    batch = GU.batch_of(z)
+    for step in range(int(z["meta/n_steps"])):
+        learner.train({k: v.copy() for k, v in batch.items()}, step)
+    qt, qi, qj = learner.get_q_and_q_tot_table()
+    assert PU.rel_err(qt, z["table/q_tot"]) < TOL_MULTI
+    assert PU.rel_err(qi, z["table/q_i"]) < TOL_MULTI and PU.rel_err(qj, z["table/q_j"]) < TOL_MULTI
+
+
+# ------------------------------------------------------------------------------------------ learner vs oracle, BASELINE shapes
+def _train_compare(args, batch, steps, graph):
+    args.cuda_graph = graph
+    learner, st = PU.build_pair(args)
+    report = []
+    for step in range(steps):
+        loss = learner.train({k: v.copy() for k, v in batch.items()}, step)
+        oloss, info = MO.train_step(st, batch, step)
+        tol = TOL if step == 0 else TOL_MULTI
+        if abs(loss - oloss) > tol * abs(oloss):
+            report.append(f"step {step}: loss {loss} vs {oloss}")
+        ws = learner.last["ws"]
+        if step == 0:
+            for mine, key in ((ws["q"][0], "q_evals"), (ws["hidden"][0], "hidden_evals"), (ws["q"][1], "q_targets"),
+                              (ws["q_tot"], "q_tot"), (ws["q_tot_t"], "q_tot_target")):
+                e = PU.rel_err(mine.reshape(-1), info[key].reshape(-1))
+                if e > TOL:
+                    report.append(f"{key} rel err {e:.3e}")
+            if info["a_star"] is not None:
+                n_bad, hard = PU.argmax_mismatches(ws["a_star"], info["q_evals_next"], info["a_star"].squeeze(3))
+                if hard:
+                    report.append(f"argmax: {n_bad} mismatches, {hard} beyond fp32 noise")
+            mine = {f"{g}.{k}": p.grad for g, m in PU.module_groups(learner).items() for k, p in m.named_parameters()}
+            PU.compare_named(mine, info["clipped_grads"], 2e-5, "grad", report)
+        mine = {f"{g}.{k}": p for g, m in PU.module_groups(learner).items() for k, p in m.named_parameters()}
+        theirs = {f"{g}.{k}": p for g, k, p in st.flat_params()}
+        PU.compare_named(mine, theirs, tol, f"param@{step}", report)
+    assert not report, "\n".join(report)
+
+
+@pytest.mark.parametrize("alg", ["vdn", "qmix"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_learner_2s3z_shape_vs_oracle(alg, graph):
+    args = PU.make_args(alg, 5, 11, 80, 120, 120)
+    batch = synthetic_batch(0, 32, 120, 5, 11, 80, 120)
+    _train_compare(args, batch, 3, graph)
+
+
+@pytest.mark.parametrize("opt", ["RMS", "Adam"])
+def test_learner_matrix_game_4096_vs_oracle(opt):
+    args = PU.make_args("qmix", 2, 3, 1, 1, 1, optimizer=opt)
+    rng = np.random.RandomState(0)
+    from marl_b200.env.single_state_matrix_game import TwoAgentsMatrixGame
+    ep = TwoAgentsMatrixGame(PAYOFF1).get_episodes()
+    idx = rng.randint(0, 9, size=4096)
+    batch = {k: v[idx] for k, v in ep.items()}
+    _train_compare(args, batch, 3, True)
+
+
+def test_device_resident_batch_matches_host_batch():
+    args = PU.make_args("qmix", 3, 4, 5, 6, 8)
+    batch = synthetic_batch(2, 6, 8, 3, 4, 5, 6, full_length_first=False, min_len=2)
+    la, _ = PU.build_pair(args)
+    lb, _ = PU.build_pair(args)
+    dev = {k: torch.as_tensor(v, device="cuda") for k, v in batch.items()}
+    dev = {k: (v.to(torch.int64) if k == "u" else v.to(torch.float32)) for k, v in dev.items()}
+    for step in range(3):
+        a = la.train({k: v.copy() for k, v in batch.items()}, step)
+        b = lb.train(dev, step)
+        assert a == b
+
+
+def test_target_sync_cadence():
+    args = PU.make_args("vdn", 2, 3, 4, 5, 3, target_update_cycle=2)
+    learner, _ = PU.build_pair(args)
+    batch = synthetic_batch(0, 4, 3, 2, 3, 4, 5)
+    t0 = learner._tflat.data.clone()
+    learner.train(batch, 0)
+    assert torch.equal(learner._tflat.data, t0)            # never at step 0 (q_learner.py:176)
+    learner.train(batch, 1)
+    assert torch.equal(learner._tflat.data, t0)
+    learner.train(batch, 2)
+    assert torch.equal(learner._tflat.data, learner._flat.data)
