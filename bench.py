@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- QMIX learner episode-samples/s (2s3z shape) + matrix-game env-steps/s on B200.
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched under torch.distributed.run)
+    python bench.py --impl reference ...                   (the CPU path of the reference algorithm)
+
+One JSON line on stdout (rank 0).  A "step" is one ``QLearner.train()`` on one synthetic 2s3z-shaped
+episode batch (BASELINE.json configs[1]: 5 agents, 11 actions, T=120, batch 32 per GPU).
+  value : whole-job episode-samples/s with the batches already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same through the reference-facing call with pinned float64 HOST batches in the ReplayBuffer
+          layout -- H2D copy, f64->f32 ingest and the loss read-back inside the timed region
+  env   : matrix-game env-steps/s of the batched environment kernel (4096 envs and 2^24 envs)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPE = dict(B=32, T=120, N=5, A=11, O=80, S=120)        # BASELINE.json configs[1]
+FLOP_PER_STEP = 6.98e9                                   # SURVEY.md section 8(d), cfg 2 QMIX, B=32
+BYTES_PER_STEP = 18.71e6                                 # each batch element read once as fp32 (u int64)
+GRU_FWD_FLOP = 3 * 32 * 120 * 5 * 2 * (3 * 64 * 64)      # 3 unrolls x rows x (W_hh h): the sequential kernel
+ENV_BYTES = 140                                          # 16 B actions in + 124 B episode record out
+PAYOFF1 = [[8, -12, -12], [-12, 0, 0], [-12, 0, 0]]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_args(alg="qmix"):
+    from marl_b200.common.arguments import default_args
+    return default_args(alg=alg, n_agents=SHAPE["N"], n_actions=SHAPE["A"], obs_shape=SHAPE["O"],
+                        state_shape=SHAPE["S"], episode_limit=SHAPE["T"], map="synthetic_2s3z")
+
+
+def oracle_state(args, seed=0):
+    import torch
+    from oracle import marl_oracle as MO
+    torch.manual_seed(seed)
+    cfg = MO.make_cfg(alg=args.alg, n_agents=args.n_agents, n_actions=args.n_actions, obs_shape=args.obs_shape,
+                      state_shape=args.state_shape, episode_limit=args.episode_limit)
+    return MO, MO.LearnerState(cfg)
+
+
+def time_cpu_reference(steps, warmup, threads=None):
+    """The reference algorithm's CPU path (oracle port: same per-timestep torch op sequence as
+    controller/share_params.py + algorithm/q_learner.py) on the host cores."""
+    import torch
+    from marl_b200.synthetic import synthetic_batch
+    if threads:
+        torch.set_num_threads(threads)
+    MO, st = oracle_state(make_args())
+    batch = synthetic_batch(0, **SHAPE)
+    for i in range(warmup):
+        MO.train_step(st, batch, i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        MO.train_step(st, batch, warmup + i)
+    dt = time.perf_counter() - t0
+    return SHAPE["B"] * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(opt):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(opt.steps, 30)
+    val, per, cores = time_cpu_reference(steps, min(opt.warmup, 3))
+    line = {"impl": "reference", "metric": "QMIX learner episode-samples/sec (2s3z shape)", "value": val,
+            "unit": "episode-samples/s", "n_gpus": opt.gpus, "steps": steps, "warmup": min(opt.warmup, 3),
+            "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "QMIX learner step, synthetic 2s3z-shaped batch (5 agents, 11 actions, T=120, batch 32)"},
+            "cpu_baseline": {"value": val, "unit": "episode-samples/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} train steps of the B=32 batch; oracle port of the reference's CPU path "
+                                       "(the Python reference cannot travel to the GPU box)"},
+            "e2e": {"value": val, "unit": "episode-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def bench_env(torch, L, n_envs, iters, hbm_peak):
+    from marl_b200.env.single_state_matrix_game import BatchedMatrixGame
+    env = BatchedMatrixGame(PAYOFF1, n_envs)
+    acts = torch.randint(0, 3, (n_envs, 2), device="cuda", dtype=torch.int64)
+    for _ in range(5):
+        env.step(acts)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        env.step(acts)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    rate = n_envs / (ms * 1e-3)
+    gbs = rate * ENV_BYTES / 1e9
+    return {"n_envs": n_envs, "value": rate, "unit": "env-steps/s", "us_per_launch": ms * 1e3,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "traffic": None}}
+
+
+def run_ours(opt):
+    import torch
+    import torch.distributed as dist
+    from marl_b200 import _lib as L
+    from marl_b200.algorithm.q_learner import QLearner
+    from marl_b200.controller.share_params import SharedMAC
+    from marl_b200.synthetic import synthetic_batch, KEYS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hbm_peak, peak_src = peaks()
+    K, W = opt.steps, max(opt.warmup, 3)
+    B = SHAPE["B"]
+
+    args = make_args()
+    torch.manual_seed(0)
+    learner = QLearner(SharedMAC(args), args)
+    if world > 1:
+        learner.enable_data_parallel()
+
+    # Each rank holds its own shard: weak scaling, B=32 episodes per GPU, global batch 32*world.
+    NB = 8                                            # 8 x 18.7 MB = 150 MB of inputs > 126 MB L2
+    dev_batches, host_batches = [], []
+    for i in range(NB):
+        hb = synthetic_batch(1000 * rank + i, **SHAPE)
+        db = {k: torch.as_tensor(v, device="cuda") for k, v in hb.items()}
+        db = {k: (v.to(torch.int64) if k == "u" else v.to(torch.float32)).contiguous() for k, v in db.items()}
+        db["max_episode_len"] = SHAPE["T"]
+        dev_batches.append(db)
+        if i < 2:                                     # pinned float64 host copies in the ReplayBuffer layout
+            pinned = {k: torch.from_numpy(v).pin_memory() for k, v in hb.items()}
+            host_batches.append({k: t.numpy() for k, t in pinned.items()})
+            host_batches[-1]["_keep"] = pinned
+    shard = learner._shard
+    if world > 1:
+        learner._shard = lambda B_glob: (0, B_glob)  # every rank already holds exactly its shard
+
+    def host_view(i):
+        return {k: host_batches[i % 2][k] for k in KEYS}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step = 0
+    for i in range(W):
+        learner.train(dev_batches[i % NB], step); step += 1
+    for i in range(max(W, 3)):
+        learner.train(host_view(i), step); step += 1
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- value: device-resident batches -------------------------------------------------------------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(K):
+        learner.train(dev_batches[i % NB], step); step += 1
+    ev1.record()
+    barrier()
+    ms_dev = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    # ---- e2e: pinned host float64 batches through the reference-facing call ---------------------------
+    barrier()
+    ev0.record()
+    for i in range(K):
+        learner.train(host_view(i), step); step += 1
+    ev1.record()
+    barrier()
+    ms_e2e = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    h2d = learner.h2d_bytes_last
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        dist.all_reduce(ms_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(ms_dev) / K, float(ms_e2e) / K
+    launches = learner.launches_per_step + 1          # + the ingest launch
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel device time (eager pass, CUDA events around every launch of the library) ---------
+    learner._use_graph = False
+    L.profile(True)
+    P = 10
+    for i in range(P):
+        if world == 1:
+            learner.train(dev_batches[i % NB], step); step += 1
+    prof = L.profile_collect() if world == 1 else {}
+    L.profile(False)
+    learner._use_graph = True
+    tot_ms = sum(ms for _, ms in prof.values()) or 1.0
+    kernels = {k: {"launches_per_step": c / P, "us_per_step": ms * 1e3 / P, "share": ms / tot_ms}
+               for k, (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    # FP32 FMA peak of this GPU (probe kernel), the compute-roofline denominator
+    scratch = torch.zeros(4, device="cuda")
+    import ctypes as C
+    flops = C.c_double()
+    for _ in range(2):
+        L.call("marl_fma_probe", scratch.data_ptr(), 1 << 14, 148 * 8, C.byref(flops), L.stream_ptr())
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    L.call("marl_fma_probe", scratch.data_ptr(), 1 << 14, 148 * 8, C.byref(flops), L.stream_ptr())
+    b.record()
+    torch.cuda.synchronize()
+    fp32_peak = flops.value / (a.elapsed_time(b) * 1e-3) / 1e12
+
+    roofline = None
+    if kernels:
+        dom = next(iter(kernels))
+        dom_us = kernels[dom]["us_per_step"] / max(kernels[dom]["launches_per_step"], 1)
+        if dom == "gru_unroll_fwd_kernel":
+            ach = GRU_FWD_FLOP / (dom_us * 1e-6) / 1e12
+            roofline = {"kernel": dom, "bound": "fp32_fma (latency-bound recurrence at B=32: 160 rows x 240 dependent steps)",
+                        "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": None,
+                        "us_per_launch": dom_us, "peak_source": "marl_fma_probe on this GPU"}
+        else:
+            ach = FLOP_PER_STEP * kernels[dom]["share"] / (kernels[dom]["us_per_step"] * 1e-6) / 1e12
+            roofline = {"kernel": dom, "bound": "fp32_fma", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                        "frac": ach / fp32_peak, "traffic": None, "us_per_launch": dom_us}
+    step_tflops = FLOP_PER_STEP / (ms_dev * 1e-3) / 1e12
+    env_small = bench_env(torch, L, 4096, 200, hbm_peak)
+    env_big = bench_env(torch, L, 1 << 24, 20, hbm_peak)
+
+    cpu = None
+    if world == 1:
+        val, per, cores = time_cpu_reference(20, 3)
+        cpu = {"value": val, "unit": "episode-samples/s", "cores": cores, "kind": "port",
+               "sample": "20 train steps (after 3 warm-up) of the same B=32 2s3z-shaped batch, oracle port of the "
+                         "reference CPU path, all host threads", "ms_per_step": per * 1e3}
+
+    line = {
+        "metric": "QMIX learner episode-samples/sec (2s3z shape)", "value": B * world / (ms_dev * 1e-3),
+        "unit": "episode-samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "QMIX learner step, synthetic 2s3z-shaped batch (5 agents, 11 actions, T=120, "
+                               "batch 32 per GPU, RMSprop, double-Q)",
+                   "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2": f"inputs rotate over {NB} resident batches (150 MB > 126 MB L2)"},
+        "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "episode-samples/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8},
+        "gpu_launches": int(launches * K * 2),
+        "launches_per_step": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "step_fp32": {"tflops": step_tflops, "frac_of_fp32_peak": step_tflops / fp32_peak, "fp32_peak_tflops": fp32_peak,
+                      "hbm_frac": BYTES_PER_STEP / (ms_dev * 1e-3) / 1e9 / hbm_peak, "hbm_peak_gbs": hbm_peak,
+                      "peak_source": peak_src},
+        "kernels": kernels,
+        "env": {"metric": "matrix-game env-steps/sec", "value": env_big["value"], "unit": "env-steps/s",
+                "bytes_per_env_step": ENV_BYTES, "cfg5_4096_envs": env_small, "bandwidth_regime_2^24_envs": env_big},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    opt = ap.parse_args()
+    if opt.impl == "reference":
+        run_reference(opt)
+    else:
+        run_ours(opt)
+
+
+if __name__ == "__main__":
+    main()

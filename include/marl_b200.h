@@ -68,6 +68,11 @@ int marl_matrix_game_validate_actions(const void* actions, int action_bytes, lon
 int marl_ingest_f64(const marl_episode_f64* src, int T_src, const marl_dims* d,
                     const marl_episode_f32* dst, void* stream);
 
+/* Device-resident variant: fp32 [B, T_src, ...] (e.g. rows sampled from a device replay buffer) ->
+ * the step's working set [B, L, ...]. */
+int marl_ingest_f32(const marl_episode_f32* src, int T_src, const marl_dims* d,
+                    const marl_episode_f32* dst, void* stream);
+
 /* ---- agent: network/q_network.py:6-21 unrolled by controller/share_params.py:125-168 ---- */
 typedef struct marl_agent_params {
     const float* fc1_w;  /* [H, O+A+N] */  const float* fc1_b;  /* [H] */
@@ -182,6 +187,15 @@ int marl_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_
                         const float* scalars, float max_norm, float lr, float beta1, float beta2, float eps,
                         int step, int* step_counter /*nullable, device*/, float* partials, float* loss_out,
                         void* stream);
+
+/* ---- built-in launch profiler (bench.py roofline leg) ----
+ * When enabled, every kernel launch of the library is bracketed by CUDA events on its stream.
+ * marl_profile_collect synchronises the device and writes "kernel,count,total_ms\n" lines. */
+/* FP32 FMA throughput probe (the compute-roofline denominator bench.py reports against):
+ * launches `blocks` x 256 threads x 8 independent FMA chains x `iters`; *flops_out = FLOPs issued. */
+int marl_fma_probe(float* scratch_device, int iters, int blocks, double* flops_out_host, void* stream);
+int marl_profile_enable(int on);
+int marl_profile_collect(char* buf_host, int buflen);
 
 #ifdef __cplusplus
 }

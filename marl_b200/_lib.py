@@ -73,6 +73,8 @@ _SIGNATURES = {
     "marl_matrix_game_step": ([_P(C.c_double), c_ptr, C.c_int, C.c_longlong, C.c_float, _P(EpisodeF32), c_ptr, c_ptr], C.c_int),
     "marl_matrix_game_validate_actions": ([c_ptr, C.c_int, C.c_longlong, c_ptr, c_ptr], C.c_int),
     "marl_ingest_f64": ([_P(EpisodeF64), C.c_int, _P(Dims), _P(EpisodeF32), c_ptr], C.c_int),
+    "marl_ingest_f32": ([_P(EpisodeF32), C.c_int, _P(Dims), _P(EpisodeF32), c_ptr], C.c_int),
+    "marl_fma_probe": ([c_ptr, C.c_int, C.c_int, _P(C.c_double), c_ptr], C.c_int),
     "marl_agent_unroll_fwd": ([_P(Dims), _P(UnrollStream), C.c_int, c_ptr], C.c_int),
     "marl_agent_unroll_bwd": ([_P(Dims), _P(UnrollBwd), c_ptr], C.c_int),
     "marl_q_select": ([_P(Dims)] + [c_ptr] * 11 + [c_ptr], C.c_int),
@@ -83,6 +85,8 @@ _SIGNATURES = {
     "marl_qmix_td_fwd_bwd": ([_P(Dims), _P(QmixParams), _P(QmixParams)] + [c_ptr] * 8 + [C.c_float] + [c_ptr] * 6
                              + [_P(QmixGrads), c_ptr, c_ptr], C.c_int),
     "marl_optim_partials": ([], C.c_int),
+    "marl_profile_enable": ([C.c_int], C.c_int),
+    "marl_profile_collect": ([C.c_char_p, C.c_int], C.c_int),
     "marl_clip_rmsprop_step": ([c_ptr, c_ptr, c_ptr, C.c_longlong, c_ptr] + [C.c_float] * 4 + [c_ptr, c_ptr, c_ptr], C.c_int),
     "marl_clip_adam_step": ([c_ptr] * 4 + [C.c_longlong, c_ptr] + [C.c_float] * 5 + [C.c_int, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
 }
@@ -135,6 +139,21 @@ def ptr(t):
 
 def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
+
+
+def profile(on):
+    load().marl_profile_enable(1 if on else 0)
+
+
+def profile_collect():
+    """{kernel name: (launch count, total ms)} since the last collect."""
+    buf = C.create_string_buffer(1 << 16)
+    check(load().marl_profile_collect(buf, len(buf)), "marl_profile_collect")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(",", 2)
+        out[name] = (int(cnt), float(ms))
+    return out
 
 
 def call(name, *args):

@@ -14,6 +14,7 @@
 // eval unroll on o, algorithm/q_learner.py:96,110) are chained inside the same CTA.
 #include "linear.h"
 #include "../../include/marl_b200.h"
+#include "profile.h"
 
 namespace marl {
 
@@ -298,9 +299,9 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
     const int rows = d->B * d->N;
     const int R = pick_rows_per_cta(rows, ga.n_chains);
     dim3 grid((rows + R - 1) / R, ga.n_chains);
-    if (R == 1) gru_unroll_fwd_kernel<1><<<grid, kGruThreads, 0, st>>>(ga);
-    else if (R == 2) gru_unroll_fwd_kernel<2><<<grid, kGruThreads, 0, st>>>(ga);
-    else gru_unroll_fwd_kernel<4><<<grid, kGruThreads, 0, st>>>(ga);
+    if (R == 1) { ProfScope ps_("gru_unroll_fwd_kernel", st); gru_unroll_fwd_kernel<1><<<grid, kGruThreads, 0, st>>>(ga); }
+    else if (R == 2) { ProfScope ps_("gru_unroll_fwd_kernel", st); gru_unroll_fwd_kernel<2><<<grid, kGruThreads, 0, st>>>(ga); }
+    else { ProfScope ps_("gru_unroll_fwd_kernel", st); gru_unroll_fwd_kernel<4><<<grid, kGruThreads, 0, st>>>(ga); }
     MARL_LAUNCH_CHECK();
     // phase C
     for (int i = 0; i < n_streams; ++i) {
@@ -338,9 +339,9 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
     const int rows = d->B * d->N;
     const int R = pick_rows_per_cta(rows, 1);
     dim3 grid((rows + R - 1) / R);
-    if (R == 1) gru_unroll_bwd_kernel<1><<<grid, kGruThreads, 0, st>>>(ga);
-    else if (R == 2) gru_unroll_bwd_kernel<2><<<grid, kGruThreads, 0, st>>>(ga);
-    else gru_unroll_bwd_kernel<4><<<grid, kGruThreads, 0, st>>>(ga);
+    if (R == 1) { ProfScope ps_("gru_unroll_bwd_kernel", st); gru_unroll_bwd_kernel<1><<<grid, kGruThreads, 0, st>>>(ga); }
+    else if (R == 2) { ProfScope ps_("gru_unroll_bwd_kernel", st); gru_unroll_bwd_kernel<2><<<grid, kGruThreads, 0, st>>>(ga); }
+    else { ProfScope ps_("gru_unroll_bwd_kernel", st); gru_unroll_bwd_kernel<4><<<grid, kGruThreads, 0, st>>>(ga); }
     MARL_LAUNCH_CHECK();
     {   // dW_hh += dgh^T . h_{t-1} (hidden shifted by one step, zeros at t = 0) ; db_hh
         LinearWgrad w{};

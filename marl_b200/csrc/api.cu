@@ -16,3 +16,27 @@ extern "C" int marl_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     if (cc_minor) *cc_minor = p.minor;
     return MARL_OK;
 }
+
+// FP32 FMA throughput probe: the denominator of the learner's compute roofline (bench.py).
+__global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters) {
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 1.0f + 1e-3f * (threadIdx.x + i);
+    const float x = 1.0000001f, y = 1e-7f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], x, y);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 12345.678f) out[0] = s;   // keep the loop alive
+}
+
+extern "C" int marl_fma_probe(float* scratch_device, int iters, int blocks, double* flops_out, void* stream) {
+    if (!scratch_device || iters <= 0 || blocks <= 0) return MARL_EINVAL;
+    fma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(scratch_device, iters);
+    MARL_LAUNCH_CHECK();
+    if (flops_out) *flops_out = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+    return MARL_OK;
+}

@@ -4,6 +4,7 @@
 // HBM-bound: 16 B of actions in, 124 B of episode record out per env-step.
 #include "common.cuh"
 #include "../../include/marl_b200.h"
+#include "profile.h"
 
 namespace marl {
 
@@ -109,13 +110,13 @@ extern "C" int marl_matrix_game_step(const double* payoff_host, const void* acti
     if (blocks > kNumSMs) blocks = (blocks / kNumSMs) * kNumSMs;   // whole waves
     cudaStream_t st = (cudaStream_t)stream;
     if (action_bytes == 8)
-        matrix_game_step_kernel<long long><<<blocks, 256, 0, st>>>(p, (const long long*)actions, n_envs, obs_value,
+        { ProfScope ps_("matrix_game_step_kernel", st); matrix_game_step_kernel<long long><<<blocks, 256, 0, st>>>(p, (const long long*)actions, n_envs, obs_value,
             out->o, out->s, out->u, out->r, out->o_next, out->s_next, out->avail_u, out->avail_u_next,
-            out->u_onehot, out->padded, out->terminated, r64);
+            out->u_onehot, out->padded, out->terminated, r64); }
     else
-        matrix_game_step_kernel<int><<<blocks, 256, 0, st>>>(p, (const int*)actions, n_envs, obs_value,
+        { ProfScope ps_("matrix_game_step_kernel", st); matrix_game_step_kernel<int><<<blocks, 256, 0, st>>>(p, (const int*)actions, n_envs, obs_value,
             out->o, out->s, out->u, out->r, out->o_next, out->s_next, out->avail_u, out->avail_u_next,
-            out->u_onehot, out->padded, out->terminated, r64);
+            out->u_onehot, out->padded, out->terminated, r64); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
@@ -127,9 +128,9 @@ extern "C" int marl_matrix_game_validate_actions(const void* actions, int action
     if (n_envs == 0) return MARL_OK;
     int blocks = (int)((2 * n_envs + 255) / 256);
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-    matrix_game_validate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+    { ProfScope ps_("matrix_game_validate_kernel", (cudaStream_t)stream); matrix_game_validate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
         action_bytes == 8 ? (const long long*)actions : nullptr, action_bytes == 4 ? (const int*)actions : nullptr,
-        n_envs, bad_flag_device);
+        n_envs, bad_flag_device); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }

@@ -3,6 +3,7 @@
 // addmm calls behind nn.Linear in the reference (network/q_network.py:17,20;
 // network/mixer.py:45-55,117-145,200-206,365-375,399-409) and their autograd duals.
 #include "linear.h"
+#include "profile.h"
 
 namespace marl {
 
@@ -121,7 +122,7 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 int linear_fwd(const LinearFwd& a, cudaStream_t st) {
     if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return MARL_OK;
     dim3 grid(cdiv(a.M, BM), cdiv(a.N, BN), a.batch);
-    linear_fwd_kernel<<<grid, GEMM_THREADS, 0, st>>>(a);
+    { ProfScope ps_("linear_fwd_kernel", st); linear_fwd_kernel<<<grid, GEMM_THREADS, 0, st>>>(a); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
@@ -129,7 +130,7 @@ int linear_fwd(const LinearFwd& a, cudaStream_t st) {
 int linear_dgrad(const LinearDgrad& a, cudaStream_t st) {
     if (a.M <= 0 || a.K <= 0 || a.batch <= 0) return MARL_OK;
     dim3 grid(cdiv(a.M, BM), cdiv(a.K, BN), a.batch);
-    linear_dgrad_kernel<<<grid, GEMM_THREADS, 0, st>>>(a);
+    { ProfScope ps_("linear_dgrad_kernel", st); linear_dgrad_kernel<<<grid, GEMM_THREADS, 0, st>>>(a); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
@@ -143,7 +144,7 @@ int linear_wgrad(const LinearWgrad& a, cudaStream_t st) {
     int chunk = cdiv(cdiv(a.M, splits), BK) * BK;
     splits = cdiv(a.M, chunk);
     dim3 grid(cdiv(a.N, BM), cdiv(Kout, BN), a.batch * splits);
-    linear_wgrad_kernel<<<grid, GEMM_THREADS, 0, st>>>(a, splits, chunk);
+    { ProfScope ps_("linear_wgrad_kernel", st); linear_wgrad_kernel<<<grid, GEMM_THREADS, 0, st>>>(a, splits, chunk); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }

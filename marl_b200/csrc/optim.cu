@@ -5,6 +5,7 @@
 // partials in the same fixed order, then updates its slice.
 #include "common.cuh"
 #include "../../include/marl_b200.h"
+#include "profile.h"
 
 namespace marl {
 
@@ -100,10 +101,10 @@ extern "C" int marl_clip_rmsprop_step(float* params, float* grads, float* square
                                       void* stream) {
     if (!params || !grads || !square_avg || n <= 0 || !scalars || !partials) return MARL_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    sumsq_kernel<<<kOptBlocks, kOptThreads, 0, st>>>(grads, n, partials, nullptr);
+    { ProfScope ps_("sumsq_kernel", st); sumsq_kernel<<<kOptBlocks, kOptThreads, 0, st>>>(grads, n, partials, nullptr); }
     MARL_LAUNCH_CHECK();
-    clip_rmsprop_kernel<<<opt_grid(n), kOptThreads, 0, st>>>(params, grads, square_avg, n, partials, scalars, max_norm, lr,
-                                                             alpha, eps, loss_out);
+    { ProfScope ps_("clip_rmsprop_kernel", st); clip_rmsprop_kernel<<<opt_grid(n), kOptThreads, 0, st>>>(params, grads, square_avg, n, partials, scalars, max_norm, lr,
+                                                             alpha, eps, loss_out); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
@@ -114,10 +115,10 @@ extern "C" int marl_clip_adam_step(float* params, float* grads, float* exp_avg, 
     if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || !scalars || !partials) return MARL_EINVAL;
     if (!step_counter && step < 1) return MARL_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    sumsq_kernel<<<kOptBlocks, kOptThreads, 0, st>>>(grads, n, partials, step_counter);
+    { ProfScope ps_("sumsq_kernel", st); sumsq_kernel<<<kOptBlocks, kOptThreads, 0, st>>>(grads, n, partials, step_counter); }
     MARL_LAUNCH_CHECK();
-    clip_adam_kernel<<<opt_grid(n), kOptThreads, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, partials, scalars,
-                                                          max_norm, lr, beta1, beta2, eps, step, step_counter, loss_out);
+    { ProfScope ps_("clip_adam_kernel", st); clip_adam_kernel<<<opt_grid(n), kOptThreads, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, partials, scalars,
+                                                          max_norm, lr, beta1, beta2, eps, step, step_counter, loss_out); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }

@@ -9,6 +9,7 @@
 //   weight-gradient GEMM dwcat += dhy^T . s.
 #include "linear.h"
 #include "../../include/marl_b200.h"
+#include "profile.h"
 
 namespace marl {
 
@@ -161,7 +162,7 @@ extern "C" int marl_qmix_fwd(int M, int N, int S, const marl_qmix_params* p, con
     if (rc) return rc;
     QmixMixArgs a{};
     a.M = M; a.N = N; a.mode = QMIX_FWD; a.hy = hy; a.q = q; a.wb2 = p->wb2; a.bb2 = p->bb2; a.q_tot = q_tot;
-    qmix_mix_kernel<<<mix_grid(M), kQmixWarps * 32, 0, st>>>(a);
+    { ProfScope ps_("qmix_mix_kernel", st); qmix_mix_kernel<<<mix_grid(M), kQmixWarps * 32, 0, st>>>(a); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
@@ -176,7 +177,7 @@ extern "C" int marl_qmix_bwd(int M, int N, int S, const marl_qmix_params* p, con
     QmixMixArgs a{};
     a.M = M; a.N = N; a.mode = QMIX_BWD; a.hy = hy; a.q = q; a.wb2 = p->wb2; a.bb2 = p->bb2;
     a.dq_tot_in = dq_tot; a.dhy = dhy; a.dq_small = dq; a.g_wb2 = g->wb2; a.g_bb2 = g->bb2;
-    qmix_mix_kernel<<<mix_grid(M), kQmixWarps * 32, 0, st>>>(a);
+    { ProfScope ps_("qmix_mix_kernel", st); qmix_mix_kernel<<<mix_grid(M), kQmixWarps * 32, 0, st>>>(a); }
     MARL_LAUNCH_CHECK();
     return hyper_wgrad(M, N, S, s, dhy, g, st);
 }
@@ -204,7 +205,7 @@ extern "C" int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* 
     a.r = r; a.term = terminated; a.padded = padded; a.gamma = gamma;
     a.q_tot = q_tot; a.q_tot_t = q_tot_target; a.dhy = dhy; a.u = u; a.dq_dense = dq;
     a.g_wb2 = g->wb2; a.g_bb2 = g->bb2; a.scalars = scalars;
-    qmix_mix_kernel<<<mix_grid(M), kQmixWarps * 32, 0, st>>>(a);
+    { ProfScope ps_("qmix_mix_kernel", st); qmix_mix_kernel<<<mix_grid(M), kQmixWarps * 32, 0, st>>>(a); }
     MARL_LAUNCH_CHECK();
     return hyper_wgrad(M, d->N, d->S, s, dhy, g, st);
 }

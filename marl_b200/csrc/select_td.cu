@@ -1,6 +1,7 @@
 // Action-value selection (gather / masked argmax / target gather), TD loss, VDN, batch ingest.
 #include "common.cuh"
 #include "../../include/marl_b200.h"
+#include "profile.h"
 
 namespace marl {
 
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) vdn_td_kernel(int M, int N, int A, const 
     block_accumulate2(sq, msk, scalars);
 }
 
-struct IngestKey { const void* src; void* dst; int inner; int kind; };   // kind 0: f64->f32, 1: f64->i64, 2: i64->i64
+struct IngestKey { const void* src; void* dst; int inner; int kind; };   // kind 0: f64->f32, 1: f64->i64, 2: i64->i64, 3: f32->f32
 struct IngestArgs { IngestKey k[11]; int B, L, T_src; };
 
 __global__ void __launch_bounds__(256) ingest_kernel(IngestArgs a) {
@@ -111,7 +112,8 @@ __global__ void __launch_bounds__(256) ingest_kernel(IngestArgs a) {
         const long long b = i / per_b, rem = i - b * per_b, si = b * src_b + rem;
         if (key.kind == 0) ((float*)key.dst)[i] = (float)((const double*)key.src)[si];
         else if (key.kind == 1) ((long long*)key.dst)[i] = (long long)((const double*)key.src)[si];   // trunc toward zero
-        else ((long long*)key.dst)[i] = ((const long long*)key.src)[si];
+        else if (key.kind == 2) ((long long*)key.dst)[i] = ((const long long*)key.src)[si];
+        else ((float*)key.dst)[i] = ((const float*)key.src)[si];
     }
 }
 
@@ -128,8 +130,8 @@ extern "C" int marl_q_select(const marl_dims* d, const float* q_evals, const lon
     if (max_q_evals && (!avail_u || !q_evals)) return MARL_EINVAL;
     const int rows = d->B * d->L * d->N;
     if (rows <= 0) return MARL_OK;
-    q_select_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, d->A, q_evals, u, q_evals_next, q_targets,
-        avail_u_next, avail_u, q_chosen, a_star, q_targets_chosen, max_q_evals, q_targets_max);
+    { ProfScope ps_("q_select_kernel", (cudaStream_t)stream); q_select_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, d->A, q_evals, u, q_evals_next, q_targets,
+        avail_u_next, avail_u, q_chosen, a_star, q_targets_chosen, max_q_evals, q_targets_max); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
@@ -138,8 +140,8 @@ extern "C" int marl_td_loss(int M, const float* q_tot, const float* q_tot_target
                             const float* padded, float gamma, float* dq_tot, float* scalars, void* stream) {
     if (M < 0 || !q_tot || !q_tot_target || !r || !terminated || !padded || !scalars) return MARL_EINVAL;
     if (M == 0) return MARL_OK;
-    td_loss_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(M, q_tot, q_tot_target, r, terminated, padded, gamma,
-                                                                     dq_tot, scalars);
+    { ProfScope ps_("td_loss_kernel", (cudaStream_t)stream); td_loss_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(M, q_tot, q_tot_target, r, terminated, padded, gamma,
+                                                                     dq_tot, scalars); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
@@ -152,8 +154,8 @@ extern "C" int marl_vdn_td_fwd_bwd(const marl_dims* d, const float* q_chosen, co
     if (dq && !u) return MARL_EINVAL;
     const int M = d->B * d->L;
     if (M <= 0) return MARL_OK;
-    vdn_td_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(M, d->N, d->A, q_chosen, q_targets_chosen, u, r,
-        terminated, padded, gamma, q_tot, q_tot_target, dq, scalars);
+    { ProfScope ps_("vdn_td_kernel", (cudaStream_t)stream); vdn_td_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(M, d->N, d->A, q_chosen, q_targets_chosen, u, r,
+        terminated, padded, gamma, q_tot, q_tot_target, dq, scalars); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
@@ -181,7 +183,35 @@ extern "C" int marl_ingest_f64(const marl_episode_f64* s, int T_src, const marl_
     int bx = (int)((biggest + 1023) / 1024);
     if (bx < 1) bx = 1;
     if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;
-    ingest_kernel<<<dim3(bx, 11), 256, 0, (cudaStream_t)stream>>>(a);
+    { ProfScope ps_("ingest_kernel", (cudaStream_t)stream); ingest_kernel<<<dim3(bx, 11), 256, 0, (cudaStream_t)stream>>>(a); }
+    MARL_LAUNCH_CHECK();
+    return MARL_OK;
+}
+
+extern "C" int marl_ingest_f32(const marl_episode_f32* s, int T_src, const marl_dims* d, const marl_episode_f32* o,
+                               void* stream) {
+    if (!s || !d || !o || T_src < d->L || d->B <= 0 || d->L <= 0) return MARL_EINVAL;
+    IngestArgs a{};
+    a.B = d->B; a.L = d->L; a.T_src = T_src;
+    const int NO = d->N * d->O, NA = d->N * d->A;
+    a.k[0] = {s->o, o->o, NO, 3};
+    a.k[1] = {s->u, o->u, d->N, 2};
+    a.k[2] = {s->s, o->s, d->S, 3};
+    a.k[3] = {s->r, o->r, 1, 3};
+    a.k[4] = {s->o_next, o->o_next, NO, 3};
+    a.k[5] = {s->s_next, o->s_next, d->S, 3};
+    a.k[6] = {s->avail_u, o->avail_u, NA, 3};
+    a.k[7] = {s->avail_u_next, o->avail_u_next, NA, 3};
+    a.k[8] = {s->u_onehot, o->u_onehot, NA, 3};
+    a.k[9] = {s->padded, o->padded, 1, 3};
+    a.k[10] = {s->terminated, o->terminated, 1, 3};
+    for (int i = 0; i < 11; ++i)
+        if (!a.k[i].src || !a.k[i].dst) return MARL_EINVAL;
+    long long biggest = (long long)d->B * d->L * (NO > NA ? NO : NA);
+    int bx = (int)((biggest + 1023) / 1024);
+    if (bx < 1) bx = 1;
+    if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;
+    { ProfScope ps_("ingest_kernel", (cudaStream_t)stream); ingest_kernel<<<dim3(bx, 11), 256, 0, (cudaStream_t)stream>>>(a); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
