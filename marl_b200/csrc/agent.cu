@@ -19,7 +19,23 @@
 namespace marl {
 
 constexpr int kMaxStreams = 4;
-constexpr int kGruThreads = 256;   // 64 hidden units x 4-way split of the reduction
+constexpr int kGruThreads = 128;   // 64 hidden units x 2-way split of the reduction, one warp per SM sub-partition
+constexpr int kGiDepth = 4;        // cp.async ring depth (time steps) of the forward's input gates
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// MUFU-based gate non-linearities: ex2.approx / rcp.approx are accurate to ~2 ulp, i.e. <= 2e-7 absolute on
+// the (0,1) / (-1,1) outputs -- the same order as the fp32 rounding of the reference's own libm path.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float gate_sigmoid(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float gate_tanh(float x) { return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * x)), 1.0f); }
 
 struct GruSegment {
     const float* gi;      // [B,L,N,3H]
@@ -34,62 +50,81 @@ struct GruFwdArgs {
     GruSegment seg[kMaxStreams];
     int chain_start[kMaxStreams];
     int chain_len[kMaxStreams];
+    int chain_rows_per_cta[kMaxStreams];
+    int chain_cta0[kMaxStreams];     // first blockIdx.x of the chain
     const float* h0[kMaxStreams];
     int n_chains, B, L, N;
 };
 
+// One CTA advances R rows (b,n) of one chain through all its segments.  Thread (j, ks): hidden unit j,
+// half ks of the 64-long reduction; its 3 x 32 W_hh weights stay in registers for the whole segment.
 template <int R>
-__global__ void __launch_bounds__(kGruThreads) gru_unroll_fwd_kernel(GruFwdArgs a) {
-    __shared__ __align__(16) float hs[2][R][MARL_H];
-    const int tid = threadIdx.x, ks = tid & 3, j = tid >> 2;
-    const int chain = blockIdx.y;
-    const int rows = a.B * a.N;
-    const int row0 = blockIdx.x * R;
-    const int my_row = row0 + ks;
-    const bool owner = (ks < R) && (my_row < rows);
+__device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, int group, float* smem) {
+    float (*hs)[R][MARL_H] = reinterpret_cast<float (*)[R][MARL_H]>(smem);                          // [2][R][H]
+    float (*ring)[R][MARL_G] = reinterpret_cast<float (*)[R][MARL_G]>(smem + 2 * R * MARL_H);       // [D][R][3H]
+    const int tid = threadIdx.x, ks = tid & 1, j = tid >> 1;
+    const int rows = a.B * a.N, row0 = group * R;
+    const int L = a.L, N = a.N;
+    constexpr int OWN = (R + 1) / 2;                  // rows whose gate math this lane owns: rr = ks + 2q
+    bool own[OWN]; long long base[OWN];
+#pragma unroll
+    for (int q = 0; q < OWN; ++q) {
+        const int rr = ks + 2 * q, row = row0 + rr;
+        own[q] = rr < R && row < rows;
+        base[q] = own[q] ? ((long long)(row / N) * L * N + (row % N)) : 0;
+    }
+    // cp.async work list: R rows x 48 chunks of 16 B per time step
+    constexpr int NCH = (R * 48 + kGruThreads - 1) / kGruThreads;
+    long long csrc[NCH]; int cdst[NCH];
+#pragma unroll
+    for (int l = 0; l < NCH; ++l) {
+        const int c = tid + l * kGruThreads, rr = c / 48, ch = c % 48, row = row0 + rr;
+        if (c < R * 48 && row < rows) {
+            csrc[l] = ((long long)(row / N) * L * N + (row % N)) * MARL_G + ch * 4;
+            cdst[l] = rr * MARL_G + ch * 4;
+        } else { csrc[l] = -1; cdst[l] = 0; }
+    }
     const float* h0 = a.h0[chain];
     for (int idx = tid; idx < R * MARL_H; idx += kGruThreads) {
-        int rr = idx / MARL_H, jj = idx % MARL_H, row = row0 + rr;
+        const int rr = idx / MARL_H, jj = idx % MARL_H, row = row0 + rr;
         hs[0][rr][jj] = (h0 && row < rows) ? h0[(long long)row * MARL_H + jj] : 0.0f;
     }
-    __syncthreads();
     int cur = 0;
-    const int L = a.L, N = a.N;
-    const long long base = owner ? ((long long)(my_row / N) * L * N + (my_row % N)) : 0;
-
     for (int sg = a.chain_start[chain]; sg < a.chain_start[chain] + a.chain_len[chain]; ++sg) {
         const GruSegment S = a.seg[sg];
-        // W_hh slice in registers: gate g, unit j, k = 4*(4*i+ks)+c  (float4-interleaved split of the 64-long dot)
-        float w[3][16];
+        float w[3][32];
 #pragma unroll
         for (int g = 0; g < 3; ++g)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float4 v = __ldg(reinterpret_cast<const float4*>(S.w_hh + (long long)(g * MARL_H + j) * MARL_H + 4 * (4 * i + ks)));
+            for (int i = 0; i < 8; ++i) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(S.w_hh + (long long)(g * MARL_H + j) * MARL_H + 4 * (2 * i + ks)));
                 w[g][4 * i + 0] = v.x; w[g][4 * i + 1] = v.y; w[g][4 * i + 2] = v.z; w[g][4 * i + 3] = v.w;
             }
         const float bh_r = __ldg(S.b_hh + j), bh_z = __ldg(S.b_hh + MARL_H + j), bh_n = __ldg(S.b_hh + 2 * MARL_H + j);
-        float gi_r = 0.f, gi_z = 0.f, gi_n = 0.f;
-        if (owner) {
-            const float* p = S.gi + base * MARL_G;
-            gi_r = __ldg(p + j); gi_z = __ldg(p + MARL_H + j); gi_n = __ldg(p + 2 * MARL_H + j);
-        }
-        for (int t = 0; t < L; ++t) {
-            float nx_r = 0.f, nx_z = 0.f, nx_n = 0.f;
-            if (owner && t + 1 < L) {   // software prefetch of the next step's input gates
-                const float* p = S.gi + (base + (long long)(t + 1) * N) * MARL_G;
-                nx_r = __ldg(p + j); nx_z = __ldg(p + MARL_H + j); nx_n = __ldg(p + 2 * MARL_H + j);
+        auto issue = [&](int t) {
+            if (t < L) {
+#pragma unroll
+                for (int l = 0; l < NCH; ++l)
+                    if (csrc[l] >= 0) cp_async16(&ring[t % kGiDepth][0][0] + cdst[l], S.gi + csrc[l] + (long long)t * N * MARL_G);
             }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int t = 0; t < kGiDepth - 1; ++t) issue(t);
+        for (int t = 0; t < L; ++t) {
+            cp_async_wait<kGiDepth - 2>();           // this thread's copies for step t have landed
+            __syncthreads();                         // ... everybody's; also orders the h double buffer
+            issue(t + kGiDepth - 1);                 // refill the slot consumed in step t-1
             float acc[3][R];
 #pragma unroll
             for (int g = 0; g < 3; ++g)
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr) acc[g][rr] = 0.0f;
 #pragma unroll
-            for (int rr = 0; rr < R; ++rr)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4 hv = *reinterpret_cast<const float4*>(&hs[cur][rr][4 * (4 * i + ks)]);
+                for (int rr = 0; rr < R; ++rr) {
+                    const float4 hv = *reinterpret_cast<const float4*>(&hs[cur][rr][4 * (2 * i + ks)]);
 #pragma unroll
                     for (int g = 0; g < 3; ++g) {
                         acc[g][rr] = fmaf(w[g][4 * i + 0], hv.x, acc[g][rr]);
@@ -98,39 +133,60 @@ __global__ void __launch_bounds__(kGruThreads) gru_unroll_fwd_kernel(GruFwdArgs 
                         acc[g][rr] = fmaf(w[g][4 * i + 3], hv.w, acc[g][rr]);
                     }
                 }
-            float ar = 0.f, az = 0.f, an = 0.f;
 #pragma unroll
-            for (int rr = 0; rr < R; ++rr)
+            for (int g = 0; g < 3; ++g)
 #pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                    float v = acc[g][rr];
-                    v += __shfl_xor_sync(0xffffffffu, v, 1);
-                    v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    if (rr == ks) { if (g == 0) ar = v; else if (g == 1) az = v; else an = v; }
-                }
-            if (owner) {
-                // GRUCell (torch/nn/modules/rnn.py; aten gru_cell): gate order r, z, n
-                const float gh_n = an + bh_n;
-                const float r = sigmoidf_acc((ar + bh_r) + gi_r);
-                const float z = sigmoidf_acc((az + bh_z) + gi_z);
-                const float n = tanhf(gi_n + r * gh_n);
-                const float hold = hs[cur][ks][j];
-                const float hnew = __fadd_rn(__fmul_rn(hold - n, z), n);
-                hs[cur ^ 1][ks][j] = hnew;
-                const long long idx = base + (long long)t * N;
-                S.hidden[idx * MARL_H + j] = hnew;
-                if (S.gates) {
-                    float* gp = S.gates + idx * (4 * MARL_H);
-                    gp[j] = r; gp[MARL_H + j] = z; gp[2 * MARL_H + j] = n; gp[3 * MARL_H + j] = gh_n;
+                for (int rr = 0; rr < R; ++rr) acc[g][rr] += __shfl_xor_sync(0xffffffffu, acc[g][rr], 1);
+            const float* gring = &ring[t % kGiDepth][0][0];
+#pragma unroll
+            for (int q = 0; q < OWN; ++q) {
+                const int e = 2 * q, o = (2 * q + 1 < R) ? 2 * q + 1 : 2 * q;      // static register indices
+                const float ar = ks ? acc[0][o] : acc[0][e];
+                const float az = ks ? acc[1][o] : acc[1][e];
+                const float an = ks ? acc[2][o] : acc[2][e];
+                if (own[q]) {
+                    const int rr = ks + 2 * q;
+                    // GRUCell (aten gru_cell): r,z = sigmoid(gi + gh); n = tanh(gi_n + r * gh_n); h' = (h - n) z + n
+                    const float* gp = gring + rr * MARL_G;
+                    const float gh_n = an + bh_n;
+                    const float r = gate_sigmoid((ar + bh_r) + gp[j]);
+                    const float z = gate_sigmoid((az + bh_z) + gp[MARL_H + j]);
+                    const float n = gate_tanh(fmaf(r, gh_n, gp[2 * MARL_H + j]));
+                    const float hold = hs[cur][rr][j];
+                    const float hnew = fmaf(hold - n, z, n);
+                    hs[cur ^ 1][rr][j] = hnew;
+                    const long long idx = base[q] + (long long)t * N;
+                    S.hidden[idx * MARL_H + j] = hnew;
+                    if (S.gates) {
+                        float* go = S.gates + idx * (4 * MARL_H);
+                        go[j] = r; go[MARL_H + j] = z; go[2 * MARL_H + j] = n; go[3 * MARL_H + j] = gh_n;
+                    }
                 }
             }
-            gi_r = nx_r; gi_z = nx_z; gi_n = nx_n;
-            __syncthreads();
             cur ^= 1;
         }
-        if (S.h_last && owner) S.h_last[(long long)my_row * MARL_H + j] = hs[cur][ks][j];
+        cp_async_wait<0>();
+        __syncthreads();
+        if (S.h_last) {
+#pragma unroll
+            for (int q = 0; q < OWN; ++q)
+                if (own[q]) S.h_last[(long long)(row0 + ks + 2 * q) * MARL_H + j] = hs[cur][ks + 2 * q][j];
+        }
     }
 }
+
+template <int R0, int R1>
+__global__ void __launch_bounds__(kGruThreads) gru_unroll_fwd_kernel(GruFwdArgs a) {
+    extern __shared__ __align__(16) float gru_smem[];
+    // chains are laid out back to back along blockIdx.x; chain 0 uses R0 rows per CTA, later chains R1
+    int chain = 0;
+    while (chain + 1 < a.n_chains && (int)blockIdx.x >= a.chain_cta0[chain + 1]) ++chain;
+    const int group = blockIdx.x - a.chain_cta0[chain];
+    if (chain == 0) gru_chain_fwd<R0>(a, chain, group, gru_smem);
+    else gru_chain_fwd<R1>(a, chain, group, gru_smem);
+}
+
+constexpr size_t gru_fwd_smem(int R) { return (size_t)(2 * R * MARL_H + kGiDepth * R * MARL_G) * sizeof(float); }
 
 struct GruBwdArgs {
     const float* gates;    // [B,L,N,4H]
@@ -145,86 +201,126 @@ struct GruBwdArgs {
     int B, L, N;
 };
 
+constexpr int kBwdSlot = 7 * MARL_H;     // r, z, n, gh_n (4H) | h_prev | dh_ext | dh_ext2   per row and time step
+constexpr int bwd_depth(int R) { return R >= 8 ? 3 : 6; }
+constexpr size_t gru_bwd_smem(int R) { return (size_t)(2 * R * MARL_G + bwd_depth(R) * R * kBwdSlot) * sizeof(float); }
+
 template <int R>
 __global__ void __launch_bounds__(kGruThreads) gru_unroll_bwd_kernel(GruBwdArgs a) {
-    __shared__ __align__(16) float sg[2][R][MARL_G];
-    const int tid = threadIdx.x, ks = tid & 3, j = tid >> 2;
-    const int rows = a.B * a.N;
-    const int row0 = blockIdx.x * R;
-    const int my_row = row0 + ks;
-    const bool owner = (ks < R) && (my_row < rows);
+    extern __shared__ __align__(16) float gru_smem[];
+    constexpr int D = bwd_depth(R);
+    float (*sg)[R][MARL_G] = reinterpret_cast<float (*)[R][MARL_G]>(gru_smem);                       // [2][R][3H]
+    float (*ring)[R][kBwdSlot] = reinterpret_cast<float (*)[R][kBwdSlot]>(gru_smem + 2 * R * MARL_G); // [D][R][7H]
+    const int tid = threadIdx.x, ks = tid & 1, j = tid >> 1;
+    const int rows = a.B * a.N, row0 = blockIdx.x * R;
     const int L = a.L, N = a.N;
-    const long long base = owner ? ((long long)(my_row / N) * L * N + (my_row % N)) : 0;
-    // column j of W_hh, rows m = 4*(4*i+ks)+c, i = 0..11   (dh_prev[j] += sum_m dgh[m] * W_hh[m, j])
-    float wt[48];
+    constexpr int OWN = (R + 1) / 2;
+    bool own[OWN]; long long base[OWN]; float dh_carry[OWN];
 #pragma unroll
-    for (int i = 0; i < 12; ++i)
+    for (int q = 0; q < OWN; ++q) {
+        const int rr = ks + 2 * q, row = row0 + rr;
+        own[q] = rr < R && row < rows;
+        base[q] = own[q] ? ((long long)(row / N) * L * N + (row % N)) : 0;
+        dh_carry[q] = 0.0f;
+    }
+    // column j of W_hh, rows m = 4*(2i+ks)+c, i = 0..23:  dh_prev[j] = dh z + sum_m dgh[m] W_hh[m, j]
+    float wt[96];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) wt[4 * i + c] = __ldg(a.w_hh + (long long)(4 * (4 * i + ks) + c) * MARL_H + j);
-    for (int idx = tid; idx < 2 * R * MARL_G; idx += kGruThreads) (&sg[0][0][0])[idx] = 0.0f;
-    __syncthreads();
-
-    float dh_carry = 0.0f;
-    float g_r = 0.f, g_z = 0.f, g_n = 0.f, g_hn = 0.f, hprev = 0.f, dhe = 0.f;
-    auto fetch = [&](int t, float& r, float& z, float& n, float& hn, float& hp, float& de) {
-        const long long idx = base + (long long)t * N;
-        const float* gp = a.gates + idx * (4 * MARL_H);
-        r = __ldg(gp + j); z = __ldg(gp + MARL_H + j); n = __ldg(gp + 2 * MARL_H + j); hn = __ldg(gp + 3 * MARL_H + j);
-        hp = t > 0 ? __ldg(a.hidden + (idx - N) * MARL_H + j) : (a.h0 ? __ldg(a.h0 + (long long)my_row * MARL_H + j) : 0.0f);
-        de = 0.0f;
-        if (a.dh_ext) de += __ldg(a.dh_ext + idx * MARL_H + j);
-        if (a.dh_ext2) de += __ldg(a.dh_ext2 + idx * MARL_H + j);
+    for (int i = 0; i < 24; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wt[4 * i + c] = __ldg(a.w_hh + (long long)(4 * (2 * i + ks) + c) * MARL_H + j);
+    // cp.async work list: per row 112 chunks of 16 B (64 gates, 16 h_prev, 16 dh_ext, 16 dh_ext2)
+    constexpr int NCH = (R * 112 + kGruThreads - 1) / kGruThreads;
+    auto issue = [&](int t) {
+        if (t >= 0) {
+#pragma unroll
+            for (int l = 0; l < NCH; ++l) {
+                const int c = tid + l * kGruThreads, rr = c / 112, ch = c % 112, row = row0 + rr;
+                if (c < R * 112 && row < rows) {
+                    const long long idx = (long long)(row / N) * L * N + (row % N) + (long long)t * N;
+                    float* dst = &ring[t % D][rr][0] + ch * 4;
+                    if (ch < 64) cp_async16(dst, a.gates + idx * (4 * MARL_H) + ch * 4);
+                    else if (ch < 80) { if (t > 0) cp_async16(dst, a.hidden + (idx - N) * MARL_H + (ch - 64) * 4);
+                                        else if (a.h0) cp_async16(dst, a.h0 + (long long)row * MARL_H + (ch - 64) * 4); }
+                    else if (ch < 96) { if (a.dh_ext) cp_async16(dst, a.dh_ext + idx * MARL_H + (ch - 80) * 4); }
+                    else { if (a.dh_ext2) cp_async16(dst, a.dh_ext2 + idx * MARL_H + (ch - 96) * 4); }
+                }
+            }
+        }
+        cp_async_commit();
     };
-    if (owner) fetch(L - 1, g_r, g_z, g_n, g_hn, hprev, dhe);
+    for (int idx = tid; idx < 2 * R * MARL_G; idx += kGruThreads) (&sg[0][0][0])[idx] = 0.0f;
+#pragma unroll
+    for (int d = 0; d < D - 1; ++d) issue(L - 1 - d);
+    cp_async_wait<D - 2>();
+    __syncthreads();
     int cur = 0;
     for (int t = L - 1; t >= 0; --t) {
-        float p_r = 0.f, p_z = 0.f, p_n = 0.f, p_hn = 0.f, p_hp = 0.f, p_de = 0.f;
-        if (owner && t > 0) fetch(t - 1, p_r, p_z, p_n, p_hn, p_hp, p_de);
-        float dh_dir = 0.0f;
-        if (owner) {
-            // h' = (h - n) z + n ; n = tanh(gi_n + r (W_hn h + b_hn)) ; r,z = sigmoid(...)
-            const float dh = dh_carry + dhe;
-            const float dn_pre = dh * (1.0f - g_z) * (1.0f - g_n * g_n);
-            const float dz_pre = dh * (hprev - g_n) * g_z * (1.0f - g_z);
-            const float dr_pre = dn_pre * g_hn * g_r * (1.0f - g_r);
-            const float dghn = dn_pre * g_r;
-            dh_dir = dh * g_z;
-            const long long idx = base + (long long)t * N;
-            float* pi = a.dgi + idx * MARL_G;
-            float* ph = a.dgh + idx * MARL_G;
-            pi[j] = dr_pre; pi[MARL_H + j] = dz_pre; pi[2 * MARL_H + j] = dn_pre;
-            ph[j] = dr_pre; ph[MARL_H + j] = dz_pre; ph[2 * MARL_H + j] = dghn;
-            sg[cur][ks][j] = dr_pre; sg[cur][ks][MARL_H + j] = dz_pre; sg[cur][ks][2 * MARL_H + j] = dghn;
-        }
-        __syncthreads();
-        float mine = 0.0f;
+        float dh_dir[OWN];
 #pragma unroll
-        for (int rr = 0; rr < R; ++rr) {
-            float part = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 12; ++i) {
-                float4 v = *reinterpret_cast<const float4*>(&sg[cur][rr][4 * (4 * i + ks)]);
-                part = fmaf(wt[4 * i + 0], v.x, part);
-                part = fmaf(wt[4 * i + 1], v.y, part);
-                part = fmaf(wt[4 * i + 2], v.z, part);
-                part = fmaf(wt[4 * i + 3], v.w, part);
+        for (int q = 0; q < OWN; ++q) {
+            dh_dir[q] = 0.0f;
+            if (own[q]) {
+                const int rr = ks + 2 * q;
+                const float* sl = &ring[t % D][rr][0];
+                const float g_r = sl[j], g_z = sl[MARL_H + j], g_n = sl[2 * MARL_H + j], g_hn = sl[3 * MARL_H + j];
+                const float hprev = (t > 0 || a.h0) ? sl[4 * MARL_H + j] : 0.0f;
+                float dh = dh_carry[q];
+                if (a.dh_ext) dh += sl[5 * MARL_H + j];
+                if (a.dh_ext2) dh += sl[6 * MARL_H + j];
+                // h' = (h - n) z + n ; n = tanh(gi_n + r (W_hn h + b_hn)) ; r, z = sigmoid(gi + gh)
+                const float dn_pre = dh * (1.0f - g_z) * (1.0f - g_n * g_n);
+                const float dz_pre = dh * (hprev - g_n) * g_z * (1.0f - g_z);
+                const float dr_pre = dn_pre * g_hn * g_r * (1.0f - g_r);
+                const float dghn = dn_pre * g_r;
+                dh_dir[q] = dh * g_z;
+                const long long idx = base[q] + (long long)t * N;
+                float* pi = a.dgi + idx * MARL_G;
+                float* ph = a.dgh + idx * MARL_G;
+                pi[j] = dr_pre; pi[MARL_H + j] = dz_pre; pi[2 * MARL_H + j] = dn_pre;
+                ph[j] = dr_pre; ph[MARL_H + j] = dz_pre; ph[2 * MARL_H + j] = dghn;
+                sg[cur][rr][j] = dr_pre; sg[cur][rr][MARL_H + j] = dz_pre; sg[cur][rr][2 * MARL_H + j] = dghn;
             }
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            if (rr == ks) mine = part;
         }
-        dh_carry = dh_dir + mine;
-        g_r = p_r; g_z = p_z; g_n = p_n; g_hn = p_hn; hprev = p_hp; dhe = p_de;
+        issue(t - (D - 1));              // refills the slot of step t+1, consumed before the previous barrier
+        cp_async_wait<D - 2>();          // this thread's copies for step t-1 have landed
+        __syncthreads();                 // dgh of step t visible; ring[t-1] visible
+        float part[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) part[rr] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 24; ++i)
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                const float4 v = *reinterpret_cast<const float4*>(&sg[cur][rr][4 * (2 * i + ks)]);
+                part[rr] = fmaf(wt[4 * i + 0], v.x, part[rr]);
+                part[rr] = fmaf(wt[4 * i + 1], v.y, part[rr]);
+                part[rr] = fmaf(wt[4 * i + 2], v.z, part[rr]);
+                part[rr] = fmaf(wt[4 * i + 3], v.w, part[rr]);
+            }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) part[rr] += __shfl_xor_sync(0xffffffffu, part[rr], 1);
+#pragma unroll
+        for (int q = 0; q < OWN; ++q) {
+            const int e = 2 * q, o = (2 * q + 1 < R) ? 2 * q + 1 : 2 * q;
+            dh_carry[q] = dh_dir[q] + (ks ? part[o] : part[e]);
+        }
         cur ^= 1;
     }
-    if (a.dh0 && owner) a.dh0[(long long)my_row * MARL_H + j] = dh_carry;
+    cp_async_wait<0>();
+    if (a.dh0) {
+#pragma unroll
+        for (int q = 0; q < OWN; ++q)
+            if (own[q]) a.dh0[(long long)(row0 + ks + 2 * q) * MARL_H + j] = dh_carry[q];
+    }
 }
 
-static int pick_rows_per_cta(int rows, int n_chains) {
-    // All CTAs must be co-resident (the chains are L steps long): <= 2 CTAs per SM.
-    for (int R = 1; R <= 4; R *= 2)
-        if (((rows + R - 1) / R) * n_chains <= 2 * kNumSMs) return R;
-    return 4;
+// Rows per CTA: as few as possible (shortest dependent step) while every CTA of the launch is
+// co-resident (3 CTAs of 128 threads per SM).
+static int pick_rows(int rows, int budget_ctas) {
+    for (int R = 1; R <= 8; R *= 2)
+        if ((rows + R - 1) / R <= budget_ctas) return R;
+    return 8;
 }
 
 static int check_dims(const marl_dims* d) {
@@ -297,11 +393,30 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         ga.seg[k] = GruSegment{u.gi, u.params.w_hh, u.params.b_hh, u.hidden, u.gates, u.h_last};
     }
     const int rows = d->B * d->N;
-    const int R = pick_rows_per_cta(rows, ga.n_chains);
-    dim3 grid((rows + R - 1) / R, ga.n_chains);
-    if (R == 1) { ProfScope ps_("gru_unroll_fwd_kernel", st); gru_unroll_fwd_kernel<1><<<grid, kGruThreads, 0, st>>>(ga); }
-    else if (R == 2) { ProfScope ps_("gru_unroll_fwd_kernel", st); gru_unroll_fwd_kernel<2><<<grid, kGruThreads, 0, st>>>(ga); }
-    else { ProfScope ps_("gru_unroll_fwd_kernel", st); gru_unroll_fwd_kernel<4><<<grid, kGruThreads, 0, st>>>(ga); }
+    // chain 0 (the longest: eval on o, then eval on o_next) gets the small row groups, the others twice that
+    int R0 = pick_rows(rows, ga.n_chains > 1 ? (kNumSMs * 11) / 10 : 3 * kNumSMs);
+    int R1 = R0 < 8 ? 2 * R0 : 8;
+    int cta = 0;
+    for (int c = 0; c < ga.n_chains; ++c) {
+        const int R = c == 0 ? R0 : R1;
+        ga.chain_rows_per_cta[c] = R;
+        ga.chain_cta0[c] = cta;
+        cta += (rows + R - 1) / R;
+    }
+    {
+        ProfScope ps_("gru_unroll_fwd_kernel", st);
+#define MARL_GRU_FWD(A, B_)                                                                                          \
+        do {                                                                                                         \
+            const size_t sm = gru_fwd_smem(A) > gru_fwd_smem(B_) ? gru_fwd_smem(A) : gru_fwd_smem(B_);               \
+            cudaFuncSetAttribute(gru_unroll_fwd_kernel<A, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+            gru_unroll_fwd_kernel<A, B_><<<cta, kGruThreads, sm, st>>>(ga);                                           \
+        } while (0)
+        if (R0 == 1) MARL_GRU_FWD(1, 2);
+        else if (R0 == 2) MARL_GRU_FWD(2, 4);
+        else if (R0 == 4) MARL_GRU_FWD(4, 8);
+        else MARL_GRU_FWD(8, 8);
+#undef MARL_GRU_FWD
+    }
     MARL_LAUNCH_CHECK();
     // phase C
     for (int i = 0; i < n_streams; ++i) {
@@ -337,11 +452,20 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
     GruBwdArgs ga{a->gates, a->hidden, a->dq ? a->dhext : nullptr, a->dhidden, a->params.w_hh, a->h0, a->dgi, a->dgh, a->dh0,
                   d->B, d->L, d->N};
     const int rows = d->B * d->N;
-    const int R = pick_rows_per_cta(rows, 1);
-    dim3 grid((rows + R - 1) / R);
-    if (R == 1) { ProfScope ps_("gru_unroll_bwd_kernel", st); gru_unroll_bwd_kernel<1><<<grid, kGruThreads, 0, st>>>(ga); }
-    else if (R == 2) { ProfScope ps_("gru_unroll_bwd_kernel", st); gru_unroll_bwd_kernel<2><<<grid, kGruThreads, 0, st>>>(ga); }
-    else { ProfScope ps_("gru_unroll_bwd_kernel", st); gru_unroll_bwd_kernel<4><<<grid, kGruThreads, 0, st>>>(ga); }
+    const int R = pick_rows(rows, 3 * kNumSMs);
+    {
+        ProfScope ps_("gru_unroll_bwd_kernel", st);
+#define MARL_GRU_BWD(A)                                                                                              \
+        do {                                                                                                         \
+            cudaFuncSetAttribute(gru_unroll_bwd_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gru_bwd_smem(A)); \
+            gru_unroll_bwd_kernel<A><<<(rows + A - 1) / A, kGruThreads, gru_bwd_smem(A), st>>>(ga);                    \
+        } while (0)
+        if (R == 1) MARL_GRU_BWD(1);
+        else if (R == 2) MARL_GRU_BWD(2);
+        else if (R == 4) MARL_GRU_BWD(4);
+        else MARL_GRU_BWD(8);
+#undef MARL_GRU_BWD
+    }
     MARL_LAUNCH_CHECK();
     {   // dW_hh += dgh^T . h_{t-1} (hidden shifted by one step, zeros at t = 0) ; db_hh
         LinearWgrad w{};

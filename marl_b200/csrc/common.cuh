@@ -62,26 +62,4 @@ __device__ __forceinline__ float lin_load(const LinOperand& a, int z, int m, int
 
 __host__ __device__ __forceinline__ int lin_width(const LinOperand& a) { return a.K1 + a.K2 + a.onehot_mod; }
 
-// 64x64x16 register-tiled FP32 GEMM micro-kernel state (256 threads, 4x4 outputs per thread).
-constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4, GEMM_THREADS = 256;
-
-struct TileSmem {
-    float a[BK][BM + 4];
-    float b[BK][BN + 4];
-};
-
-__device__ __forceinline__ void tile_fma(const TileSmem& s, float (&acc)[TM][TN], int ty, int tx) {
-#pragma unroll
-    for (int k = 0; k < BK; ++k) {
-        float4 av = *reinterpret_cast<const float4*>(&s.a[k][ty * TM]);
-        float4 bv = *reinterpret_cast<const float4*>(&s.b[k][tx * TN]);
-        float a_[4] = {av.x, av.y, av.z, av.w};
-        float b_[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-        for (int i = 0; i < TM; ++i)
-#pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a_[i], b_[j], acc[i][j]);
-    }
-}
-
 }  // namespace marl

@@ -96,3 +96,26 @@ def argmax_mismatches(a_star_mine, q_masked_oracle, a_star_oracle, noise=1e-5):
         if gap > noise * scale:
             hard += 1
     return len(bad), hard
+
+
+def params_close(mine, ref, lr, n_steps, report=None, what=""):
+    """Updated-parameter check that is robust to RMSprop/Adam noise amplification.
+
+    The first optimiser steps divide g by ~|g| (v starts at 0), so an entry whose gradient is at the
+    fp32 noise level can move by up to ~10*lr per step in EITHER implementation (the fp32 reference
+    sits 2.5e-5 max-norm from its own fp64 run at the 2s3z shape, tools/diag_parity.py).  Therefore:
+    (a) every entry within 1e-5*max|ref| + 0.1*lr*n_steps, and (b) for big tensors at most 1% of the
+    entries beyond the strict 1e-5 bound.  The strict functional check of the update is the loss of the
+    NEXT step, which the callers compare at 1e-5 / 5e-5."""
+    x = np.asarray(mine.detach().cpu() if torch.is_tensor(mine) else mine, dtype=np.float64).reshape(-1)
+    y = np.asarray(ref.detach().cpu() if torch.is_tensor(ref) else ref, dtype=np.float64).reshape(-1)
+    if y.size == 0:
+        return True
+    scale = max(float(np.max(np.abs(y))), 1e-30)
+    diff = np.abs(x - y)
+    ok = bool(diff.max() <= 1e-5 * scale + 0.1 * lr * n_steps)
+    if y.size >= 1000:
+        ok = ok and float((diff > 1e-5 * scale).mean()) <= 0.01
+    if not ok and report is not None:
+        report.append(f"{what}: max diff {diff.max():.3e} (scale {scale:.3e}), frac beyond 1e-5: {(diff > 1e-5 * scale).mean():.4f}")
+    return ok
