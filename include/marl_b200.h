@@ -135,7 +135,8 @@ int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* a, void* st
 int marl_q_select(const marl_dims* d, const float* q_evals, const long long* u, const float* q_evals_next,
                   float* q_targets, const float* avail_u_next, const float* avail_u /*nullable*/,
                   float* q_chosen, long long* a_star /*nullable*/, float* q_targets_chosen,
-                  float* max_q_evals /*nullable*/, float* q_targets_max /*nullable*/, void* stream);
+                  float* max_q_evals /*nullable*/, float* q_targets_max /*nullable*/,
+                  float* a_star_onehot /*nullable, [B,L,N,A] one-hot of a* (q_learner.py:140-143)*/, void* stream);
 
 /* ---- TD target + masked MSE: algorithm/q_learner.py:165-168 ----
  * y = r + gamma*q_tot_target*(1-terminated); d = (1-padded)*(y - q_tot);
@@ -170,6 +171,73 @@ int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* p, const ma
                          const long long* u, const float* r, const float* terminated, const float* padded, float gamma,
                          float* hy, float* hy_target, float* dhy, float* q_tot, float* q_tot_target,
                          float* dq, const marl_qmix_grads* g, float* scalars, void* stream);
+
+/* ---- QPLEX: DMAQer + DMAQ_SI_Weight, network/mixer.py:85-288 (adv_hypernet_layers = 3) ----
+ * Parameters are passed layer-concatenated (the host lays them out that way), K = num_kernel,
+ * he = hypernet_embed, ae = adv_hypernet_embed:
+ *   w1s [2he + 2K*ae, S]  rows: hyper_w_final.0 | V.0 | key_extractors.k.0 (k=0..K-1) | agents_extractors.k.0
+ *   w1a [K*ae, S + N*A]   action_extractors.k.0        (input = [states | actions], never materialised)
+ *   w2  [3K, ae, ae]      key.k.2 | agents.k.2 | action.k.2
+ *   w3k [K, ae]           key.k.4          w3n [2K, N, ae]  agents.k.4 | action.k.4
+ *   wfv [2, N, he]        hyper_w_final.2 | V.2            (biases b* in the same order)
+ * Workspaces (kept for the backward): h1 [M, 2he + 3K*ae], h2 [M, 3K*ae], o3 [M, K + 2K*N], wv [M, 2N]. */
+typedef struct marl_qplex_dims { int N, A, S, he, ae, K, weighted_head, is_minus_one; } marl_qplex_dims;
+typedef struct marl_qplex_params {
+    const float *w1s, *b1s, *w1a, *b1a, *w2, *b2, *w3k, *b3k, *w3n, *b3n, *wfv, *bfv;
+} marl_qplex_params;
+typedef struct marl_qplex_grads { float *w1s, *b1s, *w1a, *b1a, *w2, *b2, *w3k, *b3k, *w3n, *b3n, *wfv, *bfv; } marl_qplex_grads;
+typedef struct marl_qplex_ws { float *h1, *h2, *o3, *wv; } marl_qplex_ws;
+
+/* DMAQer.forward for M samples: v_tot = sum_n (w q + v)  (is_v=True, mixer.py:211-220) and, when `actions`
+ * [M, N*A] and max_q [M,N] are given, a_tot = sum_n adv (lambda - 1) with adv = (w q + v) - (w max_q + v)
+ * detached (calc_adv, mixer.py:222-247).  q_tot = v_tot + a_tot.  Any of the three outputs may be NULL. */
+int marl_qplex_fwd(int M, const marl_qplex_dims* d, const marl_qplex_params* p, const float* q, const float* s,
+                   const float* actions, const float* max_q, const marl_qplex_ws* ws,
+                   float* v_tot, float* a_tot, float* q_tot, void* stream);
+/* Backward for dL/dv_tot and dL/da_tot (either may be NULL; the learner passes dL/dq_tot for both):
+ * dq [M,N] and accumulated parameter gradients.  a_tot trains only the lambda heads (adv is detached).
+ * dws: workspaces for d(h1), d(h2), d(o3), d(wv), same shapes as ws. */
+int marl_qplex_bwd(int M, const marl_qplex_dims* d, const marl_qplex_params* p, const float* q, const float* s,
+                   const float* actions, const float* max_q, const marl_qplex_ws* ws, const float* dv_tot,
+                   const float* da_tot, const marl_qplex_ws* dws, float* dq, const marl_qplex_grads* g, void* stream);
+/* dq_dense [B,L,N,A] = dq_small [B,L,N] scattered to the chosen action u (autograd of gather, q_learner.py:100). */
+int marl_scatter_dq(const marl_dims* d, const float* dq_small, const long long* u, float* dq_dense, void* stream);
+
+/* ---- QTRAN-base: QtranQBase / QtranV (network/mixer.py:355-418) ----
+ * One "joint net" shape serves both: per-agent encoder Linear(D,D)-ReLU-Linear(D,D) on rows
+ * [hidden | action one-hot] (D = H + A_enc; A_enc = 0 for QtranV), sum over agents, head
+ * Linear(S+D,qh)-ReLU-Linear(qh,qh)-ReLU-Linear(qh,1) on [state | encoding].
+ *   QtranQBase: we1/we2 = hidden_action_encoding.{0,2}, w0/w2/w4 = q.{0,2,4}
+ *   QtranV    : we1/we2 = hidden_encoding.{0,2},        w0/w2/w4 = v.{0,2,4}
+ * Workspaces (kept for the backward): e1 [M*N, D], es [M, D], enc [M, D], a1 [M, qh], a2 [M, qh]. */
+typedef struct marl_qtran_net_params { const float *we1, *be1, *we2, *be2, *w0, *b0, *w2, *b2, *w4, *b4; } marl_qtran_net_params;
+typedef struct marl_qtran_net_grads { float *we1, *be1, *we2, *be2, *w0, *b0, *w2, *b2, *w4, *b4; } marl_qtran_net_grads;
+typedef struct marl_qtran_net_ws { float *e1, *es, *enc, *a1, *a2; } marl_qtran_net_ws;
+
+/* out[M] = net(s [M,S], hidden [M*N,H], actions [M*N,A_enc] or NULL). */
+int marl_qtran_net_fwd(int M, int N, int S, int A_enc, int qh, const marl_qtran_net_params* p, const float* s,
+                       const float* hidden, const float* actions, const marl_qtran_net_ws* ws, float* out, void* stream);
+/* Given dout[M]: accumulated parameter gradients and dL/dhidden [M*N,H] (written, or added when
+ * accumulate_dhidden != 0; NULL to skip).  dws: same shapes as ws. */
+int marl_qtran_net_bwd(int M, int N, int S, int A_enc, int qh, const marl_qtran_net_params* p, const float* s,
+                       const float* hidden, const float* actions, const marl_qtran_net_ws* ws, const float* dout,
+                       const marl_qtran_net_ws* dws, float* dhidden, int accumulate_dhidden,
+                       const marl_qtran_net_grads* g, void* stream);
+/* Greedy actions (algorithm/qtran_learner.py:103-114,129,143): eval side masked with -999999 by avail_u,
+ * target side masked IN PLACE with -9999999 by avail_u_next; one-hots of both argmaxes, the eval argmax,
+ * max_a of the masked eval Q and the Q of the taken action. */
+int marl_qtran_select(const marl_dims* d, const float* q_evals, float* q_targets, const float* avail_u,
+                      const float* avail_u_next, const long long* u, float* opt_onehot_eval, float* opt_onehot_target,
+                      long long* opt_action_eval, float* q_max_eval, float* q_taken, void* stream);
+/* L_td + lambda_opt L_opt + lambda_nopt L_nopt (qtran_learner.py:116-152) and its gradients w.r.t.
+ * joint_q (d_joint_q [M]), v (d_v [M]) and the individual Q-values (dq [B,L,N,A]); UN-normalised like
+ * marl_td_loss: scalars += {loss_sum, mask_sum}; loss_parts += {sum l_td, sum l_opt, sum l_nopt}. */
+int marl_qtran_losses_fwd_bwd(const marl_dims* d, const float* joint_q, const float* joint_q_target,
+                              const float* joint_q_hat, const float* v, const float* q_max_eval, const float* q_taken,
+                              const long long* opt_action_eval, const long long* u, const float* avail_u, const float* r,
+                              const float* terminated, const float* padded, float gamma, float lambda_opt,
+                              float lambda_nopt, float* d_joint_q, float* d_v, float* dq, float* scalars,
+                              float* loss_parts, void* stream);
 
 /* ---- clip_grad_norm_ + optimiser: algorithm/q_learner.py:172-173 ----
  * grads holds d/dtheta of the UN-normalised loss sum; scalars = {loss_sum, mask_sum} (after the

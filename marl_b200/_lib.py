@@ -66,6 +66,40 @@ class QmixGrads(C.Structure):
     _fields_ = [(k, c_ptr) for k in ("wcat", "bcat", "wb2", "bb2")]
 
 
+class QplexDims(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("N", "A", "S", "he", "ae", "K", "weighted_head", "is_minus_one")]
+
+
+QPLEX_FIELDS = ("w1s", "b1s", "w1a", "b1a", "w2", "b2", "w3k", "b3k", "w3n", "b3n", "wfv", "bfv")
+
+
+class QplexParams(C.Structure):
+    _fields_ = [(k, c_ptr) for k in QPLEX_FIELDS]
+
+
+class QplexGrads(C.Structure):
+    _fields_ = [(k, c_ptr) for k in QPLEX_FIELDS]
+
+
+class QplexWs(C.Structure):
+    _fields_ = [(k, c_ptr) for k in ("h1", "h2", "o3", "wv")]
+
+
+QTRAN_FIELDS = ("we1", "be1", "we2", "be2", "w0", "b0", "w2", "b2", "w4", "b4")
+
+
+class QtranNetParams(C.Structure):
+    _fields_ = [(k, c_ptr) for k in QTRAN_FIELDS]
+
+
+class QtranNetGrads(C.Structure):
+    _fields_ = [(k, c_ptr) for k in QTRAN_FIELDS]
+
+
+class QtranNetWs(C.Structure):
+    _fields_ = [(k, c_ptr) for k in ("e1", "es", "enc", "a1", "a2")]
+
+
 _P = C.POINTER
 _SIGNATURES = {
     "marl_version": ([], C.c_int),
@@ -77,13 +111,22 @@ _SIGNATURES = {
     "marl_fma_probe": ([c_ptr, C.c_int, C.c_int, _P(C.c_double), c_ptr], C.c_int),
     "marl_agent_unroll_fwd": ([_P(Dims), _P(UnrollStream), C.c_int, c_ptr], C.c_int),
     "marl_agent_unroll_bwd": ([_P(Dims), _P(UnrollBwd), c_ptr], C.c_int),
-    "marl_q_select": ([_P(Dims)] + [c_ptr] * 11 + [c_ptr], C.c_int),
+    "marl_q_select": ([_P(Dims)] + [c_ptr] * 12 + [c_ptr], C.c_int),
     "marl_td_loss": ([C.c_int] + [c_ptr] * 5 + [C.c_float, c_ptr, c_ptr, c_ptr], C.c_int),
     "marl_vdn_td_fwd_bwd": ([_P(Dims)] + [c_ptr] * 6 + [C.c_float] + [c_ptr] * 4 + [c_ptr], C.c_int),
     "marl_qmix_fwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "marl_qmix_bwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams)] + [c_ptr] * 6 + [_P(QmixGrads), c_ptr], C.c_int),
     "marl_qmix_td_fwd_bwd": ([_P(Dims), _P(QmixParams), _P(QmixParams)] + [c_ptr] * 8 + [C.c_float] + [c_ptr] * 6
                              + [_P(QmixGrads), c_ptr, c_ptr], C.c_int),
+    "marl_qplex_fwd": ([C.c_int, _P(QplexDims), _P(QplexParams)] + [c_ptr] * 4 + [_P(QplexWs)] + [c_ptr] * 4, C.c_int),
+    "marl_qplex_bwd": ([C.c_int, _P(QplexDims), _P(QplexParams)] + [c_ptr] * 4 + [_P(QplexWs), c_ptr, c_ptr, _P(QplexWs), c_ptr,
+                       _P(QplexGrads), c_ptr], C.c_int),
+    "marl_scatter_dq": ([_P(Dims), c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
+    "marl_qtran_net_fwd": ([C.c_int] * 5 + [_P(QtranNetParams), c_ptr, c_ptr, c_ptr, _P(QtranNetWs), c_ptr, c_ptr], C.c_int),
+    "marl_qtran_net_bwd": ([C.c_int] * 5 + [_P(QtranNetParams), c_ptr, c_ptr, c_ptr, _P(QtranNetWs), c_ptr, _P(QtranNetWs),
+                           c_ptr, C.c_int, _P(QtranNetGrads), c_ptr], C.c_int),
+    "marl_qtran_select": ([_P(Dims)] + [c_ptr] * 10 + [c_ptr], C.c_int),
+    "marl_qtran_losses_fwd_bwd": ([_P(Dims)] + [c_ptr] * 12 + [C.c_float] * 3 + [c_ptr] * 5 + [c_ptr], C.c_int),
     "marl_optim_partials": ([], C.c_int),
     "marl_profile_enable": ([C.c_int], C.c_int),
     "marl_profile_collect": ([C.c_char_p, C.c_int], C.c_int),

@@ -27,7 +27,7 @@ import numpy as np
 import torch as th
 
 from .. import _lib as L
-from ..flat import FlatBuffer
+from ..flat import FlatBuffer, prefixed
 from ..network.mixer import VDNMixer, QMixMixer, qmix_struct
 from ..network.q_network import agent_param_struct, AGENT_FLAT_ORDER
 
@@ -82,6 +82,7 @@ class QLearner:
         self.mixer = self._make_mixer(args)
         self.target_mixer = copy.deepcopy(self.mixer)
         self.params += list(self.mixer.parameters())
+        self._build_extra(args)
         if args.optimizer not in ("RMS", "Adam"):
             raise ValueError("optimizer {} not recognised.".format(args.optimizer))
 
@@ -108,23 +109,34 @@ class QLearner:
     def _pack(self):
         """All optimised tensors into one flat buffer (+grad +2 tail scalars); targets mirror it."""
         dev = self._dev
-        named = [("agent." + n, p) for n, p in self.eval_net.agent.flat_named_parameters()]
-        named += [("mixer." + n, p) for n, p in self.mixer.flat_named_parameters()]
+        named = prefixed("agent.", self.eval_net.agent.flat_named_parameters())
+        named += prefixed("mixer.", self.mixer.flat_named_parameters())
+        for prefix, module in self._extra_groups():
+            named += prefixed(prefix, module.flat_named_parameters())
         self._flat = FlatBuffer(named, device=dev, with_grad=True, extra_tail=2)
-        tnamed = [("agent." + n, p) for n, p in self.target_net.agent.flat_named_parameters()]
-        tnamed += [("mixer." + n, p) for n, p in self.target_mixer.flat_named_parameters()]
+        tnamed = prefixed("agent.", self.target_net.agent.flat_named_parameters())
+        tnamed += prefixed("mixer.", self.target_mixer.flat_named_parameters())
         self._tflat = FlatBuffer(tnamed, device=dev, with_grad=False)
         self.eval_net.agent.adopt(self._flat)
         self.target_net.agent.adopt(self._tflat)
         if hasattr(self.mixer, "adopt"):
             self.mixer.adopt(self._flat)
             self.target_mixer.adopt(self._tflat)
+        for _, module in self._extra_groups():
+            module.adopt(self._flat)
         self.optimizer = _FlatOptimizer(self.args.optimizer, self.lr, self._flat, dev)
         self._partials = th.zeros(L.load().marl_optim_partials() if os.path.exists(L.LIB_PATH) else 148,
                                   dtype=th.float32, device=dev)
         self._loss_out = th.zeros(2, dtype=th.float32, device=dev)
         self._loss_host = th.zeros(2, dtype=th.float32).pin_memory() if dev.type == "cuda" else th.zeros(2)
         self._ws, self._graphs = {}, {}
+
+    def _build_extra(self, args):
+        """Hook: networks created after the mixer, in the reference's construction order."""
+
+    def _extra_groups(self):
+        """(prefix, module) pairs optimised besides the agent and the mixer (QTRAN: the V network)."""
+        return []
 
     def cuda(self):
         self._dev = th.device("cuda")
@@ -172,6 +184,10 @@ class QLearner:
         if a.alg == "qmix":
             Ccols = N * 32 + 96
             ws.update(hy=f(M, Ccols), hy_t=f(M, Ccols), dhy=f(M, Ccols))
+        if a.alg == "qplex":
+            from ..network.qplex import qplex_workspace
+            ws.update(qp=qplex_workspace(M, a, dev), qp_t=qplex_workspace(M, a, dev), dqp=qplex_workspace(M, a, dev),
+                      max_q=f(B, Lq, N), qt_max=f(B, Lq, N), oh_star=f(B, Lq, N, A), dq_tot=f(M), dq_small=f(B, Lq, N))
         self._ws[key] = ws
         return ws
 
@@ -281,9 +297,12 @@ class QLearner:
             fill(2, bt["o_next"], 0, pe, 0, None)                     # eval net on o_next, hidden carried (:110)
         L.call("marl_agent_unroll_fwd", C.byref(d), arr, n_streams, sp)
         n_launch += 3 * n_streams + 1
+        qplex = a.alg == "qplex"
         L.call("marl_q_select", C.byref(d), ws["q"][0].data_ptr(), bt["u"].data_ptr(),
-               ws["q"][2].data_ptr() if double_q else None, ws["q"][1].data_ptr(), bt["avail_u_next"].data_ptr(), None,
-               ws["q_chosen"].data_ptr(), ws["a_star"].data_ptr(), ws["q_tc"].data_ptr(), None, None, sp)
+               ws["q"][2].data_ptr() if double_q else None, ws["q"][1].data_ptr(), bt["avail_u_next"].data_ptr(),
+               bt["avail_u"].data_ptr() if qplex else None, ws["q_chosen"].data_ptr(), ws["a_star"].data_ptr(),
+               ws["q_tc"].data_ptr(), ws["max_q"].data_ptr() if qplex else None,
+               ws["qt_max"].data_ptr() if qplex else None, ws["oh_star"].data_ptr() if qplex else None, sp)
         n_launch += 1
         scalars = self._flat.tail.data_ptr()
         if a.alg == "vdn":
@@ -304,6 +323,33 @@ class QLearner:
                    ws["hy_t"].data_ptr(), ws["dhy"].data_ptr(), ws["q_tot"].data_ptr(), ws["q_tot_t"].data_ptr(),
                    ws["dq"].data_ptr(), C.byref(g), scalars, sp)
             n_launch += 4
+        elif a.alg == "qplex":
+            from ..network.qplex import qplex_struct, qplex_dims, ws_struct
+            M = B * Lq
+            qd = qplex_dims(a)
+            K = a.num_kernel
+            p = qplex_struct(lambda n: self._flat.ptr("mixer." + n), K)
+            ptg = qplex_struct(lambda n: self._tflat.ptr("mixer." + n), K)
+            g = qplex_struct(lambda n: self._flat.ptr("mixer." + n, self._flat.grad), K, L.QplexGrads)
+            wse, wst, dws = ws_struct(ws["qp"]), ws_struct(ws["qp_t"]), ws_struct(ws["dqp"])
+            # q_tot = v_tot + a_tot (q_learner.py:120-135); target likewise with the eval net's argmax (:138-158)
+            L.call("marl_qplex_fwd", M, C.byref(qd), C.byref(p), ws["q_chosen"].data_ptr(), bt["s"].data_ptr(),
+                   bt["u_onehot"].data_ptr(), ws["max_q"].data_ptr(), C.byref(wse), None, None, ws["q_tot"].data_ptr(), sp)
+            if double_q:
+                L.call("marl_qplex_fwd", M, C.byref(qd), C.byref(ptg), ws["q_tc"].data_ptr(), bt["s_next"].data_ptr(),
+                       ws["oh_star"].data_ptr(), ws["qt_max"].data_ptr(), C.byref(wst), None, None,
+                       ws["q_tot_t"].data_ptr(), sp)
+            else:
+                L.call("marl_qplex_fwd", M, C.byref(qd), C.byref(ptg), ws["q_tc"].data_ptr(), bt["s_next"].data_ptr(),
+                       None, None, C.byref(wst), ws["q_tot_t"].data_ptr(), None, None, sp)
+            L.call("marl_td_loss", M, ws["q_tot"].data_ptr(), ws["q_tot_t"].data_ptr(), bt["r"].data_ptr(),
+                   bt["terminated"].data_ptr(), bt["padded"].data_ptr(), float(self.gamma), ws["dq_tot"].data_ptr(),
+                   scalars, sp)
+            L.call("marl_qplex_bwd", M, C.byref(qd), C.byref(p), ws["q_chosen"].data_ptr(), bt["s"].data_ptr(),
+                   bt["u_onehot"].data_ptr(), ws["max_q"].data_ptr(), C.byref(wse), ws["dq_tot"].data_ptr(),
+                   ws["dq_tot"].data_ptr(), C.byref(dws), ws["dq_small"].data_ptr(), C.byref(g), sp)
+            L.call("marl_scatter_dq", C.byref(d), ws["dq_small"].data_ptr(), bt["u"].data_ptr(), ws["dq"].data_ptr(), sp)
+            n_launch += 7 + (7 if double_q else 2) + 1 + 12 + 1
         else:
             raise NotImplementedError(a.alg)
         bw = L.UnrollBwd()
@@ -402,7 +448,8 @@ class QLearner:
         return float(self._loss_host[0])
 
     def _update_targets(self):
-        self._tflat.data.copy_(self._flat.data)
+        # targets mirror the leading [agent | mixer] region of the flat buffer: one D2D copy
+        self._tflat.data.copy_(self._flat.data[:self._tflat.numel])
 
     # ---- checkpoints -------------------------------------------------------------------------------------
     def save_models(self, train_step):

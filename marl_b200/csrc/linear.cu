@@ -157,8 +157,9 @@ __global__ void __launch_bounds__(GT) linear_fwd_kernel(LinearFwd a) {
     const float* bias = a.bias ? a.bias + (long long)z * a.b_bs : nullptr;
     float* y = a.y + (long long)z * a.y_bs;
     float bv[4];
+    const float bmul = a.bias_mul != 0.f ? a.bias_mul : 1.0f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { const int n = n0 + tx * 4 + j; bv[j] = (bias && n < a.N) ? __ldg(bias + n) : 0.f; }
+    for (int j = 0; j < 4; ++j) { const int n = n0 + tx * 4 + j; bv[j] = (bias && n < a.N) ? bmul * __ldg(bias + n) : 0.f; }
     const bool vec_out = ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && !a.accumulate;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -227,7 +228,8 @@ __global__ void __launch_bounds__(GT) linear_wgrad_kernel(LinearWgrad a, int spl
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     if (a.db != nullptr && blockIdx.y == 0) {
         gemm_loop<false, false, true>(s, acc, fa, fb, i0, j0, mbeg, mend, bsum);
-        if (tid < GM && i0 + tid < a.N) atomicAdd(a.db + (long long)zb * a.db_bs + i0 + tid, bsum);
+        if (tid < GM && i0 + tid < a.N)
+            atomicAdd(a.db + (long long)zb * a.db_bs + i0 + tid, (a.db_mul != 0.f ? a.db_mul : 1.0f) * bsum);
     } else {
         gemm_loop<false, false, false>(s, acc, fa, fb, i0, j0, mbeg, mend, bsum);
     }

@@ -11,6 +11,7 @@ struct LinearFwd {
     const float* bias;           long long b_bs;   // nullable
     float* y;          int ldy;  long long y_bs;
     int M, N;
+    float bias_mul;   // bias is added as bias_mul * bias (0 means 1): sum over agents of a per-agent Linear
     int relu;         // apply max(0, .) in the epilogue
     int accumulate;   // y += result instead of y = result
     int batch;        // independent problems over blockIdx.z (operands advance by *_bs)
@@ -33,6 +34,7 @@ struct LinearWgrad {
     LinOperand in;
     float* dw;         int ldw;  long long dw_bs;
     float* db;                   long long db_bs;   // nullable
+    float db_mul;     // db += db_mul * colsum(dy) (0 means 1)
     int M, N;
     int batch;
 };

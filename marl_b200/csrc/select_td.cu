@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(256) q_select_kernel(
     const float* __restrict__ q_evals_next, float* __restrict__ q_targets,
     const float* __restrict__ avail_next, const float* __restrict__ avail,
     float* __restrict__ q_chosen, long long* __restrict__ a_star, float* __restrict__ q_tc,
-    float* __restrict__ max_q_evals, float* __restrict__ q_targets_max) {
+    float* __restrict__ max_q_evals, float* __restrict__ q_targets_max, float* __restrict__ a_star_onehot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
     const long long o = (long long)i * A;
@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(256) q_select_kernel(
     }
     q_tc[i] = q_evals_next ? tsel : tmax;                              // q_learner.py:114 / :117
     if (a_star) a_star[i] = q_evals_next ? best : -1;
+    if (a_star_onehot)                                                 // q_learner.py:140-143
+        for (int a = 0; a < A; ++a) a_star_onehot[o + a] = (q_evals_next && a == best) ? 1.0f : 0.0f;
     if (q_targets_max) q_targets_max[i] = tmax;                        // q_learner.py:150
     if (max_q_evals) {                                                 // q_learner.py:125-127
         float m = 0.f;
@@ -124,14 +126,14 @@ using namespace marl;
 extern "C" int marl_q_select(const marl_dims* d, const float* q_evals, const long long* u, const float* q_evals_next,
                              float* q_targets, const float* avail_u_next, const float* avail_u, float* q_chosen,
                              long long* a_star, float* q_targets_chosen, float* max_q_evals, float* q_targets_max,
-                             void* stream) {
+                             float* a_star_onehot, void* stream) {
     if (!d || !q_targets || !avail_u_next || !q_targets_chosen) return MARL_EINVAL;
     if (q_chosen && (!q_evals || !u)) return MARL_EINVAL;
     if (max_q_evals && (!avail_u || !q_evals)) return MARL_EINVAL;
     const int rows = d->B * d->L * d->N;
     if (rows <= 0) return MARL_OK;
     { ProfScope ps_("q_select_kernel", (cudaStream_t)stream); q_select_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, d->A, q_evals, u, q_evals_next, q_targets,
-        avail_u_next, avail_u, q_chosen, a_star, q_targets_chosen, max_q_evals, q_targets_max); }
+        avail_u_next, avail_u, q_chosen, a_star, q_targets_chosen, max_q_evals, q_targets_max, a_star_onehot); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }

@@ -21,14 +21,20 @@ class FlatBuffer:
     """Packs ``[(name, parameter)]`` into one buffer, in the given order."""
 
     def __init__(self, named_params, device=None, with_grad=True, extra_tail=0):
-        named_params = list(named_params)
+        # entries are (name, param) -- start aligned to 16 bytes -- or (name, param, "tight"): placed
+        # directly behind its predecessor (layer-concatenated groups that one GEMM reads as one matrix)
+        entries = [(e[0], e[1], len(e) > 2 and e[2] == "tight") for e in named_params]
+        named_params = [(n, p) for n, p, _ in entries]
         self.names = [n for n, _ in named_params]
         self.params = [p for _, p in named_params]
         device = device if device is not None else (self.params[0].device if self.params else torch.device("cpu"))
         self.offsets, off = {}, 0
-        for n, p in named_params:
+        for n, p, tight in entries:
+            if not tight:
+                off = _round_up(off)
             self.offsets[n] = off
-            off += _round_up(p.numel())
+            off += p.numel()
+        off = _round_up(off)
         self.numel = off
         self.data = torch.zeros(off, dtype=torch.float32, device=device)
         # gradient buffer carries `extra_tail` trailing floats (loss_sum, mask_sum) for the all-reduce
@@ -59,3 +65,8 @@ class FlatBuffer:
         for n, p in zip(self.names, self.params):
             o = self.offsets[n]
             p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+
+def prefixed(prefix, entries):
+    """Prefix the names of FlatBuffer entries, keeping their packing markers."""
+    return [(prefix + e[0],) + tuple(e[1:]) for e in entries]

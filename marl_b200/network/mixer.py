@@ -131,3 +131,6 @@ class QMixMixer(nn.Module):
 
 # north_star alias (pymarl spelling): QMixer.forward(agent_qs, states)
 QMixer = QMixMixer
+
+from .qplex import DMAQ_SI_Weight, DMAQer  # noqa: E402,F401  (reference: network/mixer.py:85-288)
+from .qtran import QtranQBase, QtranV  # noqa: E402,F401      (reference: network/mixer.py:355-418)
