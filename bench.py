@@ -129,12 +129,15 @@ def run_reference(opt):
     print(json.dumps(line))
 
 
-def bench_env(torch, L, n_envs, iters, hbm_peak):
+def bench_env(torch, dist, world, n_envs, iters, hbm_peak):
+    """n_envs independent matrix games PER GPU (env instances shard over ranks, no collective)."""
     from marl_b200.env.single_state_matrix_game import BatchedMatrixGame
     env = BatchedMatrixGame(PAYOFF1, n_envs)
     acts = torch.randint(0, 3, (n_envs, 2), device="cuda", dtype=torch.int64)
     for _ in range(5):
         env.step(acts)
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -142,12 +145,15 @@ def bench_env(torch, L, n_envs, iters, hbm_peak):
         env.step(acts)
     b.record()
     torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / iters
-    rate = n_envs / (ms * 1e-3)
-    gbs = rate * ENV_BYTES / 1e9
-    return {"n_envs": n_envs, "value": rate, "unit": "env-steps/s", "us_per_launch": ms * 1e3,
+    ms = torch.tensor([a.elapsed_time(b) / iters], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    rate = n_envs * world / (ms * 1e-3)
+    gbs = rate / world * ENV_BYTES / 1e9
+    return {"n_envs_per_gpu": n_envs, "value": rate, "unit": "env-steps/s", "us_per_launch": ms * 1e3,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                         "traffic": None}}
+                         "traffic": None, "note": "per GPU"}}
 
 
 def run_ours(opt):
@@ -233,21 +239,21 @@ def run_ours(opt):
     ms_dev, ms_e2e = float(ms_dev) / K, float(ms_e2e) / K
     launches = learner.launches_per_step + 1          # + the ingest launch
 
+    # ---- per-kernel device time (eager pass, CUDA events around every launch of the library) ---------
+    learner._use_graph = False
+    L.profile(rank == 0)
+    P = 10
+    for i in range(P):
+        learner.train(dev_batches[i % NB], step); step += 1
+    prof = L.profile_collect() if rank == 0 else {}
+    L.profile(False)
+    learner._use_graph = True
+    env_small = bench_env(torch, dist, world, 4096, 200, hbm_peak)
+    env_big = bench_env(torch, dist, world, 1 << 24, 20, hbm_peak)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-
-    # ---- per-kernel device time (eager pass, CUDA events around every launch of the library) ---------
-    learner._use_graph = False
-    L.profile(True)
-    P = 10
-    for i in range(P):
-        if world == 1:
-            learner.train(dev_batches[i % NB], step); step += 1
-    prof = L.profile_collect() if world == 1 else {}
-    L.profile(False)
-    learner._use_graph = True
     tot_ms = sum(ms for _, ms in prof.values()) or 1.0
     kernels = {k: {"launches_per_step": c / P, "us_per_step": ms * 1e3 / P, "share": ms / tot_ms}
                for k, (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
@@ -278,8 +284,6 @@ def run_ours(opt):
             roofline = {"kernel": dom, "bound": "fp32_fma", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                         "frac": ach / fp32_peak, "traffic": None, "us_per_launch": dom_us}
     step_tflops = FLOP_PER_STEP / (ms_dev * 1e-3) / 1e12
-    env_small = bench_env(torch, L, 4096, 200, hbm_peak)
-    env_big = bench_env(torch, L, 1 << 24, 20, hbm_peak)
 
     cpu = None
     if world == 1:

@@ -28,6 +28,7 @@ import torch as th
 
 from .. import _lib as L
 from ..flat import FlatBuffer, prefixed
+from ..parallel import shard_bounds, allreduce_flat
 from ..network.mixer import VDNMixer, QMixMixer, qmix_struct
 from ..network.q_network import agent_param_struct, AGENT_FLAT_ORDER
 
@@ -262,11 +263,7 @@ class QLearner:
         if self._dist is None:
             return 0, B_glob
         dist, group = self._dist
-        g, r = dist.get_world_size(group), dist.get_rank(group)
-        per = B_glob // g
-        if per * g != B_glob:
-            raise ValueError("data-parallel training needs the batch size to be a multiple of the world size")
-        return r * per, (r + 1) * per
+        return shard_bounds(B_glob, dist.get_world_size(group), dist.get_rank(group))
 
     # ---- the device step -----------------------------------------------------------------------------
     def _agent_structs(self, flat, prefix="agent."):
@@ -382,7 +379,7 @@ class QLearner:
         if self._dist is not None:
             n = self._launch_forward_backward(bt, ws, B, Lq)
             dist, group = self._dist
-            dist.all_reduce(self._flat.grad_full, group=group)
+            allreduce_flat(self._flat.grad_full, dist, group)
             return n + self._launch_optimizer()
         return self._launch_forward_backward(bt, ws, B, Lq) + self._launch_optimizer()
 
@@ -416,7 +413,7 @@ class QLearner:
         else:
             dist, group = self._dist
             entry[0].replay()
-            dist.all_reduce(self._flat.grad_full, group=group)
+            allreduce_flat(self._flat.grad_full, dist, group)
             entry[1].replay()
 
     # ---- reference surface: the train step -------------------------------------------------------------
