@@ -13,6 +13,7 @@
 // dependent ones (the double-Q eval unroll on o_next that starts from the final hidden of the
 // eval unroll on o, algorithm/q_learner.py:96,110) are chained inside the same CTA.
 #include "linear.h"
+#include "forkjoin.h"
 #include "../../include/marl_b200.h"
 #include "profile.h"
 
@@ -21,14 +22,6 @@ namespace marl {
 constexpr int kMaxStreams = 4;
 constexpr int kGruThreads = 128;   // 64 hidden units x 2-way split of the reduction, one warp per SM sub-partition
 constexpr int kGiDepth = 4;        // cp.async ring depth (time steps) of the forward's input gates
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // MUFU-based gate non-linearities: ex2.approx / rcp.approx are accurate to ~2 ulp, i.e. <= 2e-7 absolute on
 // the (0,1) / (-1,1) outputs -- the same order as the fp32 rounding of the reference's own libm path.
@@ -352,8 +345,10 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         if (!s[i].obs || (!s[i].onehot && !s[i].full_input) || !s[i].hidden || !s[i].x || !s[i].gi) return MARL_EINVAL;
         if (s[i].h0_from >= i) return MARL_EINVAL;
     }
-    // phase A
+    // phase A: the streams are independent -> one lane each
+    ForkJoin fa(st, n_streams);
     for (int i = 0; i < n_streams; ++i) {
+        cudaStream_t st = fa.lane(i);
         LinearFwd f{};
         f.in = agent_input(d, s[i].obs, s[i].onehot, s[i].shift_onehot, s[i].full_input);
         f.w = s[i].params.fc1_w; f.ldw = I; f.bias = s[i].params.fc1_b;
@@ -367,6 +362,7 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         rc = linear_fwd(g, st);
         if (rc) return rc;
     }
+    fa.join();
     // phase B: build chains (a stream whose h0_from == j continues chain of j; j must be a chain tail)
     GruFwdArgs ga{};
     ga.B = d->B; ga.L = d->L; ga.N = d->N;
@@ -419,8 +415,10 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
     }
     MARL_LAUNCH_CHECK();
     // phase C
+    ForkJoin fc(st, n_streams);
     for (int i = 0; i < n_streams; ++i) {
         if (!s[i].q) continue;
+        cudaStream_t st = fc.lane(i);
         LinearFwd f{};
         f.in = plain_operand(s[i].hidden, MARL_H, MARL_H);
         f.w = s[i].params.fc2_w; f.ldw = MARL_H; f.bias = s[i].params.fc2_b;
@@ -428,6 +426,7 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         int rc = linear_fwd(f, st);
         if (rc) return rc;
     }
+    fc.join();
     return MARL_OK;
 }
 
@@ -444,10 +443,6 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
         g.dy = a->dq; g.lddy = d->A; g.w = a->params.fc2_w; g.ldw = MARL_H; g.w_col0 = 0;
         g.dx = a->dhext; g.lddx = MARL_H; g.M = rows_total; g.N = d->A; g.K = MARL_H; g.batch = 1;
         if ((rc = linear_dgrad(g, st))) return rc;
-        LinearWgrad w{};
-        w.dy = a->dq; w.lddy = d->A; w.in = plain_operand(a->hidden, MARL_H, MARL_H);
-        w.dw = a->grads.fc2_w; w.ldw = MARL_H; w.db = a->grads.fc2_b; w.M = rows_total; w.N = d->A; w.batch = 1;
-        if ((rc = linear_wgrad(w, st))) return rc;
     }
     GruBwdArgs ga{a->gates, a->hidden, a->dq ? a->dhext : nullptr, a->dhidden, a->params.w_hh, a->h0, a->dgi, a->dgh, a->dh0,
                   d->B, d->L, d->N};
@@ -467,7 +462,17 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
 #undef MARL_GRU_BWD
     }
     MARL_LAUNCH_CHECK();
+    // the four weight gradients and the dx chain are independent: fan them out
+    ForkJoin fb(st, 4);
+    if (a->dq) {   // dW2 += dq^T h ; db2 += colsum(dq)
+        cudaStream_t st = fb.lane(3);
+        LinearWgrad w{};
+        w.dy = a->dq; w.lddy = d->A; w.in = plain_operand(a->hidden, MARL_H, MARL_H);
+        w.dw = a->grads.fc2_w; w.ldw = MARL_H; w.db = a->grads.fc2_b; w.M = rows_total; w.N = d->A; w.batch = 1;
+        if ((rc = linear_wgrad(w, st))) return rc;
+    }
     {   // dW_hh += dgh^T . h_{t-1} (hidden shifted by one step, zeros at t = 0) ; db_hh
+        cudaStream_t st = fb.lane(1);
         LinearWgrad w{};
         w.dy = a->dgh; w.lddy = MARL_G;
         LinOperand in{};
@@ -485,6 +490,7 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
         }
     }
     {   // dW_ih += dgi^T . x ; db_ih
+        cudaStream_t st = fb.lane(2);
         LinearWgrad w{};
         w.dy = a->dgi; w.lddy = MARL_G; w.in = plain_operand(a->x, MARL_H, MARL_H);
         w.dw = a->grads.w_ih; w.ldw = MARL_H; w.db = a->grads.b_ih; w.M = rows_total; w.N = MARL_G; w.batch = 1;
@@ -503,5 +509,6 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
         w.dw = a->grads.fc1_w; w.ldw = I; w.db = a->grads.fc1_b; w.M = rows_total; w.N = MARL_H; w.batch = 1;
         if ((rc = linear_wgrad(w, st))) return rc;
     }
+    fb.join();
     return MARL_OK;
 }

@@ -85,6 +85,58 @@ __global__ void __launch_bounds__(kOptThreads) clip_adam_kernel(float* __restric
     }
 }
 
+// Small parameter sets (<= kFusedMax): one CTA does norm + clip + update in a single launch.
+constexpr long long kFusedMax = 4096;   // one CTA only pays off for tiny parameter sets (latency-bound loop)
+constexpr int kFusedThreads = 1024;
+
+template <bool ADAM>
+__global__ void __launch_bounds__(kFusedThreads) clip_step_fused_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                                       float* __restrict__ m1, float* __restrict__ m2, long long n,
+                                                                       const float* __restrict__ scalars, float max_norm, float lr,
+                                                                       float c1, float c2, float eps, int step, int* step_counter,
+                                                                       float* loss_out) {
+    __shared__ float sw[kFusedThreads / 32];
+    __shared__ float s_scale;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < n; i += kFusedThreads) { const float v = g[i]; acc = fmaf(v, v, acc); }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < kFusedThreads / 32; ++w) t += sw[w];
+        const float inv = 1.0f / scalars[1];
+        const float total_norm = sqrtf(t) * inv;
+        float coef = max_norm / (total_norm + 1e-6f);
+        coef = coef > 1.0f ? 1.0f : coef;
+        s_scale = inv * coef;
+        if (loss_out) { loss_out[0] = scalars[0] * inv; loss_out[1] = total_norm; }
+        if (ADAM && step_counter) *step_counter += 1;
+    }
+    __syncthreads();
+    const float scale = s_scale;
+    float step_size = 0.f, bc2_sqrt = 1.f;
+    if (ADAM) {
+        const int stp = step_counter ? *step_counter : step;
+        step_size = (float)((double)lr / (1.0 - pow((double)c1, (double)stp)));
+        bc2_sqrt = (float)sqrt(1.0 - pow((double)c2, (double)stp));
+    }
+    for (long long i = threadIdx.x; i < n; i += kFusedThreads) {
+        const float gr = g[i] * scale;
+        g[i] = gr;
+        if (ADAM) {
+            const float a = m1[i] + (1.0f - c1) * (gr - m1[i]);
+            const float b = c2 * m2[i] + (1.0f - c2) * gr * gr;
+            m1[i] = a; m2[i] = b;
+            p[i] = p[i] - step_size * (a / (sqrtf(b) / bc2_sqrt + eps));
+        } else {
+            const float v = c1 * m1[i] + (1.0f - c1) * gr * gr;
+            m1[i] = v;
+            p[i] = p[i] - lr * (gr / (sqrtf(v) + eps));
+        }
+    }
+}
+
 }  // namespace marl
 
 using namespace marl;
@@ -101,6 +153,13 @@ extern "C" int marl_clip_rmsprop_step(float* params, float* grads, float* square
                                       void* stream) {
     if (!params || !grads || !square_avg || n <= 0 || !scalars || !partials) return MARL_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
+    if (n <= kFusedMax) {
+        { ProfScope ps_("clip_step_fused_kernel", st);
+          clip_step_fused_kernel<false><<<1, kFusedThreads, 0, st>>>(params, grads, square_avg, nullptr, n, scalars, max_norm,
+                                                                     lr, alpha, 0.f, eps, 0, nullptr, loss_out); }
+        MARL_LAUNCH_CHECK();
+        return MARL_OK;
+    }
     { ProfScope ps_("sumsq_kernel", st); sumsq_kernel<<<kOptBlocks, kOptThreads, 0, st>>>(grads, n, partials, nullptr); }
     MARL_LAUNCH_CHECK();
     { ProfScope ps_("clip_rmsprop_kernel", st); clip_rmsprop_kernel<<<opt_grid(n), kOptThreads, 0, st>>>(params, grads, square_avg, n, partials, scalars, max_norm, lr,
@@ -115,6 +174,13 @@ extern "C" int marl_clip_adam_step(float* params, float* grads, float* exp_avg, 
     if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || !scalars || !partials) return MARL_EINVAL;
     if (!step_counter && step < 1) return MARL_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
+    if (n <= kFusedMax) {
+        { ProfScope ps_("clip_step_fused_kernel", st);
+          clip_step_fused_kernel<true><<<1, kFusedThreads, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, scalars, max_norm,
+                                                                    lr, beta1, beta2, eps, step, step_counter, loss_out); }
+        MARL_LAUNCH_CHECK();
+        return MARL_OK;
+    }
     { ProfScope ps_("sumsq_kernel", st); sumsq_kernel<<<kOptBlocks, kOptThreads, 0, st>>>(grads, n, partials, step_counter); }
     MARL_LAUNCH_CHECK();
     { ProfScope ps_("clip_adam_kernel", st); clip_adam_kernel<<<opt_grid(n), kOptThreads, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, partials, scalars,

@@ -8,6 +8,7 @@
 //   backward in the same warp emits the per-sample gradient row dhy[C] that feeds the
 //   weight-gradient GEMM dwcat += dhy^T . s.
 #include "linear.h"
+#include "forkjoin.h"
 #include "../../include/marl_b200.h"
 #include "profile.h"
 
@@ -196,8 +197,12 @@ extern "C" int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* 
     if (M <= 0) return MARL_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if ((rc = hyper_fwd(M, d->N, d->S, p, s, hy, st))) return rc;
-    if ((rc = hyper_fwd(M, d->N, d->S, pt, s_next, hy_target, st))) return rc;
+    {
+        ForkJoin fj(st, 2);      // eval and target hyper-networks side by side
+        if ((rc = hyper_fwd(M, d->N, d->S, p, s, hy, fj.lane(0)))) return rc;
+        if ((rc = hyper_fwd(M, d->N, d->S, pt, s_next, hy_target, fj.lane(1)))) return rc;
+        fj.join();
+    }
     QmixMixArgs a{};
     a.M = M; a.N = d->N; a.A = d->A; a.mode = QMIX_TD;
     a.hy = hy; a.q = q_chosen; a.wb2 = p->wb2; a.bb2 = p->bb2;

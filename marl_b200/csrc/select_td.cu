@@ -110,7 +110,23 @@ __global__ void __launch_bounds__(256) ingest_kernel(IngestArgs a) {
     const IngestKey key = a.k[blockIdx.y];
     const long long per_b = (long long)a.L * key.inner, total = (long long)a.B * per_b;
     const long long src_b = (long long)a.T_src * key.inner;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    if (a.T_src == a.L && (total & 3) == 0 && (key.kind == 0 || key.kind == 3)) {
+        // no truncation: straight vectorised cast / copy
+        const long long nq = total >> 2;
+        if (key.kind == 0) {
+            const double2* s = (const double2*)key.src; float4* d = (float4*)key.dst;
+            for (long long i = tid0; i < nq; i += stride) {
+                const double2 u0 = s[2 * i], u1 = s[2 * i + 1];
+                d[i] = make_float4((float)u0.x, (float)u0.y, (float)u1.x, (float)u1.y);
+            }
+        } else {
+            const float4* s = (const float4*)key.src; float4* d = (float4*)key.dst;
+            for (long long i = tid0; i < nq; i += stride) d[i] = s[i];
+        }
+        return;
+    }
+    for (long long i = tid0; i < total; i += stride) {
         const long long b = i / per_b, rem = i - b * per_b, si = b * src_b + rem;
         if (key.kind == 0) ((float*)key.dst)[i] = (float)((const double*)key.src)[si];
         else if (key.kind == 1) ((long long*)key.dst)[i] = (long long)((const double*)key.src)[si];   // trunc toward zero
@@ -182,9 +198,9 @@ extern "C" int marl_ingest_f64(const marl_episode_f64* s, int T_src, const marl_
     for (int i = 0; i < 11; ++i)
         if (!a.k[i].src || !a.k[i].dst) return MARL_EINVAL;
     long long biggest = (long long)d->B * d->L * (NO > NA ? NO : NA);
-    int bx = (int)((biggest + 1023) / 1024);
+    int bx = (int)((biggest + 4095) / 4096);
     if (bx < 1) bx = 1;
-    if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;
+    if (bx > kNumSMs) bx = kNumSMs;
     { ProfScope ps_("ingest_kernel", (cudaStream_t)stream); ingest_kernel<<<dim3(bx, 11), 256, 0, (cudaStream_t)stream>>>(a); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
@@ -210,9 +226,9 @@ extern "C" int marl_ingest_f32(const marl_episode_f32* s, int T_src, const marl_
     for (int i = 0; i < 11; ++i)
         if (!a.k[i].src || !a.k[i].dst) return MARL_EINVAL;
     long long biggest = (long long)d->B * d->L * (NO > NA ? NO : NA);
-    int bx = (int)((biggest + 1023) / 1024);
+    int bx = (int)((biggest + 4095) / 4096);
     if (bx < 1) bx = 1;
-    if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;
+    if (bx > kNumSMs) bx = kNumSMs;
     { ProfScope ps_("ingest_kernel", (cudaStream_t)stream); ingest_kernel<<<dim3(bx, 11), 256, 0, (cudaStream_t)stream>>>(a); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
