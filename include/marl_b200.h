@@ -170,7 +170,12 @@ int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* p, const ma
                          const float* s, const float* s_next, const float* q_chosen, const float* q_targets_chosen,
                          const long long* u, const float* r, const float* terminated, const float* padded, float gamma,
                          float* hy, float* hy_target, float* dhy, float* q_tot, float* q_tot_target,
-                         float* dq, const marl_qmix_grads* g, float* scalars, void* stream);
+                         float* dq, const marl_qmix_grads* g, float* scalars, int flags, void* stream);
+/* The state-only halves of the QMIX step, so that a caller can overlap them with the agent unrolls:
+ * flags bit 0 of marl_qmix_td_fwd_bwd = hy / hy_target were already filled by marl_qmix_hyper_fwd,
+ * bit 1 = leave dwcat/dbcat to a later marl_qmix_hyper_wgrad(dhy). */
+int marl_qmix_hyper_fwd(int M, int N, int S, const marl_qmix_params* p, const float* s, float* hy, void* stream);
+int marl_qmix_hyper_wgrad(int M, int N, int S, const float* s, const float* dhy, const marl_qmix_grads* g, void* stream);
 
 /* ---- QPLEX: DMAQer + DMAQ_SI_Weight, network/mixer.py:85-288 (adv_hypernet_layers = 3) ----
  * Parameters are passed layer-concatenated (the host lays them out that way), K = num_kernel,

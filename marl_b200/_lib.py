@@ -117,7 +117,9 @@ _SIGNATURES = {
     "marl_qmix_fwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "marl_qmix_bwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams)] + [c_ptr] * 6 + [_P(QmixGrads), c_ptr], C.c_int),
     "marl_qmix_td_fwd_bwd": ([_P(Dims), _P(QmixParams), _P(QmixParams)] + [c_ptr] * 8 + [C.c_float] + [c_ptr] * 6
-                             + [_P(QmixGrads), c_ptr, c_ptr], C.c_int),
+                             + [_P(QmixGrads), c_ptr, C.c_int, c_ptr], C.c_int),
+    "marl_qmix_hyper_fwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams), c_ptr, c_ptr, c_ptr], C.c_int),
+    "marl_qmix_hyper_wgrad": ([C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, _P(QmixGrads), c_ptr], C.c_int),
     "marl_qplex_fwd": ([C.c_int, _P(QplexDims), _P(QplexParams)] + [c_ptr] * 4 + [_P(QplexWs)] + [c_ptr] * 4, C.c_int),
     "marl_qplex_bwd": ([C.c_int, _P(QplexDims), _P(QplexParams)] + [c_ptr] * 4 + [_P(QplexWs), c_ptr, c_ptr, _P(QplexWs), c_ptr,
                        _P(QplexGrads), c_ptr], C.c_int),

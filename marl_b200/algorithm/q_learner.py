@@ -93,6 +93,7 @@ class QLearner:
         self._graphs = {}
         self._use_graph = bool(getattr(args, "cuda_graph", True))
         self._dist = None
+        self._side = None
         self.last = {}
         self.launches_per_step = 0
 
@@ -278,6 +279,24 @@ class QLearner:
         n_launch = 1
         pe, pt = self._agent_structs(self._flat), self._agent_structs(self._tflat)
         double_q = bool(a.double_q)
+        cur = th.cuda.current_stream()
+        if a.alg == "qmix":
+            # the hyper-networks only read the states: run them beside the (latency-bound) agent unrolls
+            if self._side is None:
+                self._side = th.cuda.Stream()
+            qp = qmix_struct({n: self._flat.ptr("mixer." + n) for n in ("hyper_w1.weight", "hyper_w1.bias",
+                                                                        "hyper_b2.2.weight", "hyper_b2.2.bias")})
+            qpt = qmix_struct({n: self._tflat.ptr("mixer." + n) for n in ("hyper_w1.weight", "hyper_w1.bias",
+                                                                          "hyper_b2.2.weight", "hyper_b2.2.bias")})
+            qg = qmix_struct({n: self._flat.ptr("mixer." + n, self._flat.grad) for n in
+                              ("hyper_w1.weight", "hyper_w1.bias", "hyper_b2.2.weight", "hyper_b2.2.bias")}, L.QmixGrads)
+            self._side.wait_stream(cur)
+            with th.cuda.stream(self._side):
+                ssp = L.stream_ptr()
+                L.call("marl_qmix_hyper_fwd", B * Lq, a.n_agents, a.state_shape, C.byref(qp), bt["s"].data_ptr(),
+                       ws["hy"].data_ptr(), ssp)
+                L.call("marl_qmix_hyper_fwd", B * Lq, a.n_agents, a.state_shape, C.byref(qpt), bt["s_next"].data_ptr(),
+                       ws["hy_t"].data_ptr(), ssp)
         n_streams = 3 if double_q else 2
         arr = (L.UnrollStream * 3)()
 
@@ -308,17 +327,18 @@ class QLearner:
                    ws["q_tot"].data_ptr(), ws["q_tot_t"].data_ptr(), ws["dq"].data_ptr(), scalars, sp)
             n_launch += 1
         elif a.alg == "qmix":
-            p = qmix_struct({n: self._flat.ptr("mixer." + n) for n in ("hyper_w1.weight", "hyper_w1.bias",
-                                                                       "hyper_b2.2.weight", "hyper_b2.2.bias")})
-            ptg = qmix_struct({n: self._tflat.ptr("mixer." + n) for n in ("hyper_w1.weight", "hyper_w1.bias",
-                                                                          "hyper_b2.2.weight", "hyper_b2.2.bias")})
-            g = qmix_struct({n: self._flat.ptr("mixer." + n, self._flat.grad) for n in
-                             ("hyper_w1.weight", "hyper_w1.bias", "hyper_b2.2.weight", "hyper_b2.2.bias")}, L.QmixGrads)
+            p, ptg, g = qp, qpt, qg
+            cur.wait_stream(self._side)
             L.call("marl_qmix_td_fwd_bwd", C.byref(d), C.byref(p), C.byref(ptg), bt["s"].data_ptr(), bt["s_next"].data_ptr(),
                    ws["q_chosen"].data_ptr(), ws["q_tc"].data_ptr(), bt["u"].data_ptr(), bt["r"].data_ptr(),
                    bt["terminated"].data_ptr(), bt["padded"].data_ptr(), float(self.gamma), ws["hy"].data_ptr(),
                    ws["hy_t"].data_ptr(), ws["dhy"].data_ptr(), ws["q_tot"].data_ptr(), ws["q_tot_t"].data_ptr(),
-                   ws["dq"].data_ptr(), C.byref(g), scalars, sp)
+                   ws["dq"].data_ptr(), C.byref(g), scalars, 3, sp)
+            # ... and their weight gradient beside the BPTT
+            self._side.wait_stream(cur)
+            with th.cuda.stream(self._side):
+                L.call("marl_qmix_hyper_wgrad", B * Lq, a.n_agents, a.state_shape, bt["s"].data_ptr(), ws["dhy"].data_ptr(),
+                       C.byref(g), L.stream_ptr())
             n_launch += 4
         elif a.alg == "qplex":
             from ..network.qplex import qplex_struct, qplex_dims, ws_struct
@@ -359,6 +379,8 @@ class QLearner:
         bw.grads = agent_param_struct({n: self._flat.ptr("agent." + n, self._flat.grad) for n in AGENT_FLAT_ORDER},
                                       L.AgentGrads)
         L.call("marl_agent_unroll_bwd", C.byref(d), C.byref(bw), sp)
+        if a.alg == "qmix":
+            cur.wait_stream(self._side)
         n_launch += 7
         return n_launch
 

@@ -43,27 +43,27 @@ struct GruFwdArgs {
     GruSegment seg[kMaxStreams];
     int chain_start[kMaxStreams];
     int chain_len[kMaxStreams];
-    int chain_rows_per_cta[kMaxStreams];
-    int chain_cta0[kMaxStreams];     // first blockIdx.x of the chain
     const float* h0[kMaxStreams];
     int n_chains, B, L, N;
 };
 
 // One CTA advances R rows (b,n) of one chain through all its segments.  Thread (j, ks): hidden unit j,
 // half ks of the 64-long reduction; its 3 x 32 W_hh weights stay in registers for the whole segment.
+// 128-thread named barrier: the CTA hosts one such group per chain, each advancing its own rows
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kGruThreads) : "memory"); }
+
 template <int R>
-__device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, int group, float* smem) {
+__device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, int row0, int nrows, float* smem, int bar_id) {
     float (*hs)[R][MARL_H] = reinterpret_cast<float (*)[R][MARL_H]>(smem);                          // [2][R][H]
     float (*ring)[R][MARL_G] = reinterpret_cast<float (*)[R][MARL_G]>(smem + 2 * R * MARL_H);       // [D][R][3H]
-    const int tid = threadIdx.x, ks = tid & 1, j = tid >> 1;
-    const int rows = a.B * a.N, row0 = group * R;
+    const int tid = threadIdx.x & (kGruThreads - 1), ks = tid & 1, j = tid >> 1;
     const int L = a.L, N = a.N;
     constexpr int OWN = (R + 1) / 2;                  // rows whose gate math this lane owns: rr = ks + 2q
     bool own[OWN]; long long base[OWN];
 #pragma unroll
     for (int q = 0; q < OWN; ++q) {
         const int rr = ks + 2 * q, row = row0 + rr;
-        own[q] = rr < R && row < rows;
+        own[q] = rr < nrows;
         base[q] = own[q] ? ((long long)(row / N) * L * N + (row % N)) : 0;
     }
     // cp.async work list: R rows x 48 chunks of 16 B per time step
@@ -72,7 +72,7 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
 #pragma unroll
     for (int l = 0; l < NCH; ++l) {
         const int c = tid + l * kGruThreads, rr = c / 48, ch = c % 48, row = row0 + rr;
-        if (c < R * 48 && row < rows) {
+        if (c < R * 48 && rr < nrows) {
             csrc[l] = ((long long)(row / N) * L * N + (row % N)) * MARL_G + ch * 4;
             cdst[l] = rr * MARL_G + ch * 4;
         } else { csrc[l] = -1; cdst[l] = 0; }
@@ -80,7 +80,7 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
     const float* h0 = a.h0[chain];
     for (int idx = tid; idx < R * MARL_H; idx += kGruThreads) {
         const int rr = idx / MARL_H, jj = idx % MARL_H, row = row0 + rr;
-        hs[0][rr][jj] = (h0 && row < rows) ? h0[(long long)row * MARL_H + jj] : 0.0f;
+        hs[0][rr][jj] = (h0 && rr < nrows) ? h0[(long long)row * MARL_H + jj] : 0.0f;
     }
     int cur = 0;
     for (int sg = a.chain_start[chain]; sg < a.chain_start[chain] + a.chain_len[chain]; ++sg) {
@@ -106,13 +106,13 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
         for (int t = 0; t < kGiDepth - 1; ++t) issue(t);
         for (int t = 0; t < L; ++t) {
             cp_async_wait<kGiDepth - 2>();           // this thread's copies for step t have landed
-            __syncthreads();                         // ... everybody's; also orders the h double buffer
+            group_sync(bar_id);                      // ... the whole group's; also orders the h double buffer
             issue(t + kGiDepth - 1);                 // refill the slot consumed in step t-1
-            float acc[3][R];
+            float acc[3][R], acc2[3][R];          // two partial sums per dot product: short dependent FMA chains
 #pragma unroll
             for (int g = 0; g < 3; ++g)
 #pragma unroll
-                for (int rr = 0; rr < R; ++rr) acc[g][rr] = 0.0f;
+                for (int rr = 0; rr < R; ++rr) { acc[g][rr] = 0.0f; acc2[g][rr] = 0.0f; }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -121,15 +121,18 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
 #pragma unroll
                     for (int g = 0; g < 3; ++g) {
                         acc[g][rr] = fmaf(w[g][4 * i + 0], hv.x, acc[g][rr]);
-                        acc[g][rr] = fmaf(w[g][4 * i + 1], hv.y, acc[g][rr]);
+                        acc2[g][rr] = fmaf(w[g][4 * i + 1], hv.y, acc2[g][rr]);
                         acc[g][rr] = fmaf(w[g][4 * i + 2], hv.z, acc[g][rr]);
-                        acc[g][rr] = fmaf(w[g][4 * i + 3], hv.w, acc[g][rr]);
+                        acc2[g][rr] = fmaf(w[g][4 * i + 3], hv.w, acc2[g][rr]);
                     }
                 }
 #pragma unroll
             for (int g = 0; g < 3; ++g)
 #pragma unroll
-                for (int rr = 0; rr < R; ++rr) acc[g][rr] += __shfl_xor_sync(0xffffffffu, acc[g][rr], 1);
+                for (int rr = 0; rr < R; ++rr) {
+                    acc[g][rr] += acc2[g][rr];
+                    acc[g][rr] += __shfl_xor_sync(0xffffffffu, acc[g][rr], 1);
+                }
             const float* gring = &ring[t % kGiDepth][0][0];
 #pragma unroll
             for (int q = 0; q < OWN; ++q) {
@@ -159,7 +162,7 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
             cur ^= 1;
         }
         cp_async_wait<0>();
-        __syncthreads();
+        group_sync(bar_id);
         if (S.h_last) {
 #pragma unroll
             for (int q = 0; q < OWN; ++q)
@@ -168,18 +171,37 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
     }
 }
 
-template <int R0, int R1>
-__global__ void __launch_bounds__(kGruThreads) gru_unroll_fwd_kernel(GruFwdArgs a) {
-    extern __shared__ __align__(16) float gru_smem[];
-    // chains are laid out back to back along blockIdx.x; chain 0 uses R0 rows per CTA, later chains R1
-    int chain = 0;
-    while (chain + 1 < a.n_chains && (int)blockIdx.x >= a.chain_cta0[chain + 1]) ++chain;
-    const int group = blockIdx.x - a.chain_cta0[chain];
-    if (chain == 0) gru_chain_fwd<R0>(a, chain, group, gru_smem);
-    else gru_chain_fwd<R1>(a, chain, group, gru_smem);
+// This CTA's share of a chain's rows: rows are dealt out as evenly as possible over the CTAs (one CTA per SM);
+// odd chains deal the remainder from the other end, so that an SM that got an extra row of the long eval
+// chain does not also get an extra row of the target chain.
+__device__ __forceinline__ void cta_rows(int rows, int chain, int& begin, int& count) {
+    const int n = gridDim.x, base = rows / n, rem = rows % n;
+    const int pos = (chain & 1) ? n - 1 - (int)blockIdx.x : (int)blockIdx.x;
+    count = base + (pos < rem ? 1 : 0);
+    begin = pos * base + (pos < rem ? pos : rem);
 }
 
+constexpr int kGruGroups = 2;      // chains advanced side by side in one CTA (one 128-thread group each)
+constexpr int kGruMaxRows = 8;     // rows per group and pass
 constexpr size_t gru_fwd_smem(int R) { return (size_t)(2 * R * MARL_H + kGiDepth * R * MARL_G) * sizeof(float); }
+
+__global__ void __launch_bounds__(kGruThreads * kGruGroups) gru_unroll_fwd_kernel(GruFwdArgs a) {
+    extern __shared__ __align__(16) float gru_smem[];
+    const int grp = threadIdx.x >> 7;
+    const int chain = blockIdx.y * kGruGroups + grp;
+    if (chain >= a.n_chains) return;
+    float* smem = gru_smem + grp * (gru_fwd_smem(kGruMaxRows) / sizeof(float));
+    int begin, count;
+    cta_rows(a.B * a.N, chain, begin, count);
+    for (int off = 0; off < count; off += kGruMaxRows) {
+        const int n = min(kGruMaxRows, count - off);
+        if (n == 1) gru_chain_fwd<1>(a, chain, begin + off, n, smem, 1 + grp);
+        else if (n == 2) gru_chain_fwd<2>(a, chain, begin + off, n, smem, 1 + grp);
+        else if (n <= 4) gru_chain_fwd<4>(a, chain, begin + off, n, smem, 1 + grp);
+        else gru_chain_fwd<8>(a, chain, begin + off, n, smem, 1 + grp);
+        group_sync(1 + grp);
+    }
+}
 
 struct GruBwdArgs {
     const float* gates;    // [B,L,N,4H]
@@ -199,20 +221,18 @@ constexpr int bwd_depth(int R) { return R >= 8 ? 3 : 6; }
 constexpr size_t gru_bwd_smem(int R) { return (size_t)(2 * R * MARL_G + bwd_depth(R) * R * kBwdSlot) * sizeof(float); }
 
 template <int R>
-__global__ void __launch_bounds__(kGruThreads) gru_unroll_bwd_kernel(GruBwdArgs a) {
-    extern __shared__ __align__(16) float gru_smem[];
+__device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int nrows, float* gru_smem) {
     constexpr int D = bwd_depth(R);
     float (*sg)[R][MARL_G] = reinterpret_cast<float (*)[R][MARL_G]>(gru_smem);                       // [2][R][3H]
     float (*ring)[R][kBwdSlot] = reinterpret_cast<float (*)[R][kBwdSlot]>(gru_smem + 2 * R * MARL_G); // [D][R][7H]
     const int tid = threadIdx.x, ks = tid & 1, j = tid >> 1;
-    const int rows = a.B * a.N, row0 = blockIdx.x * R;
     const int L = a.L, N = a.N;
     constexpr int OWN = (R + 1) / 2;
     bool own[OWN]; long long base[OWN]; float dh_carry[OWN];
 #pragma unroll
     for (int q = 0; q < OWN; ++q) {
         const int rr = ks + 2 * q, row = row0 + rr;
-        own[q] = rr < R && row < rows;
+        own[q] = rr < nrows;
         base[q] = own[q] ? ((long long)(row / N) * L * N + (row % N)) : 0;
         dh_carry[q] = 0.0f;
     }
@@ -222,22 +242,35 @@ __global__ void __launch_bounds__(kGruThreads) gru_unroll_bwd_kernel(GruBwdArgs 
     for (int i = 0; i < 24; ++i)
 #pragma unroll
         for (int c = 0; c < 4; ++c) wt[4 * i + c] = __ldg(a.w_hh + (long long)(4 * (2 * i + ks) + c) * MARL_H + j);
-    // cp.async work list: per row 112 chunks of 16 B (64 gates, 16 h_prev, 16 dh_ext, 16 dh_ext2)
+    // cp.async work list: per row 112 chunks of 16 B (64 gates, 16 h_prev, 16 dh_ext, 16 dh_ext2); the
+    // per-chunk source pointer at t = 0 and its per-step stride are fixed, so they are computed once.
     constexpr int NCH = (R * 112 + kGruThreads - 1) / kGruThreads;
+    const float* csrc[NCH]; int cstride[NCH], cdst[NCH], ckind[NCH];
+#pragma unroll
+    for (int l = 0; l < NCH; ++l) {
+        const int c = tid + l * kGruThreads, rr = c / 112, ch = c % 112, row = row0 + rr;
+        csrc[l] = nullptr; cstride[l] = 0; cdst[l] = rr * kBwdSlot + ch * 4; ckind[l] = 0;
+        if (c < R * 112 && rr < nrows) {
+            const long long idx0 = (long long)(row / N) * L * N + (row % N);
+            if (ch < 64) { csrc[l] = a.gates + idx0 * (4 * MARL_H) + ch * 4; cstride[l] = N * 4 * MARL_H; }
+            else if (ch < 80) { csrc[l] = a.hidden + (idx0 - N) * MARL_H + (ch - 64) * 4; cstride[l] = N * MARL_H; ckind[l] = 1;
+                                 if (a.h0) ckind[l] = 2; }
+            else if (ch < 96) { if (a.dh_ext) { csrc[l] = a.dh_ext + idx0 * MARL_H + (ch - 80) * 4; cstride[l] = N * MARL_H; } }
+            else { if (a.dh_ext2) { csrc[l] = a.dh_ext2 + idx0 * MARL_H + (ch - 96) * 4; cstride[l] = N * MARL_H; } }
+        }
+    }
+    const float* h0row = a.h0 ? a.h0 + (long long)row0 * MARL_H : nullptr;
     auto issue = [&](int t) {
         if (t >= 0) {
+            float* slot = &ring[t % D][0][0];
 #pragma unroll
             for (int l = 0; l < NCH; ++l) {
-                const int c = tid + l * kGruThreads, rr = c / 112, ch = c % 112, row = row0 + rr;
-                if (c < R * 112 && row < rows) {
-                    const long long idx = (long long)(row / N) * L * N + (row % N) + (long long)t * N;
-                    float* dst = &ring[t % D][rr][0] + ch * 4;
-                    if (ch < 64) cp_async16(dst, a.gates + idx * (4 * MARL_H) + ch * 4);
-                    else if (ch < 80) { if (t > 0) cp_async16(dst, a.hidden + (idx - N) * MARL_H + (ch - 64) * 4);
-                                        else if (a.h0) cp_async16(dst, a.h0 + (long long)row * MARL_H + (ch - 64) * 4); }
-                    else if (ch < 96) { if (a.dh_ext) cp_async16(dst, a.dh_ext + idx * MARL_H + (ch - 80) * 4); }
-                    else { if (a.dh_ext2) cp_async16(dst, a.dh_ext2 + idx * MARL_H + (ch - 96) * 4); }
+                if (!csrc[l]) continue;
+                if (ckind[l] != 0 && t == 0) {      // h_prev of the first step: h0 (or zeros, handled by the consumer)
+                    if (ckind[l] == 2) cp_async16(slot + cdst[l], h0row + (cdst[l] / kBwdSlot) * MARL_H + (cdst[l] % kBwdSlot - 4 * MARL_H));
+                    continue;
                 }
+                cp_async16(slot + cdst[l], csrc[l] + (long long)t * cstride[l]);
             }
         }
         cp_async_commit();
@@ -278,21 +311,24 @@ __global__ void __launch_bounds__(kGruThreads) gru_unroll_bwd_kernel(GruBwdArgs 
         issue(t - (D - 1));              // refills the slot of step t+1, consumed before the previous barrier
         cp_async_wait<D - 2>();          // this thread's copies for step t-1 have landed
         __syncthreads();                 // dgh of step t visible; ring[t-1] visible
-        float part[R];
+        float part[R], pb[R], pc[R], pd[R];     // four partial sums per row: short dependent FMA chains
 #pragma unroll
-        for (int rr = 0; rr < R; ++rr) part[rr] = 0.0f;
+        for (int rr = 0; rr < R; ++rr) { part[rr] = 0.0f; pb[rr] = 0.0f; pc[rr] = 0.0f; pd[rr] = 0.0f; }
 #pragma unroll
         for (int i = 0; i < 24; ++i)
 #pragma unroll
             for (int rr = 0; rr < R; ++rr) {
                 const float4 v = *reinterpret_cast<const float4*>(&sg[cur][rr][4 * (2 * i + ks)]);
                 part[rr] = fmaf(wt[4 * i + 0], v.x, part[rr]);
-                part[rr] = fmaf(wt[4 * i + 1], v.y, part[rr]);
-                part[rr] = fmaf(wt[4 * i + 2], v.z, part[rr]);
-                part[rr] = fmaf(wt[4 * i + 3], v.w, part[rr]);
+                pb[rr] = fmaf(wt[4 * i + 1], v.y, pb[rr]);
+                pc[rr] = fmaf(wt[4 * i + 2], v.z, pc[rr]);
+                pd[rr] = fmaf(wt[4 * i + 3], v.w, pd[rr]);
             }
 #pragma unroll
-        for (int rr = 0; rr < R; ++rr) part[rr] += __shfl_xor_sync(0xffffffffu, part[rr], 1);
+        for (int rr = 0; rr < R; ++rr) {
+            part[rr] = (part[rr] + pb[rr]) + (pc[rr] + pd[rr]);
+            part[rr] += __shfl_xor_sync(0xffffffffu, part[rr], 1);
+        }
 #pragma unroll
         for (int q = 0; q < OWN; ++q) {
             const int e = 2 * q, o = (2 * q + 1 < R) ? 2 * q + 1 : 2 * q;
@@ -306,14 +342,22 @@ __global__ void __launch_bounds__(kGruThreads) gru_unroll_bwd_kernel(GruBwdArgs 
         for (int q = 0; q < OWN; ++q)
             if (own[q]) a.dh0[(long long)(row0 + ks + 2 * q) * MARL_H + j] = dh_carry[q];
     }
+    __syncthreads();
 }
 
-// Rows per CTA: as few as possible (shortest dependent step) while every CTA of the launch is
-// co-resident (3 CTAs of 128 threads per SM).
-static int pick_rows(int rows, int budget_ctas) {
-    for (int R = 1; R <= 8; R *= 2)
-        if ((rows + R - 1) / R <= budget_ctas) return R;
-    return 8;
+constexpr size_t gru_bwd_smem_max() { return gru_bwd_smem(8) > gru_bwd_smem(4) ? gru_bwd_smem(8) : gru_bwd_smem(4); }
+
+__global__ void __launch_bounds__(kGruThreads) gru_unroll_bwd_kernel(GruBwdArgs a) {
+    extern __shared__ __align__(16) float gru_smem[];
+    int begin, count;
+    cta_rows(a.B * a.N, 0, begin, count);
+    for (int off = 0; off < count; off += kGruMaxRows) {
+        const int n = min(kGruMaxRows, count - off);
+        if (n == 1) gru_rows_bwd<1>(a, begin + off, n, gru_smem);
+        else if (n == 2) gru_rows_bwd<2>(a, begin + off, n, gru_smem);
+        else if (n <= 4) gru_rows_bwd<4>(a, begin + off, n, gru_smem);
+        else gru_rows_bwd<8>(a, begin + off, n, gru_smem);
+    }
 }
 
 static int check_dims(const marl_dims* d) {
@@ -389,29 +433,14 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         ga.seg[k] = GruSegment{u.gi, u.params.w_hh, u.params.b_hh, u.hidden, u.gates, u.h_last};
     }
     const int rows = d->B * d->N;
-    // chain 0 (the longest: eval on o, then eval on o_next) gets the small row groups, the others twice that
-    int R0 = pick_rows(rows, ga.n_chains > 1 ? (kNumSMs * 11) / 10 : 3 * kNumSMs);
-    int R1 = R0 < 8 ? 2 * R0 : 8;
-    int cta = 0;
-    for (int c = 0; c < ga.n_chains; ++c) {
-        const int R = c == 0 ? R0 : R1;
-        ga.chain_rows_per_cta[c] = R;
-        ga.chain_cta0[c] = cta;
-        cta += (rows + R - 1) / R;
-    }
     {
+        // one CTA per SM; each CTA advances its share of every chain side by side (one 128-thread group per chain)
         ProfScope ps_("gru_unroll_fwd_kernel", st);
-#define MARL_GRU_FWD(A, B_)                                                                                          \
-        do {                                                                                                         \
-            const size_t sm = gru_fwd_smem(A) > gru_fwd_smem(B_) ? gru_fwd_smem(A) : gru_fwd_smem(B_);               \
-            cudaFuncSetAttribute(gru_unroll_fwd_kernel<A, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-            gru_unroll_fwd_kernel<A, B_><<<cta, kGruThreads, sm, st>>>(ga);                                           \
-        } while (0)
-        if (R0 == 1) MARL_GRU_FWD(1, 2);
-        else if (R0 == 2) MARL_GRU_FWD(2, 4);
-        else if (R0 == 4) MARL_GRU_FWD(4, 8);
-        else MARL_GRU_FWD(8, 8);
-#undef MARL_GRU_FWD
+        const size_t sm = kGruGroups * gru_fwd_smem(kGruMaxRows);
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(gru_unroll_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); attr_set = true; }
+        dim3 grid(rows < kNumSMs ? rows : kNumSMs, (ga.n_chains + kGruGroups - 1) / kGruGroups);
+        gru_unroll_fwd_kernel<<<grid, kGruThreads * kGruGroups, sm, st>>>(ga);
     }
     MARL_LAUNCH_CHECK();
     // phase C
@@ -447,19 +476,11 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
     GruBwdArgs ga{a->gates, a->hidden, a->dq ? a->dhext : nullptr, a->dhidden, a->params.w_hh, a->h0, a->dgi, a->dgh, a->dh0,
                   d->B, d->L, d->N};
     const int rows = d->B * d->N;
-    const int R = pick_rows(rows, 3 * kNumSMs);
     {
         ProfScope ps_("gru_unroll_bwd_kernel", st);
-#define MARL_GRU_BWD(A)                                                                                              \
-        do {                                                                                                         \
-            cudaFuncSetAttribute(gru_unroll_bwd_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gru_bwd_smem(A)); \
-            gru_unroll_bwd_kernel<A><<<(rows + A - 1) / A, kGruThreads, gru_bwd_smem(A), st>>>(ga);                    \
-        } while (0)
-        if (R == 1) MARL_GRU_BWD(1);
-        else if (R == 2) MARL_GRU_BWD(2);
-        else if (R == 4) MARL_GRU_BWD(4);
-        else MARL_GRU_BWD(8);
-#undef MARL_GRU_BWD
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(gru_unroll_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gru_bwd_smem_max()); attr_set = true; }
+        gru_unroll_bwd_kernel<<<rows < kNumSMs ? rows : kNumSMs, kGruThreads, gru_bwd_smem_max(), st>>>(ga);
     }
     MARL_LAUNCH_CHECK();
     // the four weight gradients and the dx chain are independent: fan them out

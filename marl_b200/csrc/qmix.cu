@@ -187,7 +187,7 @@ extern "C" int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* 
                                     const float* s, const float* s_next, const float* q_chosen, const float* q_tc,
                                     const long long* u, const float* r, const float* terminated, const float* padded,
                                     float gamma, float* hy, float* hy_target, float* dhy, float* q_tot, float* q_tot_target,
-                                    float* dq, const marl_qmix_grads* g, float* scalars, void* stream) {
+                                    float* dq, const marl_qmix_grads* g, float* scalars, int flags, void* stream) {
     if (!d || !qmix_params_ok(p) || !qmix_params_ok(pt) || !s || !s_next || !q_chosen || !q_tc || !r || !terminated ||
         !padded || !hy || !hy_target || !dhy || !g || !scalars)
         return MARL_EINVAL;
@@ -197,7 +197,7 @@ extern "C" int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* 
     if (M <= 0) return MARL_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    {
+    if (!(flags & 1)) {
         ForkJoin fj(st, 2);      // eval and target hyper-networks side by side
         if ((rc = hyper_fwd(M, d->N, d->S, p, s, hy, fj.lane(0)))) return rc;
         if ((rc = hyper_fwd(M, d->N, d->S, pt, s_next, hy_target, fj.lane(1)))) return rc;
@@ -212,5 +212,19 @@ extern "C" int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* 
     a.g_wb2 = g->wb2; a.g_bb2 = g->bb2; a.scalars = scalars;
     { ProfScope ps_("qmix_mix_kernel", st); qmix_mix_kernel<<<mix_grid(M), kQmixWarps * 32, 0, st>>>(a); }
     MARL_LAUNCH_CHECK();
+    if (flags & 2) return MARL_OK;
     return hyper_wgrad(M, d->N, d->S, s, dhy, g, st);
+}
+
+extern "C" int marl_qmix_hyper_fwd(int M, int N, int S, const marl_qmix_params* p, const float* s, float* hy, void* stream) {
+    if (M < 0 || N < 1 || N > kQmixMaxAgents || S < 1 || !qmix_params_ok(p) || !s || !hy) return MARL_EINVAL;
+    if (M == 0) return MARL_OK;
+    return hyper_fwd(M, N, S, p, s, hy, (cudaStream_t)stream);
+}
+
+extern "C" int marl_qmix_hyper_wgrad(int M, int N, int S, const float* s, const float* dhy, const marl_qmix_grads* g,
+                                     void* stream) {
+    if (M < 0 || N < 1 || N > kQmixMaxAgents || S < 1 || !s || !dhy || !g || !g->wcat || !g->bcat) return MARL_EINVAL;
+    if (M == 0) return MARL_OK;
+    return hyper_wgrad(M, N, S, s, dhy, g, (cudaStream_t)stream);
 }
