@@ -1,32 +1,38 @@
-// Dense-layer primitives: forward, data-gradient and weight-gradient GEMMs.
-// 128x64x16 shared-memory tiles on the tensor cores: mma.sync m16n8k8 TF32 with the 3xTF32 split
-// (fp32-level accuracy, see mma_tile), fp32 accumulation, 128-bit global loads where the operand allows it,
-// register double-buffering of the next k-tile.  They replace the cuBLAS
-// addmm calls behind nn.Linear in the reference (network/q_network.py:17,20;
+// Dense-layer primitives: forward, data-gradient and weight-gradient GEMMs on the 5th-generation tensor
+// cores.  One CTA owns a 128 x 64 output tile: operands are staged in shared memory in the canonical
+// K-major (no-swizzle) UMMA layout, a single elected thread issues tcgen05.mma kind::tf32 (M=128, N=64,
+// K=8) with the accumulator in tensor memory (TMEM), completion is tracked with tcgen05.commit ->
+// mbarrier, and the epilogue reads the accumulator back with tcgen05.ld.
+//
+// Accuracy: the parity gate on losses / gradients is 1e-5 relative, which a single TF32 pass (2^-11)
+// cannot meet.  Every operand tile is therefore stored twice, x = hi + lo with hi = the fp32 word
+// itself (the tensor core reads its top 19 bits) and lo = x - trunc_tf32(x), and each k-step issues
+//     D += A_lo.B_hi ;  D += A_hi.B_lo ;  D += A_hi.B_hi            (3xTF32, ~5e-7 relative, fp32 accumulate)
+// -- measured with tools/micro/tc5_probe.cu.
+//
+// They replace the cuBLAS addmm calls behind nn.Linear in the reference (network/q_network.py:17,20;
 // network/mixer.py:45-55,117-145,200-206,365-375,399-409) and their autograd duals.
 #include "linear.h"
 #include "profile.h"
 
 namespace marl {
 
-constexpr int GM = 128, GN = 64, GK = 16, GT = 256;   // CTA tile and thread count
+constexpr int UM = 128, UN = 64, UK = 16, UT = 256;   // CTA tile (UMMA M, N), k-tile, threads
+constexpr int kKChunks = UK / 4;                       // 16-byte k-chunks per k-tile
+// Canonical K-major layout: element (row, k) at float offset (k/4)*PITCH + row*4 + k%4, i.e. 8 rows x 16 B
+// core matrices, SBO = 128 B between 8-row groups, LBO = PITCH*4 B between k-chunks.  PITCH = ROWS*4 + 8
+// keeps both the 128-bit stores of k-contiguous operands and the scalar stores of transposed operands
+// (almost) free of bank conflicts.
+constexpr int A_PITCH = UM * 4 + 8, B_PITCH = UN * 4 + 8;
 
-// Shared-memory tile of one operand: ROWS output rows/cols x GK reduction elements.
-//   RED operand (memory contiguous along the reduction): stored [row][k], pitch GK+4
-//   otherwise (contiguous along the output index):        stored [k][row], pitch ROWS+8
-// Both pitches make the per-lane fragment reads of mma.m16n8k8 (row = lane/4, k = lane%4) hit 32
-// distinct banks, and let the global->shared copy use one 128-bit store per fetched quad.
-template <bool RED, int ROWS>
-struct OperandTile {
-    static constexpr int LD = RED ? (GK + 4) : (ROWS + 8);
-    float v[RED ? ROWS * LD : GK * LD];
-    __device__ __forceinline__ void store_quad(int i, int r, const float4& q) {
-        if (RED) *reinterpret_cast<float4*>(&v[i * LD + r]) = q;      // (i, r..r+3)
-        else *reinterpret_cast<float4*>(&v[r * LD + i]) = q;          // (i..i+3, r)
-    }
-    __device__ __forceinline__ float* quad_ptr(int i, int r) { return RED ? &v[i * LD + r] : &v[r * LD + i]; }
-    __device__ __forceinline__ float at(int i, int k) const { return RED ? v[i * LD + k] : v[k * LD + i]; }
+struct alignas(128) UmmaStage {
+    float a_hi[kKChunks * A_PITCH];
+    float a_lo[kKChunks * A_PITCH];
+    float b_hi[kKChunks * B_PITCH];
+    float b_lo[kKChunks * B_PITCH];
 };
+constexpr int kUmmaStages = 2;
+constexpr size_t kUmmaSmem = kUmmaStages * sizeof(UmmaStage) + 128;
 
 // ---- operand fetchers: one float4 (4 consecutive elements along the contiguous dim) per call ---------
 
@@ -62,21 +68,6 @@ struct OpLin {
         }
         return make_float4(e[0], e[1], e[2], e[3]);
     }
-    // Fills dst (16 B of shared memory) with elements (i, r..r+3): cp.async when the source is a 16-byte
-    // aligned run of a real tensor, a plain store otherwise (ragged edge, one-hot columns, zero padding).
-    __device__ __forceinline__ void fill(float* dst, int i, int r) const {
-        if (i < rows) {
-            if (vec && r + 3 < o.K1) {
-                cp_async16(dst, o.x + (long long)z * o.x_bs + (long long)i * o.ldx + r);
-                return;
-            }
-            if (vec2 && r >= o.K1 && r + 3 < o.K1 + o.K2 && !(o.x2_shift && (i % o.x2_period) < o.x2_shift)) {
-                cp_async16(dst, o.x2 + (long long)z * o.x2_bs + (long long)(i - o.x2_shift) * o.ldx2 + (r - o.K1));
-                return;
-            }
-        }
-        *reinterpret_cast<float4*>(dst) = quad(i, r);
-    }
 };
 
 // Plain row-major matrix P[rows, cols] (ld), fetched along its contiguous (column) dimension.
@@ -93,10 +84,6 @@ struct OpMat {
         v.w = col + 3 < cols ? __ldg(q + 3) : 0.f;
         return v;
     }
-    __device__ __forceinline__ void fill(float* dst, int row, int col) const {
-        if (vec && row < rows && col + 3 < cols) cp_async16(dst, p + (long long)row * ld + col);
-        else *reinterpret_cast<float4*>(dst) = quad(row, col);
-    }
 };
 
 // second-source 128-bit loads: x2 aligned, pitches and region starts multiples of 4 floats
@@ -105,237 +92,280 @@ __host__ __device__ __forceinline__ bool vec2_ok(const LinOperand& o) {
            (o.K1 & 3) == 0 && (o.K2 & 3) == 0 && (o.x2_bs & 3) == 0;
 }
 
-__device__ __forceinline__ unsigned to_tf32(float x) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return u; }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+// 64-bit shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp layout): start address, leading /
+// stride byte offsets (all >> 4), version 1, no swizzle.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
+// 32-bit instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+constexpr uint32_t kUmmaIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
 
-// Accumulators of one warp: its 32x32 slice of the 128x64 CTA tile as 2 (m16) x 4 (n8) mma tiles.
-struct WarpAcc {
-    float c[2][4][4];
-    __device__ __forceinline__ WarpAcc() {
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) c[i][j][k] = 0.f;
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kUmmaIdesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait on an mbarrier phase: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int spins = 0; !done; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (spins > (1 << 24)) __trap();
     }
-    // g(row_in_tile, col_in_tile, v0, v1): the thread's outputs as 16 pairs of horizontally adjacent values
-    template <class G>
-    __device__ __forceinline__ void for_each_pair(G g) const {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int r0 = (warp & 3) * 32 + (lane >> 2), c0 = (warp >> 2) * 32 + 2 * (lane & 3);
+}
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// Per-thread share of one k-tile and where it lands in shared memory.
+//   RED operand (memory contiguous along the reduction): quad = 4 consecutive reduction elements of one
+//     row -> one 128-bit store;
+//   otherwise (contiguous along the output index): quad = rows i..i+3 at one reduction index, fetched with
+//     the 16 reduction indices of the tile across neighbouring lanes -> 4 scalar stores (the transpose into
+//     the K-major layout the tensor core wants for 32-bit operands).
+template <bool RED, int ROWS, int NQ>
+struct QuadMap {
+    int i[NQ], r[NQ];
+    __device__ __forceinline__ QuadMap() {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) g(r0 + mt * 16 + h * 8, c0 + nt * 8, c[mt][nt][2 * h], c[mt][nt][2 * h + 1]);
+        for (int l = 0; l < NQ; ++l) {
+            const int q = threadIdx.x + l * UT;
+            if (RED) { i[l] = q >> 2; r[l] = (q & 3) * 4; } else { i[l] = (q >> 4) * 4; r[l] = q & 15; }
+        }
     }
-    // f(row_in_tile, col_in_tile, value) for each of the 32 outputs this thread owns
-    template <class F>
-    __device__ __forceinline__ void for_each(F f) const {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int r0 = (warp & 3) * 32 + (lane >> 2), c0 = (warp >> 2) * 32 + 2 * (lane & 3);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                f(r0 + mt * 16, c0 + nt * 8, c[mt][nt][0]);
-                f(r0 + mt * 16, c0 + nt * 8 + 1, c[mt][nt][1]);
-                f(r0 + mt * 16 + 8, c0 + nt * 8, c[mt][nt][2]);
-                f(r0 + mt * 16 + 8, c0 + nt * 8 + 1, c[mt][nt][3]);
-            }
+    static __device__ __forceinline__ void store(float* hi, float* lo, int pitch, int i, int r, const float4& v) {
+        if (RED) {
+            const int off = (r >> 2) * pitch + i * 4;
+            *reinterpret_cast<float4*>(hi + off) = v;
+            *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        } else {
+            const int off = (r >> 2) * pitch + i * 4 + (r & 3);
+            hi[off] = v.x; hi[off + 4] = v.y; hi[off + 8] = v.z; hi[off + 12] = v.w;
+            lo[off] = tf32_lo(v.x); lo[off + 4] = tf32_lo(v.y); lo[off + 8] = tf32_lo(v.z); lo[off + 12] = tf32_lo(v.w);
+        }
     }
 };
 
-// One k-tile on the tensor cores with the 3xTF32 split (x = hi + lo, both TF32):
-//   a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi   -- fp32-level accuracy (the dropped a_lo.b_lo is ~2^-22 relative),
-// which is what the 1e-5 parity gate on losses and gradients needs; a single TF32 pass (2^-11) would not do.
-template <bool A_RED, bool B_RED>
-__device__ __forceinline__ void mma_tile(const OperandTile<A_RED, GM>& A, const OperandTile<B_RED, GN>& B, WarpAcc& acc) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ar = (warp & 3) * 32 + (lane >> 2), bn = (warp >> 2) * 32 + (lane >> 2), kq = lane & 3;
+struct UmmaCtx {
+    UmmaStage* stages;
+    uint64_t* bars;        // [kUmmaStages] "MMAs that read this stage are done"
+    uint32_t tmem;         // TMEM base (lane 0, first of UN columns)
+};
+
+// CTA prologue: carve shared memory, init the mbarriers, allocate UN TMEM columns (warp 0).
+__device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw) {
+    __shared__ uint64_t bars[kUmmaStages];
+    __shared__ uint32_t tmem_base;
+    UmmaCtx c;
+    c.stages = reinterpret_cast<UmmaStage*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    c.bars = bars;
+    if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k8 = 0; k8 < GK; k8 += 8) {
-        unsigned ah[2][4], al[2][4], bh[4][2], bl[4][2];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            const float v[4] = {A.at(ar + mt * 16, k8 + kq), A.at(ar + mt * 16 + 8, k8 + kq),
-                                A.at(ar + mt * 16, k8 + kq + 4), A.at(ar + mt * 16 + 8, k8 + kq + 4)};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { ah[mt][e] = to_tf32(v[e]); al[mt][e] = to_tf32(v[e] - __uint_as_float(ah[mt][e])); }
-        }
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            const float v[2] = {B.at(bn + nt * 8, k8 + kq), B.at(bn + nt * 8, k8 + kq + 4)};
-#pragma unroll
-            for (int e = 0; e < 2; ++e) { bh[nt][e] = to_tf32(v[e]); bl[nt][e] = to_tf32(v[e] - __uint_as_float(bh[nt][e])); }
-        }
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                mma_tf32(acc.c[mt][nt], al[mt], bh[nt]);
-                mma_tf32(acc.c[mt][nt], ah[mt], bl[nt]);
-                mma_tf32(acc.c[mt][nt], ah[mt], bh[nt]);
-            }
+        for (int s = 0; s < kUmmaStages; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(UN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    c.tmem = tmem_base;
+    return c;
 }
 
-// Per-thread share of the global->shared copy of one k-tile: A tile GM x GK = 512 quads (2 per thread),
-// B tile GN x GK = 256 quads (1 per thread).  RED: quad = 4 consecutive reduction elements of row i;
-// otherwise quad = rows i..i+3 at reduction index r.
-template <bool A_RED, bool B_RED>
-struct TileMap {
-    int ai[2], ar[2], bj, br;
-    __device__ __forceinline__ TileMap() {
-        const int tid = threadIdx.x;
+__device__ __forceinline__ void umma_teardown(const UmmaCtx& c) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "r"(UN));
+}
+
+// Main loop over the reduction range [rbeg, rend): global -> registers (two k-tiles ahead) -> shared (hi, lo)
+// -> tcgen05.mma.  FA(i, r) / FB(j, r) return the operand quad as a float4.  BIAS (weight gradient only)
+// also accumulates the column sums of the A operand into bsum.
+template <bool A_RED, bool B_RED, bool BIAS, class FA, class FB>
+__device__ __forceinline__ void umma_loop(const UmmaCtx& c, FA fa, FB fb, int i0, int j0, int rbeg, int rend, float (&bsum)[2][4]) {
+    const QuadMap<A_RED, UM, 2> ma;
+    const QuadMap<B_RED, UN, 1> mb;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nk = (rend - rbeg + UK - 1) / UK;
+    float4 ra[2][2], rb[2];            // two register sets: tiles kt and kt+1 in flight
+    auto fetch = [&](int kt, int set) {
+        const int r0 = rbeg + kt * UK;
+#pragma unroll
+        for (int l = 0; l < 2; ++l) ra[set][l] = (kt < nk && r0 + ma.r[l] < rend) ? fa(i0 + ma.i[l], r0 + ma.r[l]) : zero4;
+        rb[set] = (kt < nk && r0 + mb.r[0] < rend) ? fb(j0 + mb.i[0], r0 + mb.r[0]) : zero4;
+    };
+    fetch(0, 0);
+    fetch(1, 1);
+    for (int kt = 0; kt < nk; ++kt) {
+        const int s = kt & 1;
+        UmmaStage& st = c.stages[s];
+        if (kt >= kUmmaStages) mbar_wait(&c.bars[s], (uint32_t)((kt / kUmmaStages - 1) & 1));   // MMAs of tile kt-2 have read this stage
 #pragma unroll
         for (int l = 0; l < 2; ++l) {
-            const int q = tid + l * GT;
-            if (A_RED) { ai[l] = q >> 2; ar[l] = (q & 3) * 4; } else { ai[l] = (q & 31) * 4; ar[l] = q >> 5; }
+            const float4 v = s ? ra[1][l] : ra[0][l];
+            QuadMap<A_RED, UM, 2>::store(st.a_hi, st.a_lo, A_PITCH, ma.i[l], ma.r[l], v);
+            if (BIAS) { bsum[l][0] += v.x; bsum[l][1] += v.y; bsum[l][2] += v.z; bsum[l][3] += v.w; }
         }
-        if (B_RED) { bj = tid >> 2; br = (tid & 3) * 4; } else { bj = (tid & 15) * 4; br = tid >> 4; }
-    }
-};
-
-template <bool A_RED, bool B_RED>
-struct GemmSmem {
-    OperandTile<A_RED, GM> a;
-    OperandTile<B_RED, GN> b;
-};
-
-constexpr int kStages = 3;   // cp.async ring: two k-tiles in flight while one is on the tensor cores
-
-// Main loop.  FA(dst, i, r) / FB(dst, j, r) fill 16 bytes of shared memory with the operand quad at
-// (row i or rows i..i+3, reduction r).  BIAS additionally accumulates the column sums of the (non-RED)
-// A tile into bsum (threads 0..GM-1).  One __syncthreads per k-tile.
-template <bool A_RED, bool B_RED, bool BIAS, class FA, class FB>
-__device__ __forceinline__ void gemm_loop(GemmSmem<A_RED, B_RED>* s, WarpAcc& acc, FA fa, FB fb, int i0, int j0, int rbeg,
-                                          int rend, float& bsum) {
-    const int tid = threadIdx.x;
-    const TileMap<A_RED, B_RED> tm;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int nk = (rend - rbeg + GK - 1) / GK;
-    auto load = [&](int kt) {
-        if (kt < nk) {
-            GemmSmem<A_RED, B_RED>& st = s[kt % kStages];
-            const int r0 = rbeg + kt * GK;
+        QuadMap<B_RED, UN, 1>::store(st.b_hi, st.b_lo, B_PITCH, mb.i[0], mb.r[0], s ? rb[1] : rb[0]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int l = 0; l < 2; ++l) {
-                float* dst = st.a.quad_ptr(tm.ai[l], tm.ar[l]);
-                if (r0 + tm.ar[l] < rend) fa(dst, i0 + tm.ai[l], r0 + tm.ar[l]);
-                else *reinterpret_cast<float4*>(dst) = zero4;
+            for (int k8 = 0; k8 < UK / 8; ++k8) {
+                const uint32_t ao = (uint32_t)(2 * k8) * A_PITCH * 4, bo = (uint32_t)(2 * k8) * B_PITCH * 4;
+                const uint64_t dah = umma_desc(smem_u32(st.a_hi) + ao, A_PITCH * 4, 128), dal = umma_desc(smem_u32(st.a_lo) + ao, A_PITCH * 4, 128);
+                const uint64_t dbh = umma_desc(smem_u32(st.b_hi) + bo, B_PITCH * 4, 128), dbl = umma_desc(smem_u32(st.b_lo) + bo, B_PITCH * 4, 128);
+                umma_tf32(c.tmem, dal, dbh, (kt | k8) ? 1u : 0u);
+                umma_tf32(c.tmem, dah, dbl, 1u);
+                umma_tf32(c.tmem, dah, dbh, 1u);
             }
-            float* dst = st.b.quad_ptr(tm.bj, tm.br);
-            if (r0 + tm.br < rend) fb(dst, j0 + tm.bj, r0 + tm.br);
-            else *reinterpret_cast<float4*>(dst) = zero4;
+            umma_commit(&c.bars[s]);
         }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int kt = 0; kt < kStages - 1; ++kt) load(kt);
-    for (int kt = 0; kt < nk; ++kt) {
-        cp_async_wait<kStages - 2>();            // this thread's copies of tile kt have landed
-        __syncthreads();                         // ... everybody's; and everyone is done with tile kt-1
-        load(kt + kStages - 1);                  // refill the stage tile kt-1 occupied
-        const GemmSmem<A_RED, B_RED>& st = s[kt % kStages];
-        if (BIAS && tid < GM) {
-#pragma unroll
-            for (int k = 0; k < GK; ++k) bsum += st.a.at(tid, k);
-        }
-        mma_tile<A_RED, B_RED>(st.a, st.b, acc);
+        if (s) fetch(kt + 2, 1); else fetch(kt + 2, 0);       // refill the register set just consumed
     }
-    cp_async_wait<0>();
+    // all MMAs done: the last commit of each stage covers everything issued before it
+    const int last = nk - 1;
+    if (nk >= 1) mbar_wait(&c.bars[last & 1], (uint32_t)((last / kUmmaStages) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// Epilogue: warp w reads TMEM lanes 32*(w%4).. (= tile rows) and 32 of the 64 columns ((w/4)*32..);
+// f(row_in_tile, col_in_tile, v[4]) is called for each group of 4 consecutive columns.
+template <class F>
+__device__ __forceinline__ void umma_epilogue(const UmmaCtx& c, F f) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = (warp & 3) * 32 + lane, c0 = (warp >> 2) * 32;
+    uint32_t v[32];
+    const uint32_t taddr = c.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        float o[4] = {__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])};
+        f(row, c0 + 4 * g, o);
+    }
 }
 
 // y[M,N] (+)= act(in . w^T + bias)
 template <bool VEC_A, bool VEC_B>
-__global__ void __launch_bounds__(GT) linear_fwd_kernel(LinearFwd a) {
-    __shared__ GemmSmem<true, true> s[kStages];
-    const int z = blockIdx.z, m0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
+__global__ void __launch_bounds__(UT) linear_fwd_kernel(LinearFwd a) {
+    extern __shared__ unsigned char umma_smem[];
+    const UmmaCtx c = umma_setup(umma_smem);
+    const int z = blockIdx.z, m0 = blockIdx.x * UM, n0 = blockIdx.y * UN;
     const int K = lin_width(a.in);
     const OpLin A{a.in, z, a.M, K, VEC_A, VEC_A && vec2_ok(a.in)};               // rows m, reduction k (contiguous)
     const OpMat B{a.w + (long long)z * a.w_bs, a.ldw, a.N, K, VEC_B};             // rows n, reduction k (contiguous)
-    auto fa = [&](float* dst, int m, int k) { A.fill(dst, m, k); };
-    auto fb = [&](float* dst, int n, int k) { B.fill(dst, n, k); };
-    WarpAcc acc;
-    float unused = 0.f;
-    gemm_loop<true, true, false>(s, acc, fa, fb, m0, n0, 0, K, unused);
+    auto fa = [&](int m, int k) { return A.quad(m, k); };
+    auto fb = [&](int n, int k) { return B.quad(n, k); };
+    float unused[2][4];
+    umma_loop<true, true, false>(c, fa, fb, m0, n0, 0, K, unused);
     const float* bias = a.bias ? a.bias + (long long)z * a.b_bs : nullptr;
     float* y = a.y + (long long)z * a.y_bs;
     const float bmul = a.bias_mul != 0.f ? a.bias_mul : 1.0f;
-    const bool pair_ok = ((a.ldy & 1) == 0) && ((reinterpret_cast<uintptr_t>(y) & 7) == 0) && !a.accumulate;
-    acc.for_each_pair([&](int i, int j, float v0, float v1) {
+    const bool vec_out = ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && !a.accumulate;
+    umma_epilogue(c, [&](int i, int j, float (&v)[4]) {
         const int m = m0 + i, n = n0 + j;
         if (m >= a.M || n >= a.N) return;
-        const bool two = n + 1 < a.N;
-        if (bias) { v0 += bmul * __ldg(bias + n); if (two) v1 += bmul * __ldg(bias + n + 1); }
-        if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (bias && n + e < a.N) v[e] += bmul * __ldg(bias + n + e);
+            if (a.relu) v[e] = fmaxf(v[e], 0.f);
+        }
         float* dst = y + (long long)m * a.ldy + n;
-        if (pair_ok && two) { *reinterpret_cast<float2*>(dst) = make_float2(v0, v1); return; }
-        dst[0] = a.accumulate ? dst[0] + v0 : v0;
-        if (two) dst[1] = a.accumulate ? dst[1] + v1 : v1;
+        if (vec_out && n + 3 < a.N) { *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]); return; }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (n + e < a.N) dst[e] = a.accumulate ? dst[e] + v[e] : v[e];
     });
+    umma_teardown(c);
 }
 
 // dx[M,K] (+)= (dy[M,N] . w[N, col0:col0+K]) * (relu_src > 0)
 template <bool VEC_A, bool VEC_B>
-__global__ void __launch_bounds__(GT) linear_dgrad_kernel(LinearDgrad a) {
-    __shared__ GemmSmem<true, false> s[kStages];
-    const int z = blockIdx.z, m0 = blockIdx.x * GM, k0 = blockIdx.y * GN;
+__global__ void __launch_bounds__(UT) linear_dgrad_kernel(LinearDgrad a) {
+    extern __shared__ unsigned char umma_smem[];
+    const UmmaCtx c = umma_setup(umma_smem);
+    const int z = blockIdx.z, m0 = blockIdx.x * UM, k0 = blockIdx.y * UN;
     const OpMat A{a.dy + (long long)z * a.dy_bs, a.lddy, a.M, a.N, VEC_A};               // rows m, reduction n (contiguous)
-    const OpMat B{a.w + (long long)z * a.w_bs + a.w_col0, a.ldw, a.N, a.K, VEC_B};       // rows n (reduction), cols k
-    auto fa = [&](float* dst, int m, int n) { A.fill(dst, m, n); };
-    auto fb = [&](float* dst, int k, int n) { B.fill(dst, n, k); };
-    WarpAcc acc;
-    float unused = 0.f;
-    gemm_loop<true, false, false>(s, acc, fa, fb, m0, k0, 0, a.N, unused);
+    const OpMat B{a.w + (long long)z * a.w_bs + a.w_col0, a.ldw, a.N, a.K, VEC_B};       // rows n (reduction), cols k (contiguous)
+    auto fa = [&](int m, int n) { return A.quad(m, n); };
+    auto fb = [&](int k, int n) { return B.quad(n, k); };
+    float unused[2][4];
+    umma_loop<true, false, false>(c, fa, fb, m0, k0, 0, a.N, unused);
     float* dx = a.dx + (long long)z * a.dx_bs;
     const float* rs = a.relu_src ? a.relu_src + (long long)z * a.rs_bs : nullptr;
-    acc.for_each([&](int i, int j, float v) {
+    umma_epilogue(c, [&](int i, int j, float (&v)[4]) {
         const int m = m0 + i, k = k0 + j;
-        if (m < a.M && k < a.K) {
-            if (rs && !(__ldg(rs + (long long)m * a.ldrs + k) > 0.0f)) v = 0.0f;
-            float* dst = dx + (long long)m * a.lddx + k;
-            *dst = a.accumulate ? (*dst + v) : v;
+        if (m >= a.M) return;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (k + e >= a.K) continue;
+            float val = v[e];
+            if (rs && !(__ldg(rs + (long long)m * a.ldrs + k + e) > 0.0f)) val = 0.0f;
+            float* dst = dx + (long long)m * a.lddx + k + e;
+            *dst = a.accumulate ? (*dst + val) : val;
         }
     });
+    umma_teardown(c);
 }
 
 // dw[N, 0:K] += dy^T . in ; db[N] += colsum(dy).  Split over the M rows (blockIdx.z), atomics on the output.
 template <bool VEC_A, bool VEC_B>
-__global__ void __launch_bounds__(GT) linear_wgrad_kernel(LinearWgrad a, int splits, int chunk) {
-    __shared__ GemmSmem<false, false> s[kStages];
+__global__ void __launch_bounds__(UT) linear_wgrad_kernel(LinearWgrad a, int splits, int chunk) {
+    extern __shared__ unsigned char umma_smem[];
+    const UmmaCtx c = umma_setup(umma_smem);
     const int zb = blockIdx.z / splits, sp = blockIdx.z % splits;
-    const int i0 = blockIdx.x * GM, j0 = blockIdx.y * GN;
+    const int i0 = blockIdx.x * UM, j0 = blockIdx.y * UN;
     const int K = lin_width(a.in);
     const int mbeg = sp * chunk, mend = min(a.M, mbeg + chunk);
-    if (mbeg >= mend) return;
     const OpMat A{a.dy + (long long)zb * a.dy_bs, a.lddy, a.M, a.N, VEC_A};      // rows m (reduction), cols n
     const OpLin B{a.in, zb, a.M, K, VEC_B, VEC_B && vec2_ok(a.in)};             // rows m (reduction), cols k
-    auto fa = [&](float* dst, int n, int m) { A.fill(dst, m, n); };
-    auto fb = [&](float* dst, int k, int m) { B.fill(dst, m, k); };
-    WarpAcc acc;
-    float bsum = 0.f;
-    const int tid = threadIdx.x;
-    if (a.db != nullptr && blockIdx.y == 0) {
-        gemm_loop<false, false, true>(s, acc, fa, fb, i0, j0, mbeg, mend, bsum);
-        if (tid < GM && i0 + tid < a.N)
-            atomicAdd(a.db + (long long)zb * a.db_bs + i0 + tid, (a.db_mul != 0.f ? a.db_mul : 1.0f) * bsum);
-    } else {
-        gemm_loop<false, false, false>(s, acc, fa, fb, i0, j0, mbeg, mend, bsum);
+    auto fa = [&](int n, int m) { return A.quad(m, n); };
+    auto fb = [&](int k, int m) { return B.quad(m, k); };
+    float bsum[2][4] = {};
+    const bool want_bias = a.db != nullptr && blockIdx.y == 0;
+    if (want_bias) umma_loop<false, false, true>(c, fa, fb, i0, j0, mbeg, mend, bsum);
+    else umma_loop<false, false, false>(c, fa, fb, i0, j0, mbeg, mend, bsum);
+    if (want_bias) {
+        // the 16 reduction indices of a k-tile sit in 16 neighbouring lanes: fold them, lane r == 0 publishes
+        const QuadMap<false, UM, 2> ma;
+        const float bmul = a.db_mul != 0.f ? a.db_mul : 1.0f;
+#pragma unroll
+        for (int l = 0; l < 2; ++l)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float v = bsum[l][e];
+                v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8);
+                const int n = i0 + ma.i[l] + e;
+                if (ma.r[l] == 0 && n < a.N) atomicAdd(a.db + (long long)zb * a.db_bs + n, bmul * v);
+            }
     }
     float* dw = a.dw + (long long)zb * a.dw_bs;
-    acc.for_each([&](int i, int j, float v) {
-        const int n = i0 + i, k = j0 + j;
-        if (n < a.N && k < K) atomicAdd(dw + (long long)n * a.ldw + k, v);
-    });
+    if (mbeg < mend)
+        umma_epilogue(c, [&](int i, int j, float (&v)[4]) {
+            const int n = i0 + i, k = j0 + j;
+            if (n >= a.N) return;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (k + e < K) atomicAdd(dw + (long long)n * a.ldw + k + e, v[e]);
+        });
+    umma_teardown(c);
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -350,17 +380,25 @@ static bool vec_ok_mat(const float* p, int ld, long long bs, int col0 = 0) {
     return p && aligned16(p + col0) && (ld & 3) == 0 && ((bs & 3) == 0);
 }
 
-#define MARL_DISPATCH2(KERNEL, VA, VB, GRID, ST, ...)                                              \
-    do {                                                                                           \
-        if (VA && VB) KERNEL<true, true><<<GRID, GT, 0, ST>>>(__VA_ARGS__);                        \
-        else if (VA) KERNEL<true, false><<<GRID, GT, 0, ST>>>(__VA_ARGS__);                        \
-        else if (VB) KERNEL<false, true><<<GRID, GT, 0, ST>>>(__VA_ARGS__);                        \
-        else KERNEL<false, false><<<GRID, GT, 0, ST>>>(__VA_ARGS__);                               \
+#define MARL_DISPATCH2(KERNEL, VA, VB, GRID, ST, ...)                                                      \
+    do {                                                                                                   \
+        static bool attr_done = false;                                                                     \
+        if (!attr_done) {                                                                                  \
+            cudaFuncSetAttribute(KERNEL<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);   \
+            cudaFuncSetAttribute(KERNEL<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);  \
+            cudaFuncSetAttribute(KERNEL<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);  \
+            cudaFuncSetAttribute(KERNEL<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem); \
+            attr_done = true;                                                                              \
+        }                                                                                                  \
+        if (VA && VB) KERNEL<true, true><<<GRID, UT, kUmmaSmem, ST>>>(__VA_ARGS__);                        \
+        else if (VA) KERNEL<true, false><<<GRID, UT, kUmmaSmem, ST>>>(__VA_ARGS__);                        \
+        else if (VB) KERNEL<false, true><<<GRID, UT, kUmmaSmem, ST>>>(__VA_ARGS__);                        \
+        else KERNEL<false, false><<<GRID, UT, kUmmaSmem, ST>>>(__VA_ARGS__);                               \
     } while (0)
 
 int linear_fwd(const LinearFwd& a, cudaStream_t st) {
     if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return MARL_OK;
-    dim3 grid(cdiv(a.M, GM), cdiv(a.N, GN), a.batch);
+    dim3 grid(cdiv(a.M, UM), cdiv(a.N, UN), a.batch);
     const bool va = vec_ok_lin(a.in), vb = vec_ok_mat(a.w, a.ldw, a.w_bs);
     { ProfScope ps_("linear_fwd_kernel", st); MARL_DISPATCH2(linear_fwd_kernel, va, vb, grid, st, a); }
     MARL_LAUNCH_CHECK();
@@ -369,7 +407,7 @@ int linear_fwd(const LinearFwd& a, cudaStream_t st) {
 
 int linear_dgrad(const LinearDgrad& a, cudaStream_t st) {
     if (a.M <= 0 || a.K <= 0 || a.batch <= 0) return MARL_OK;
-    dim3 grid(cdiv(a.M, GM), cdiv(a.K, GN), a.batch);
+    dim3 grid(cdiv(a.M, UM), cdiv(a.K, UN), a.batch);
     const bool va = vec_ok_mat(a.dy, a.lddy, a.dy_bs), vb = vec_ok_mat(a.w, a.ldw, a.w_bs, a.w_col0);
     { ProfScope ps_("linear_dgrad_kernel", st); MARL_DISPATCH2(linear_dgrad_kernel, va, vb, grid, st, a); }
     MARL_LAUNCH_CHECK();
@@ -379,12 +417,12 @@ int linear_dgrad(const LinearDgrad& a, cudaStream_t st) {
 int linear_wgrad(const LinearWgrad& a, cudaStream_t st) {
     if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return MARL_OK;
     const int K = lin_width(a.in);
-    const int tiles = cdiv(a.N, GM) * cdiv(K, GN) * a.batch;
+    const int tiles = cdiv(a.N, UM) * cdiv(K, UN) * a.batch;
     int splits = cdiv(2 * kNumSMs, tiles);
     splits = max(1, min(splits, cdiv(a.M, 256)));
-    int chunk = cdiv(cdiv(a.M, splits), GK) * GK;
+    int chunk = cdiv(cdiv(a.M, splits), UK) * UK;
     splits = cdiv(a.M, chunk);
-    dim3 grid(cdiv(a.N, GM), cdiv(K, GN), a.batch * splits);
+    dim3 grid(cdiv(a.N, UM), cdiv(K, UN), a.batch * splits);
     const bool va = vec_ok_mat(a.dy, a.lddy, a.dy_bs), vb = vec_ok_lin(a.in);
     { ProfScope ps_("linear_wgrad_kernel", st); MARL_DISPATCH2(linear_wgrad_kernel, va, vb, grid, st, a, splits, chunk); }
     MARL_LAUNCH_CHECK();

@@ -104,7 +104,7 @@ def params_close(mine, ref, lr, n_steps, report=None, what=""):
     The first optimiser steps divide g by ~|g| (v starts at 0), so an entry whose gradient is at the
     fp32 noise level can move by up to ~10*lr per step in EITHER implementation (the fp32 reference
     sits 2.5e-5 max-norm from its own fp64 run at the 2s3z shape, tools/diag_parity.py).  Therefore:
-    (a) every entry within 1e-5*max|ref| + 0.1*lr*n_steps, and (b) for big tensors at most 1% of the
+    (a) every entry within 1e-5*max|ref| + 0.25*lr*n_steps (2.5% of the largest possible RMSprop move), and (b) for big tensors at most 1% of the
     entries beyond the strict 1e-5 bound.  The strict functional check of the update is the loss of the
     NEXT step, which the callers compare at 1e-5 / 5e-5."""
     x = np.asarray(mine.detach().cpu() if torch.is_tensor(mine) else mine, dtype=np.float64).reshape(-1)
@@ -113,7 +113,7 @@ def params_close(mine, ref, lr, n_steps, report=None, what=""):
         return True
     scale = max(float(np.max(np.abs(y))), 1e-30)
     diff = np.abs(x - y)
-    ok = bool(diff.max() <= 1e-5 * scale + 0.1 * lr * n_steps)
+    ok = bool(diff.max() <= 1e-5 * scale + 0.25 * lr * n_steps)
     if y.size >= 1000:
         ok = ok and float((diff > 1e-5 * scale).mean()) <= 0.01
     if not ok and report is not None:
