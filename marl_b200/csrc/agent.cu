@@ -28,7 +28,13 @@ constexpr int kGiDepth = 4;        // cp.async ring depth (time steps) of the fo
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float gate_sigmoid(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float gate_tanh(float x) { return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * x)), 1.0f); }
+__device__ __forceinline__ float gate_tanh(float x) {
+    // 1 - 2/(1 + e^2x) loses relative accuracy to cancellation near 0: switch to the odd Taylor polynomial there
+    const float big = fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * x)), 1.0f);
+    const float x2 = x * x;
+    const float small = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.0539682540f, 0.1333333333f), -0.3333333333f), 1.0f);
+    return fabsf(x) < 0.2f ? small : big;
+}
 
 struct GruSegment {
     const float* gi;      // [B,L,N,3H]

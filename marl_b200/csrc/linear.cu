@@ -5,8 +5,8 @@
 // mbarrier, and the epilogue reads the accumulator back with tcgen05.ld.
 //
 // Accuracy: the parity gate on losses / gradients is 1e-5 relative, which a single TF32 pass (2^-11)
-// cannot meet.  Every operand tile is therefore stored twice, x = hi + lo with hi = the fp32 word
-// itself (the tensor core reads its top 19 bits) and lo = x - trunc_tf32(x), and each k-step issues
+// cannot meet.  Every operand tile is therefore stored twice, x = hi + lo with hi = rna_tf32(x) and
+// lo = rna_tf32(x - hi), and each k-step issues
 //     D += A_lo.B_hi ;  D += A_hi.B_lo ;  D += A_hi.B_hi            (3xTF32, ~5e-7 relative, fp32 accumulate)
 // -- measured with tools/micro/tc5_probe.cu.
 //
@@ -32,6 +32,14 @@ struct alignas(128) UmmaStage {
     float b_lo[kKChunks * B_PITCH];
 };
 constexpr int kUmmaStages = 2;
+// Accumulators per CTA tile in TMEM.  The tensor core adds every K=8 product block into the fp32 accumulator
+// with truncation, an error that grows with the NUMBER of accumulator updates; the hi.hi products are
+// therefore dealt round-robin to kAccMain accumulators, the two (2^-11 smaller) correction products go to
+// their own accumulator, and the epilogue adds the four up in fp32.
+constexpr int kAccMain = 3, kAccAll = kAccMain + 1, kTmemCols = 256;
+static_assert(kAccAll * UN <= kTmemCols, "TMEM allocation too small");
+// short reductions (<= 32 accumulator updates) keep one main accumulator: reading TMEM back costs ~0.25 us each
+__host__ __device__ __forceinline__ int acc_main_count(int nsteps) { return nsteps > 32 ? kAccMain : 1; }
 constexpr size_t kUmmaSmem = kUmmaStages * sizeof(UmmaStage) + 128;
 
 // ---- operand fetchers: one float4 (4 consecutive elements along the contiguous dim) per call ---------
@@ -120,7 +128,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (spins > (1 << 24)) __trap();
     }
 }
-__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// x = hi + lo with both halves ROUNDED to TF32 (cvt.rna): unbiased, unlike the truncation the tensor core
+// applies to raw fp32 words, whose error grows linearly with the reduction length.
+__device__ __forceinline__ float tf32_rna(float x) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) { hi = tf32_rna(x); lo = tf32_rna(x - hi); }
 
 // Per-thread share of one k-tile and where it lands in shared memory.
 //   RED operand (memory contiguous along the reduction): quad = 4 consecutive reduction elements of one
@@ -139,14 +150,16 @@ struct QuadMap {
         }
     }
     static __device__ __forceinline__ void store(float* hi, float* lo, int pitch, int i, int r, const float4& v) {
+        float4 h, l;
+        tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
         if (RED) {
             const int off = (r >> 2) * pitch + i * 4;
-            *reinterpret_cast<float4*>(hi + off) = v;
-            *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+            *reinterpret_cast<float4*>(hi + off) = h;
+            *reinterpret_cast<float4*>(lo + off) = l;
         } else {
             const int off = (r >> 2) * pitch + i * 4 + (r & 3);
-            hi[off] = v.x; hi[off + 4] = v.y; hi[off + 8] = v.z; hi[off + 12] = v.w;
-            lo[off] = tf32_lo(v.x); lo[off + 4] = tf32_lo(v.y); lo[off + 8] = tf32_lo(v.z); lo[off + 12] = tf32_lo(v.w);
+            hi[off] = h.x; hi[off + 4] = h.y; hi[off + 8] = h.z; hi[off + 12] = h.w;
+            lo[off] = l.x; lo[off + 4] = l.y; lo[off + 8] = l.z; lo[off + 12] = l.w;
         }
     }
 };
@@ -158,7 +171,9 @@ struct UmmaCtx {
 };
 
 // CTA prologue: carve shared memory, init the mbarriers, allocate UN TMEM columns (warp 0).
-__device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw) {
+__device__ __forceinline__ uint32_t tmem_cols_for(int nsteps) { return acc_main_count(nsteps) > 1 ? (uint32_t)kTmemCols : 2u * UN; }
+
+__device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw, int nsteps) {
     __shared__ uint64_t bars[kUmmaStages];
     __shared__ uint32_t tmem_base;
     UmmaCtx c;
@@ -170,7 +185,7 @@ __device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(UN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(tmem_cols_for(nsteps)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -180,10 +195,10 @@ __device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw) {
     return c;
 }
 
-__device__ __forceinline__ void umma_teardown(const UmmaCtx& c) {
+__device__ __forceinline__ void umma_teardown(const UmmaCtx& c, int nsteps) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "r"(UN));
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "r"(tmem_cols_for(nsteps)));
 }
 
 // Main loop over the reduction range [rbeg, rend): global -> registers (two k-tiles ahead) -> shared (hi, lo)
@@ -195,6 +210,7 @@ __device__ __forceinline__ void umma_loop(const UmmaCtx& c, FA fa, FB fb, int i0
     const QuadMap<B_RED, UN, 1> mb;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int nk = (rend - rbeg + UK - 1) / UK;
+    const int nmain = acc_main_count(nk * (UK / 8));
     float4 ra[2][2], rb[2];            // two register sets: tiles kt and kt+1 in flight
     auto fetch = [&](int kt, int set) {
         const int r0 = rbeg + kt * UK;
@@ -225,9 +241,10 @@ __device__ __forceinline__ void umma_loop(const UmmaCtx& c, FA fa, FB fb, int i0
                 const uint32_t ao = (uint32_t)(2 * k8) * A_PITCH * 4, bo = (uint32_t)(2 * k8) * B_PITCH * 4;
                 const uint64_t dah = umma_desc(smem_u32(st.a_hi) + ao, A_PITCH * 4, 128), dal = umma_desc(smem_u32(st.a_lo) + ao, A_PITCH * 4, 128);
                 const uint64_t dbh = umma_desc(smem_u32(st.b_hi) + bo, B_PITCH * 4, 128), dbl = umma_desc(smem_u32(st.b_lo) + bo, B_PITCH * 4, 128);
-                umma_tf32(c.tmem, dal, dbh, (kt | k8) ? 1u : 0u);
-                umma_tf32(c.tmem, dah, dbl, 1u);
-                umma_tf32(c.tmem, dah, dbh, 1u);
+                const int step = kt * (UK / 8) + k8;                       // global k8 index of this CTA
+                umma_tf32(c.tmem + nmain * UN, dal, dbh, step ? 1u : 0u);      // corrections
+                umma_tf32(c.tmem + nmain * UN, dah, dbl, 1u);
+                umma_tf32(c.tmem + (step % nmain) * UN, dah, dbh, step >= nmain ? 1u : 0u);
             }
             umma_commit(&c.bars[s]);
         }
@@ -242,21 +259,29 @@ __device__ __forceinline__ void umma_loop(const UmmaCtx& c, FA fa, FB fb, int i0
 // Epilogue: warp w reads TMEM lanes 32*(w%4).. (= tile rows) and 32 of the 64 columns ((w/4)*32..);
 // f(row_in_tile, col_in_tile, v[4]) is called for each group of 4 consecutive columns.
 template <class F>
-__device__ __forceinline__ void umma_epilogue(const UmmaCtx& c, F f) {
+__device__ __forceinline__ void umma_epilogue(const UmmaCtx& c, int nsteps, F f) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = (warp & 3) * 32 + lane, c0 = (warp >> 2) * 32;
-    uint32_t v[32];
-    const uint32_t taddr = c.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int nmain = acc_main_count(nsteps);
+    float sum[32];
+#pragma unroll
+    for (int acc = 0; acc < kAccAll; ++acc) {
+        if (acc > nmain) continue;                            // main accumulators 0..nmain-1, corrections at nmain
+        uint32_t v[32];
+        const uint32_t taddr = c.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * UN + c0);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                       "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sum[e] = (acc == 0) ? __uint_as_float(v[e]) : sum[e] + __uint_as_float(v[e]);
+    }
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-        float o[4] = {__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])};
+        float o[4] = {sum[4 * g], sum[4 * g + 1], sum[4 * g + 2], sum[4 * g + 3]};
         f(row, c0 + 4 * g, o);
     }
 }
@@ -265,9 +290,10 @@ __device__ __forceinline__ void umma_epilogue(const UmmaCtx& c, F f) {
 template <bool VEC_A, bool VEC_B>
 __global__ void __launch_bounds__(UT) linear_fwd_kernel(LinearFwd a) {
     extern __shared__ unsigned char umma_smem[];
-    const UmmaCtx c = umma_setup(umma_smem);
-    const int z = blockIdx.z, m0 = blockIdx.x * UM, n0 = blockIdx.y * UN;
     const int K = lin_width(a.in);
+    const int nsteps = ((K + UK - 1) / UK) * (UK / 8);
+    const UmmaCtx c = umma_setup(umma_smem, nsteps);
+    const int z = blockIdx.z, m0 = blockIdx.x * UM, n0 = blockIdx.y * UN;
     const OpLin A{a.in, z, a.M, K, VEC_A, VEC_A && vec2_ok(a.in)};               // rows m, reduction k (contiguous)
     const OpMat B{a.w + (long long)z * a.w_bs, a.ldw, a.N, K, VEC_B};             // rows n, reduction k (contiguous)
     auto fa = [&](int m, int k) { return A.quad(m, k); };
@@ -278,12 +304,15 @@ __global__ void __launch_bounds__(UT) linear_fwd_kernel(LinearFwd a) {
     float* y = a.y + (long long)z * a.y_bs;
     const float bmul = a.bias_mul != 0.f ? a.bias_mul : 1.0f;
     const bool vec_out = ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && !a.accumulate;
-    umma_epilogue(c, [&](int i, int j, float (&v)[4]) {
+    __shared__ float sbias[UN];          // the tile's bias slice, fetched once per CTA
+    if (threadIdx.x < UN) sbias[threadIdx.x] = (bias && n0 + threadIdx.x < a.N) ? bmul * __ldg(bias + n0 + threadIdx.x) : 0.f;
+    __syncthreads();
+    umma_epilogue(c, nsteps, [&](int i, int j, float (&v)[4]) {
         const int m = m0 + i, n = n0 + j;
         if (m >= a.M || n >= a.N) return;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            if (bias && n + e < a.N) v[e] += bmul * __ldg(bias + n + e);
+            v[e] += sbias[j + e];
             if (a.relu) v[e] = fmaxf(v[e], 0.f);
         }
         float* dst = y + (long long)m * a.ldy + n;
@@ -292,14 +321,15 @@ __global__ void __launch_bounds__(UT) linear_fwd_kernel(LinearFwd a) {
         for (int e = 0; e < 4; ++e)
             if (n + e < a.N) dst[e] = a.accumulate ? dst[e] + v[e] : v[e];
     });
-    umma_teardown(c);
+    umma_teardown(c, nsteps);
 }
 
 // dx[M,K] (+)= (dy[M,N] . w[N, col0:col0+K]) * (relu_src > 0)
 template <bool VEC_A, bool VEC_B>
 __global__ void __launch_bounds__(UT) linear_dgrad_kernel(LinearDgrad a) {
     extern __shared__ unsigned char umma_smem[];
-    const UmmaCtx c = umma_setup(umma_smem);
+    const int nsteps = ((a.N + UK - 1) / UK) * (UK / 8);
+    const UmmaCtx c = umma_setup(umma_smem, nsteps);
     const int z = blockIdx.z, m0 = blockIdx.x * UM, k0 = blockIdx.y * UN;
     const OpMat A{a.dy + (long long)z * a.dy_bs, a.lddy, a.M, a.N, VEC_A};               // rows m, reduction n (contiguous)
     const OpMat B{a.w + (long long)z * a.w_bs + a.w_col0, a.ldw, a.N, a.K, VEC_B};       // rows n (reduction), cols k (contiguous)
@@ -309,30 +339,47 @@ __global__ void __launch_bounds__(UT) linear_dgrad_kernel(LinearDgrad a) {
     umma_loop<true, false, false>(c, fa, fb, m0, k0, 0, a.N, unused);
     float* dx = a.dx + (long long)z * a.dx_bs;
     const float* rs = a.relu_src ? a.relu_src + (long long)z * a.rs_bs : nullptr;
-    umma_epilogue(c, [&](int i, int j, float (&v)[4]) {
+    const bool vec_rs = rs && ((a.ldrs & 3) == 0) && ((reinterpret_cast<uintptr_t>(rs) & 15) == 0);
+    const bool vec_dx = ((a.lddx & 3) == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0);
+    umma_epilogue(c, nsteps, [&](int i, int j, float (&v)[4]) {
         const int m = m0 + i, k = k0 + j;
-        if (m >= a.M) return;
+        if (m >= a.M || k >= a.K) return;
+        const bool full = k + 3 < a.K;
+        if (rs) {
+            float r4[4] = {1.f, 1.f, 1.f, 1.f};
+            if (vec_rs && full) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(rs + (long long)m * a.ldrs + k));
+                r4[0] = t.x; r4[1] = t.y; r4[2] = t.z; r4[3] = t.w;
+            } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (k + e >= a.K) continue;
-            float val = v[e];
-            if (rs && !(__ldg(rs + (long long)m * a.ldrs + k + e) > 0.0f)) val = 0.0f;
-            float* dst = dx + (long long)m * a.lddx + k + e;
-            *dst = a.accumulate ? (*dst + val) : val;
+                for (int e = 0; e < 4; ++e) if (k + e < a.K) r4[e] = __ldg(rs + (long long)m * a.ldrs + k + e);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (!(r4[e] > 0.0f)) v[e] = 0.0f;
         }
+        float* dst = dx + (long long)m * a.lddx + k;
+        if (vec_dx && full) {
+            float4 o = make_float4(v[0], v[1], v[2], v[3]);
+            if (a.accumulate) { const float4 t = *reinterpret_cast<float4*>(dst); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            *reinterpret_cast<float4*>(dst) = o;
+            return;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (k + e < a.K) dst[e] = a.accumulate ? dst[e] + v[e] : v[e];
     });
-    umma_teardown(c);
+    umma_teardown(c, nsteps);
 }
 
 // dw[N, 0:K] += dy^T . in ; db[N] += colsum(dy).  Split over the M rows (blockIdx.z), atomics on the output.
 template <bool VEC_A, bool VEC_B>
 __global__ void __launch_bounds__(UT) linear_wgrad_kernel(LinearWgrad a, int splits, int chunk) {
     extern __shared__ unsigned char umma_smem[];
-    const UmmaCtx c = umma_setup(umma_smem);
     const int zb = blockIdx.z / splits, sp = blockIdx.z % splits;
     const int i0 = blockIdx.x * UM, j0 = blockIdx.y * UN;
     const int K = lin_width(a.in);
     const int mbeg = sp * chunk, mend = min(a.M, mbeg + chunk);
+    const int nsteps = mend > mbeg ? ((mend - mbeg + UK - 1) / UK) * (UK / 8) : 0;
+    const UmmaCtx c = umma_setup(umma_smem, nsteps);
     const OpMat A{a.dy + (long long)zb * a.dy_bs, a.lddy, a.M, a.N, VEC_A};      // rows m (reduction), cols n
     const OpLin B{a.in, zb, a.M, K, VEC_B, VEC_B && vec2_ok(a.in)};             // rows m (reduction), cols k
     auto fa = [&](int n, int m) { return A.quad(m, n); };
@@ -357,15 +404,21 @@ __global__ void __launch_bounds__(UT) linear_wgrad_kernel(LinearWgrad a, int spl
             }
     }
     float* dw = a.dw + (long long)zb * a.dw_bs;
+    const bool vec_dw = ((a.ldw & 3) == 0) && ((reinterpret_cast<uintptr_t>(dw) & 15) == 0);
     if (mbeg < mend)
-        umma_epilogue(c, [&](int i, int j, float (&v)[4]) {
+        umma_epilogue(c, nsteps, [&](int i, int j, float (&v)[4]) {
             const int n = i0 + i, k = j0 + j;
-            if (n >= a.N) return;
+            if (n >= a.N || k >= K) return;
+            float* dst = dw + (long long)n * a.ldw + k;
+            if (vec_dw && k + 3 < K) {      // one 128-bit reduction instead of four atomics
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+                return;
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                if (k + e < K) atomicAdd(dw + (long long)n * a.ldw + k + e, v[e]);
+                if (k + e < K) atomicAdd(dst + e, v[e]);
         });
-    umma_teardown(c);
+    umma_teardown(c, nsteps);
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }

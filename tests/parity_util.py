@@ -119,3 +119,23 @@ def params_close(mine, ref, lr, n_steps, report=None, what=""):
     if not ok and report is not None:
         report.append(f"{what}: max diff {diff.max():.3e} (scale {scale:.3e}), frac beyond 1e-5: {(diff > 1e-5 * scale).mean():.4f}")
     return ok
+
+
+def compare_grads(mine, theirs, tol, report):
+    """Gradients: every tensor with >= 64 entries within `tol` (max-norm, relative to that tensor); tensors
+    with fewer entries (biases of 1-wide heads: a single cancelling sum over all samples) within 5*tol; and
+    the whole gradient, concatenated, within `tol`."""
+    num = den = 0.0
+    for k, v in theirs.items():
+        if v is None:
+            continue
+        x = np.asarray(mine[k].detach().cpu(), dtype=np.float64)
+        y = np.asarray(v.detach().cpu() if torch.is_tensor(v) else v, dtype=np.float64)
+        e = rel_err(x, y)
+        lim = tol if y.size >= 64 else 5 * tol
+        if e > lim:
+            report.append(f"grad[{k}] rel err {e:.3e} > {lim:g}")
+        num = max(num, float(np.max(np.abs(x - y))) if y.size else 0.0)
+        den = max(den, float(np.max(np.abs(y))) if y.size else 0.0)
+    if num > tol * max(den, 1e-30):
+        report.append(f"whole gradient: max abs diff {num:.3e} vs scale {den:.3e}")

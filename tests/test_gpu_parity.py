@@ -223,7 +223,7 @@ def _train_compare(args, batch, steps, graph):
                 if hard:
                     report.append(f"argmax: {n_bad} mismatches, {hard} beyond fp32 noise")
             mine = {f"{g}.{k}": p.grad for g, m in PU.module_groups(learner).items() for k, p in m.named_parameters()}
-            PU.compare_named(mine, info["clipped_grads"], TOL, "grad", report)
+            PU.compare_grads(mine, info["clipped_grads"], TOL, report)
         mine = {f"{g}.{k}": p for g, m in PU.module_groups(learner).items() for k, p in m.named_parameters()}
         for g, k, p in st.flat_params():
             if f"{g}.{k}" in mine and info["clipped_grads"].get(f"{g}.{k}") is not None:
