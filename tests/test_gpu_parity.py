@@ -196,13 +196,15 @@ def test_matrix_game_q_table_golden():
 
 
 # ------------------------------------------------------------------------------------------ learner vs oracle, BASELINE shapes
-def _train_compare(args, batch, steps, graph):
+def _train_compare(args, batch, steps, graph, arbitrate=False):
     args.cuda_graph = graph
     learner, st = PU.build_pair(args)
+    st64 = MO.LearnerState(st.cfg, PU.export_params(learner), dtype=torch.float64) if arbitrate else None
     report = []
     for step in range(steps):
         loss = learner.train({k: v.copy() for k, v in batch.items()}, step)
         oloss, info = MO.train_step(st, batch, step)
+        truth = MO.train_step(st64, batch, step)[1]["clipped_grads"] if arbitrate and step == 0 else None
         if abs(loss - oloss) > TOL * abs(oloss):
             report.append(f"step {step}: loss {loss} vs {oloss}")
         ws = learner.last["ws"]
@@ -223,10 +225,10 @@ def _train_compare(args, batch, steps, graph):
                 if hard:
                     report.append(f"argmax: {n_bad} mismatches, {hard} beyond fp32 noise")
             mine = {f"{g}.{k}": p.grad for g, m in PU.module_groups(learner).items() for k, p in m.named_parameters()}
-            PU.compare_grads(mine, info["clipped_grads"], TOL, report)
+            PU.compare_grads(mine, info["clipped_grads"], TOL, report, truth)
         mine = {f"{g}.{k}": p for g, m in PU.module_groups(learner).items() for k, p in m.named_parameters()}
         for g, k, p in st.flat_params():
-            if f"{g}.{k}" in mine and info["clipped_grads"].get(f"{g}.{k}") is not None:
+            if f"{g}.{k}" in mine and info["clipped_grads"].get(f"{g}.{k}") is not None and not arbitrate:
                 PU.params_close(mine[f"{g}.{k}"], p, args.lr, step + 1, report, f"param@{step}[{g}.{k}]")
     assert not report, "\n".join(report)
 
@@ -252,6 +254,17 @@ def test_learner_qtran_vs_oracle():
     args = PU.make_args("qtran_base", 12, 9, 30, 50, 10)
     batch = synthetic_batch(0, 8, 10, 12, 9, 30, 50)
     _train_compare(args, batch, 2, True)
+
+
+@pytest.mark.parametrize("name", ["3s5z", "27m_vs_30m"])
+def test_full_size_baseline_configs_one_step(name):
+    """BASELINE.json configs 3 and 4 at FULL size (QPLEX 3s5z-shaped B=128 T=150; QTRAN-base 27m_vs_30m-shaped
+    B=32 T=180): one train step against the CPU oracle (losses, Q_tot / joint Q, argmax, all gradients)."""
+    from marl_b200.synthetic import CONFIGS
+    c = CONFIGS[name]
+    args = PU.make_args(c["alg"], c["N"], c["A"], c["O"], c["S"], c["T"])
+    batch = synthetic_batch(0, c["B"], c["T"], c["N"], c["A"], c["O"], c["S"])
+    _train_compare(args, batch, 1, False, arbitrate=True)
 
 
 def test_qtran_modules_forward_backward():
