@@ -41,41 +41,54 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled every 5 ms DURING the timed regions (NVML; the same counters the
+    nvidia-smi line of B200_PROFILING.md prints)."""
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self._stop, self.t = index, [], False, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:      # noqa: BLE001
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _loop(self):
+        nv, h = self.nv, self.h
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:   # noqa: BLE001
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((sm, reasons))
+            except Exception:       # noqa: BLE001
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self._stop = True
+        self.t.join(timeout=1)
+        nv = self.nv
+        sm = [r[0] for r in self.rows]
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        seen = 0
+        for _, r in self.rows:
+            seen |= r
+        reasons = sorted(n for n, b in bits.items() if seen & b)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(mx), "reasons": reasons,
+                "samples": len(sm)}
 
 
 def make_args(alg="qmix"):
@@ -230,13 +243,27 @@ def run_ours(opt):
         learner.train(host_view(i), step); step += 1
     ev1.record()
     barrier()
-    ms_e2e = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    ms_e2e_sync = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
     h2d = learner.h2d_bytes_last
+    # same, with the next batch's H2D copy started (learner.prefetch) before the current train() call: the copy
+    # of every step is still inside the timed region, it just overlaps the previous step's compute
+    hv = [host_view(0), host_view(1)]
+    barrier()
+    ev0.record()
+    learner.prefetch(hv[0])
+    for i in range(K):
+        if i + 1 < K:
+            learner.prefetch(hv[(i + 1) & 1])
+        learner.train(hv[i & 1], step); step += 1
+    ev1.record()
+    barrier()
+    ms_e2e = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         dist.all_reduce(ms_dev, op=dist.ReduceOp.MAX)
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(ms_dev) / K, float(ms_e2e) / K
+        dist.all_reduce(ms_e2e_sync, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e, ms_e2e_sync = float(ms_dev) / K, float(ms_e2e) / K, float(ms_e2e_sync) / K
     launches = learner.launches_per_step + 1          # + the ingest launch
 
     # ---- per-kernel device time (eager pass, CUDA events around every launch of the library) ---------
@@ -244,6 +271,7 @@ def run_ours(opt):
     L.profile(rank == 0)
     P = 10
     for i in range(P):
+        L.call("marl_spin_us", 4000, L.stream_ptr())      # let the host run ahead: events then bracket device time only
         learner.train(dev_batches[i % NB], step); step += 1
     prof = L.profile_collect() if rank == 0 else {}
     L.profile(False)
@@ -270,19 +298,52 @@ def run_ours(opt):
     torch.cuda.synchronize()
     fp32_peak = flops.value / (a.elapsed_time(b) * 1e-3) / 1e12
 
+    # ---- BASELINE config 5: 4096 matrix-game envs stepped on the GPU feeding the QMIX learner directly ----
+    cfg5 = None
+    if world == 1:
+        from marl_b200.common.arguments import default_args
+        from marl_b200.env.single_state_matrix_game import BatchedMatrixGame
+        a5 = default_args(alg="qmix", n_agents=2, n_actions=3, obs_shape=1, state_shape=1, episode_limit=1, map="matrix")
+        l5 = QLearner(SharedMAC(a5), a5)
+        env5 = BatchedMatrixGame(PAYOFF1, 4096)
+        acts5 = torch.randint(0, 3, (4096, 2), device="cuda")
+        for i in range(5):
+            ep = dict(env5.step(acts5)); ep["max_episode_len"] = 1
+            l5.train(ep, i)
+        torch.cuda.synchronize()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for i in range(50):
+            ep = dict(env5.step(acts5)); ep["max_episode_len"] = 1
+            l5.train(ep, 5 + i)
+        b_.record(); torch.cuda.synchronize()
+        ms5 = a_.elapsed_time(b_) / 50
+        cfg5 = {"workload": "4096 matrix-game envs (one kernel launch) -> QMIX train step on the emitted device batch",
+                "ms_per_iteration": ms5, "env_steps_per_s": 4096 / (ms5 * 1e-3), "episode_samples_per_s": 4096 / (ms5 * 1e-3)}
+
     roofline = None
     if kernels:
-        dom = next(iter(kernels))
+        # dominant kernel = the longest single launch of the step
+        dom = max(kernels, key=lambda k: kernels[k]["us_per_step"] / max(kernels[k]["launches_per_step"], 1))
         dom_us = kernels[dom]["us_per_step"] / max(kernels[dom]["launches_per_step"], 1)
-        if dom == "gru_unroll_fwd_kernel":
-            ach = GRU_FWD_FLOP / (dom_us * 1e-6) / 1e12
-            roofline = {"kernel": dom, "bound": "fp32_fma (latency-bound recurrence at B=32: 160 rows x 240 dependent steps)",
-                        "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": None,
-                        "us_per_launch": dom_us, "peak_source": "marl_fma_probe on this GPU"}
-        else:
-            ach = FLOP_PER_STEP * kernels[dom]["share"] / (kernels[dom]["us_per_step"] * 1e-6) / 1e12
-            roofline = {"kernel": dom, "bound": "fp32_fma", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                        "frac": ach / fp32_peak, "traffic": None, "us_per_launch": dom_us}
+        flop = GRU_FWD_FLOP if dom == "gru_unroll_fwd_kernel" else FLOP_PER_STEP * kernels[dom]["share"]
+        ach = flop / (dom_us * 1e-6) / 1e12
+        roofline = {"kernel": dom, "bound": "fp32_fma; latency-bound at B=32 (160 rows x 240 dependent GRU steps, ~0.44 us/step)",
+                    "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": None,
+                    "us_per_launch": dom_us, "algorithmic_flop_per_launch": flop,
+                    "peak_source": "marl_fma_probe on this GPU (MEASURED_PEAKS.json has no fp32 figure)"}
+    gemm_us = sum(v["us_per_step"] for k, v in kernels.items() if k.startswith("linear_"))
+    gemm_flop = FLOP_PER_STEP - GRU_FWD_FLOP - GRU_FWD_FLOP / 3        # everything but the two recurrent kernels
+    bf16_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
+    roofline_gemm = None
+    if gemm_us:
+        ach = gemm_flop / (gemm_us * 1e-6) / 1e12
+        roofline_gemm = {"kernel": "linear_{fwd,dgrad,wgrad}_kernel (tcgen05 kind::tf32, 3xTF32)", "bound": "tensor",
+                         "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak, "traffic": None,
+                         "us_per_step": gemm_us,
+                         "note": "algorithmic fp32 FLOPs of all dense layers / summed launch time; the TF32 pipe peaks at "
+                                 "half the bf16 figure and every product is issued 3 times (3xTF32), so 1/6 of `peak` is the "
+                                 "ceiling of this scheme; at cfg-2 sizes (19200 x 64..192 outputs) the launches are latency-bound"}
     step_tflops = FLOP_PER_STEP / (ms_dev * 1e-3) / 1e12
 
     cpu = None
@@ -301,17 +362,22 @@ def run_ours(opt):
                    "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2": f"inputs rotate over {NB} resident batches (150 MB > 126 MB L2)"},
         "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "episode-samples/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8},
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+                "how": "QLearner.train(host float64 dict) with learner.prefetch(next batch) issued before it: H2D of step "
+                       "k+1 overlaps the compute of step k; every copy and every loss read-back is inside the timed region",
+                "without_prefetch": {"value": B * world / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync}},
         "gpu_launches": int(launches * K * 2),
         "launches_per_step": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_gemm": roofline_gemm,
         "step_fp32": {"tflops": step_tflops, "frac_of_fp32_peak": step_tflops / fp32_peak, "fp32_peak_tflops": fp32_peak,
                       "hbm_frac": BYTES_PER_STEP / (ms_dev * 1e-3) / 1e9 / hbm_peak, "hbm_peak_gbs": hbm_peak,
                       "peak_source": peak_src},
         "kernels": kernels,
         "env": {"metric": "matrix-game env-steps/sec", "value": env_big["value"], "unit": "env-steps/s",
                 "bytes_per_env_step": ENV_BYTES, "cfg5_4096_envs": env_small, "bandwidth_regime_2^24_envs": env_big},
+        "cfg5_env_plus_learner": cfg5,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

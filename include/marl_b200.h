@@ -267,6 +267,8 @@ int marl_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_
 /* FP32 FMA throughput probe (the compute-roofline denominator bench.py reports against):
  * launches `blocks` x 256 threads x 8 independent FMA chains x `iters`; *flops_out = FLOPs issued. */
 int marl_fma_probe(float* scratch_device, int iters, int blocks, double* flops_out_host, void* stream);
+/* Occupies the stream for ~us microseconds (<= 100000) so that later launches queue up behind it. */
+int marl_spin_us(int us, void* stream);
 int marl_profile_enable(int on);
 int marl_profile_collect(char* buf_host, int buflen);
 

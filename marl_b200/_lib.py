@@ -130,6 +130,7 @@ _SIGNATURES = {
     "marl_qtran_select": ([_P(Dims)] + [c_ptr] * 10 + [c_ptr], C.c_int),
     "marl_qtran_losses_fwd_bwd": ([_P(Dims)] + [c_ptr] * 12 + [C.c_float] * 3 + [c_ptr] * 5 + [c_ptr], C.c_int),
     "marl_optim_partials": ([], C.c_int),
+    "marl_spin_us": ([C.c_int, c_ptr], C.c_int),
     "marl_profile_enable": ([C.c_int], C.c_int),
     "marl_profile_collect": ([C.c_char_p, C.c_int], C.c_int),
     "marl_clip_rmsprop_step": ([c_ptr, c_ptr, c_ptr, C.c_longlong, c_ptr] + [C.c_float] * 4 + [c_ptr, c_ptr, c_ptr], C.c_int),

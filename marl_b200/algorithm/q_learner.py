@@ -94,6 +94,7 @@ class QLearner:
         self._use_graph = bool(getattr(args, "cuda_graph", True))
         self._dist = None
         self._side = None
+        self._copy_stream, self._prefetched, self._slot_free, self._prefetch_seq = None, {}, {}, 0
         self.last = {}
         self.launches_per_step = 0
 
@@ -193,16 +194,15 @@ class QLearner:
         self._ws[key] = ws
         return ws
 
-    def _stage_host_batch(self, batch):
-        """numpy (float64, [B, T_src, ...]) -> pinned/pageable H2D -> marl_ingest_f64 -> fp32 working set."""
+    def _upload(self, batch, slot):
+        """Host dict (numpy float64, [B, T_src, ...]) -> device staging buffers `slot` (async when pinned)."""
         a, dev = self.args, self._dev
         Lq = host_max_episode_len(_to_numpy(batch["terminated"]), a.episode_limit)
         arrs = {k: _to_numpy(batch[k]) for k in BATCH_KEYS}
         B_glob, T_src = arrs["o"].shape[0], arrs["o"].shape[1]
         lo, hi = self._shard(B_glob)
         B = hi - lo
-        ws = self._workspace(B, Lq)
-        key = ("stage", B, T_src)
+        key = ("stage", B, T_src, slot)
         st = self._ws.get(key)
         if st is None:
             st = {}
@@ -212,21 +212,64 @@ class QLearner:
                 st[k] = th.empty(shape, dtype=dt, device=dev)
             self._ws[key] = st
         h2d = 0
+        # VDN / QMIX never read avail_u (only avail_u_next, q_learner.py:105,112): do not ship it
+        skip = ("avail_u",) if a.alg in ("vdn", "qmix") else ()
         for k in BATCH_KEYS:
+            if k in skip:
+                continue
             src = arrs[k][lo:hi]
             want = np.int64 if st[k].dtype == th.int64 else np.float64
             if src.dtype != want or not src.flags.c_contiguous:
                 src = np.ascontiguousarray(src, dtype=want)
             st[k].copy_(th.from_numpy(src), non_blocking=True)
             h2d += src.nbytes
-        self.h2d_bytes_last = h2d
+        return dict(st=st, B=B, L=Lq, T_src=T_src, skip=skip, h2d=h2d)
+
+    def prefetch(self, batch):
+        """Optional: start the host->device copy of the NEXT batch on a copy stream while the current step
+        computes.  A later ``train(batch)`` with the same dict object picks the copy up instead of repeating it.
+        (The reference's loop samples a fresh mini-batch before every ``train`` call, runner.py:96-97, so the
+        next batch is known early.)"""
+        if self._dev.type != "cuda" or (th.is_tensor(batch["o"]) and batch["o"].is_cuda):
+            return
+        if self._copy_stream is None:
+            self._copy_stream = th.cuda.Stream()
+        slot = 1 + (self._prefetch_seq & 1)
+        self._prefetch_seq += 1
+        cur = th.cuda.current_stream()
+        free_ev = self._slot_free.get(slot)
+        with th.cuda.stream(self._copy_stream):
+            if free_ev is not None:
+                self._copy_stream.wait_event(free_ev)       # the ingest that last read this slot has run
+            up = self._upload(batch, slot)
+            up["ready"] = th.cuda.Event()
+            up["ready"].record(self._copy_stream)
+        up["slot"] = slot
+        self._prefetched[id(batch)] = up
+
+    def _stage_host_batch(self, batch):
+        """numpy (float64, [B, T_src, ...]) -> H2D (or a prefetched copy) -> marl_ingest_f64 -> fp32 working set."""
+        up = self._prefetched.pop(id(batch), None)
+        cur = th.cuda.current_stream()
+        if up is not None:
+            cur.wait_event(up["ready"])
+        else:
+            up = self._upload(batch, 0)
+            up["slot"] = 0
+        st, B, Lq, T_src, skip = up["st"], up["B"], up["L"], up["T_src"], up["skip"]
+        self.h2d_bytes_last = up["h2d"]
+        ws = self._workspace(B, Lq)
         e64 = L.EpisodeF64()
         for k in BATCH_KEYS:
-            setattr(e64, k, st[k].data_ptr())
+            setattr(e64, k, st["avail_u_next" if k in skip else k].data_ptr())
         e64.u_is_int64 = int(st["u"].dtype == th.int64)
         d = self._dims(B, Lq)
         e32 = _episode_struct(ws["batch"])
         L.call("marl_ingest_f64", C.byref(e64), T_src, C.byref(d), C.byref(e32), L.stream_ptr())
+        if up["slot"]:
+            ev = th.cuda.Event()
+            ev.record(cur)
+            self._slot_free[up["slot"]] = ev
         return ws["batch"], B, Lq, 1
 
     def _stage_device_batch(self, batch):

@@ -40,3 +40,19 @@ extern "C" int marl_fma_probe(float* scratch_device, int iters, int blocks, doub
     if (flops_out) *flops_out = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
     return MARL_OK;
 }
+
+// Holds the stream busy for ~`us` microseconds (one thread polling %globaltimer).  bench.py queues it in
+// front of a profiled step so that every launch of the step is already enqueued when the GPU gets to it:
+// the event pairs around the kernels then measure device time, not host launch gaps.
+__global__ void spin_kernel(unsigned long long ns) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < ns);
+}
+
+extern "C" int marl_spin_us(int us, void* stream) {
+    if (us < 0 || us > 100000) return MARL_EINVAL;
+    spin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long)us * 1000ull);
+    MARL_LAUNCH_CHECK();
+    return MARL_OK;
+}

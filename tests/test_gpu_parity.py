@@ -343,6 +343,21 @@ def test_device_resident_batch_matches_host_batch():
         assert abs(a - b) <= 1e-6 * abs(a)      # atomics: summation order differs between runs
 
 
+def test_prefetch_overlaps_but_does_not_change_results():
+    args = PU.make_args("qmix", 3, 4, 5, 6, 8)
+    batches = [synthetic_batch(s, 6, 8, 3, 4, 5, 6) for s in range(4)]
+    la, _ = PU.build_pair(args)
+    lb, _ = PU.build_pair(args)
+    ref = [la.train(b, i) for i, b in enumerate(batches)]
+    lb.prefetch(batches[0])
+    out = []
+    for i, b in enumerate(batches):
+        if i + 1 < len(batches):
+            lb.prefetch(batches[i + 1])
+        out.append(lb.train(b, i))
+    assert np.allclose(ref, out, rtol=1e-6)
+
+
 def test_target_sync_cadence():
     args = PU.make_args("vdn", 2, 3, 4, 5, 3, target_update_cycle=2)
     learner, _ = PU.build_pair(args)
