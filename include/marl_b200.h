@@ -271,6 +271,8 @@ int marl_fma_probe(float* scratch_device, int iters, int blocks, double* flops_o
 int marl_spin_us(int us, void* stream);
 int marl_profile_enable(int on);
 int marl_profile_collect(char* buf_host, int buflen);
+/* "kernel,start_us,end_us\n" per recorded launch, relative to the first one; records are kept. */
+int marl_profile_timeline(char* buf_host, int buflen);
 
 #ifdef __cplusplus
 }

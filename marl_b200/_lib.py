@@ -133,6 +133,7 @@ _SIGNATURES = {
     "marl_spin_us": ([C.c_int, c_ptr], C.c_int),
     "marl_profile_enable": ([C.c_int], C.c_int),
     "marl_profile_collect": ([C.c_char_p, C.c_int], C.c_int),
+    "marl_profile_timeline": ([C.c_char_p, C.c_int], C.c_int),
     "marl_clip_rmsprop_step": ([c_ptr, c_ptr, c_ptr, C.c_longlong, c_ptr] + [C.c_float] * 4 + [c_ptr, c_ptr, c_ptr], C.c_int),
     "marl_clip_adam_step": ([c_ptr] * 4 + [C.c_longlong, c_ptr] + [C.c_float] * 5 + [C.c_int, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
 }
@@ -200,6 +201,17 @@ def profile_collect():
         name, cnt, ms = line.rsplit(",", 2)
         out[name] = (int(cnt), float(ms))
     return out
+
+
+def profile_timeline():
+    """[(kernel name, start_us, end_us)] of the launches recorded since the last collect (records are kept)."""
+    buf = C.create_string_buffer(1 << 20)
+    check(load().marl_profile_timeline(buf, len(buf)), "marl_profile_timeline")
+    rows = []
+    for line in buf.value.decode().splitlines():
+        name, s, e = line.rsplit(",", 2)
+        rows.append((name, float(s), float(e)))
+    return rows
 
 
 def call(name, *args):

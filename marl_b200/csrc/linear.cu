@@ -453,7 +453,7 @@ int linear_fwd(const LinearFwd& a, cudaStream_t st) {
     if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return MARL_OK;
     dim3 grid(cdiv(a.M, UM), cdiv(a.N, UN), a.batch);
     const bool va = vec_ok_lin(a.in), vb = vec_ok_mat(a.w, a.ldw, a.w_bs);
-    { ProfScope ps_("linear_fwd_kernel", st); MARL_DISPATCH2(linear_fwd_kernel, va, vb, grid, st, a); }
+    { if (prof_enabled()) prof_note(a.M, a.N, lin_width(a.in)); ProfScope ps_("linear_fwd_kernel", st); MARL_DISPATCH2(linear_fwd_kernel, va, vb, grid, st, a); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
@@ -462,7 +462,7 @@ int linear_dgrad(const LinearDgrad& a, cudaStream_t st) {
     if (a.M <= 0 || a.K <= 0 || a.batch <= 0) return MARL_OK;
     dim3 grid(cdiv(a.M, UM), cdiv(a.K, UN), a.batch);
     const bool va = vec_ok_mat(a.dy, a.lddy, a.dy_bs), vb = vec_ok_mat(a.w, a.ldw, a.w_bs, a.w_col0);
-    { ProfScope ps_("linear_dgrad_kernel", st); MARL_DISPATCH2(linear_dgrad_kernel, va, vb, grid, st, a); }
+    { if (prof_enabled()) prof_note(a.M, a.K, a.N); ProfScope ps_("linear_dgrad_kernel", st); MARL_DISPATCH2(linear_dgrad_kernel, va, vb, grid, st, a); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
@@ -477,7 +477,7 @@ int linear_wgrad(const LinearWgrad& a, cudaStream_t st) {
     splits = cdiv(a.M, chunk);
     dim3 grid(cdiv(a.N, UM), cdiv(K, UN), a.batch * splits);
     const bool va = vec_ok_mat(a.dy, a.lddy, a.dy_bs), vb = vec_ok_lin(a.in);
-    { ProfScope ps_("linear_wgrad_kernel", st); MARL_DISPATCH2(linear_wgrad_kernel, va, vb, grid, st, a, splits, chunk); }
+    { if (prof_enabled()) prof_note(a.N, K, a.M); ProfScope ps_("linear_wgrad_kernel", st); MARL_DISPATCH2(linear_wgrad_kernel, va, vb, grid, st, a, splits, chunk); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }

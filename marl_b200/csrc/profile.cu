@@ -12,7 +12,8 @@
 namespace marl {
 namespace {
 bool g_on = false;
-struct Rec { const char* name; cudaEvent_t a, b; };
+struct Rec { const char* name; cudaEvent_t a, b; int m, n, k; };
+int g_m = 0, g_n = 0, g_k = 0;
 std::vector<Rec> g_recs;
 std::vector<cudaEvent_t> g_pool;
 cudaEvent_t get_event() {
@@ -22,15 +23,40 @@ cudaEvent_t get_event() {
 }  // namespace
 bool prof_enabled() { return g_on; }
 void prof_begin(const char* name, cudaStream_t st) {
-    Rec r{name, get_event(), get_event()};
+    Rec r{name, get_event(), get_event(), g_m, g_n, g_k};
+    g_m = g_n = g_k = 0;
     cudaEventRecord(r.a, st);
     g_recs.push_back(r);
 }
+void prof_note(int m, int n, int k) { g_m = m; g_n = n; g_k = k; }
 void prof_end(cudaStream_t st) { cudaEventRecord(g_recs.back().b, st); }
 }  // namespace marl
 
 extern "C" int marl_profile_enable(int on) {
     marl::g_on = on != 0;
+    return 0;
+}
+
+// Timeline of the launches recorded since the last collect: "kernel,start_us,end_us\n" relative to the first
+// recorded launch (event timestamps of different streams share the device clock).  Does not clear the records.
+extern "C" int marl_profile_timeline(char* buf, int buflen) {
+    using namespace marl;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return (int)e;
+    std::string out;
+    char line[256];
+    for (auto& r : g_recs) {
+        float s = 0.f, t = 0.f;
+        cudaEventElapsedTime(&s, g_recs.front().a, r.a);
+        cudaEventElapsedTime(&t, g_recs.front().a, r.b);
+        if (r.m) snprintf(line, sizeof line, "%s[%dx%dx%d],%.3f,%.3f\n", r.name, r.m, r.n, r.k, s * 1e3, t * 1e3);
+        else snprintf(line, sizeof line, "%s,%.3f,%.3f\n", r.name, s * 1e3, t * 1e3);
+        out += line;
+    }
+    if (buf && buflen > 0) {
+        strncpy(buf, out.c_str(), buflen - 1);
+        buf[buflen - 1] = 0;
+    }
     return 0;
 }
 

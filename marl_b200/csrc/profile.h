@@ -6,6 +6,7 @@ namespace marl {
 bool prof_enabled();
 void prof_begin(const char* name, cudaStream_t st);
 void prof_end(cudaStream_t st);
+void prof_note(int m, int n, int k);   // problem size shown beside the next recorded launch in the timeline
 
 struct ProfScope {
     cudaStream_t st; bool on;

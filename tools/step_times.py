@@ -10,8 +10,11 @@ from marl_b200.algorithm.qtran_learner import QTRANLearner
 
 names = sys.argv[1:] or ["matrix_game", "2s3z:vdn", "2s3z", "3s5z", "27m_vs_30m", "matrix_game_4096"]
 for spec in names:
+    spec, _, bsz = spec.partition("@")
     name, _, alg = spec.partition(":")
     c = dict(CONFIGS[name]); alg = alg or c["alg"]
+    if bsz:
+        c["B"] = int(bsz)
     args = default_args(alg=alg, n_agents=c["N"], n_actions=c["A"], obs_shape=c["O"], state_shape=c["S"], episode_limit=c["T"], map=name)
     torch.manual_seed(0)
     mac = SharedMAC(args)

@@ -1,5 +1,6 @@
-"""Per-kernel device time of one train step (eager pass, library profiler) + graph-replay step time."""
-import os, sys, time
+"""Multi-stream timeline of ONE eager train step (library profiler events; the host is run ahead with a spin
+kernel so the events bracket device time only).  usage: timeline.py [alg] [B]"""
+import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import torch
 from bench import make_args, SHAPE
@@ -17,23 +18,16 @@ hb = synthetic_batch(0, **SHAPE)
 db = {k: torch.as_tensor(v, device="cuda") for k, v in hb.items()}
 db = {k: (v.to(torch.int64) if k == "u" else v.to(torch.float32)).contiguous() for k, v in db.items()}
 db["max_episode_len"] = SHAPE["T"]
-for i in range(5):
-    loss = learner.train(db, i)
-torch.cuda.synchronize()
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record()
-K = 50
-for i in range(K):
-    learner.train(db, 5 + i)
-b.record(); torch.cuda.synchronize()
-print(f"graph replay: {a.elapsed_time(b)/K*1e3:.1f} us/step, loss {loss:.6f}")
 learner._use_graph = False
+for i in range(5):
+    learner.train(db, i)
+torch.cuda.synchronize()
 L.profile(True)
-P = 10
-for i in range(P):
-    learner.train(db, 100 + i)
-prof = L.profile_collect()
-tot = sum(ms for _, ms in prof.values())
-for k, (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-    print(f"{k:28s} {c/P:5.1f} launches  {ms/P*1e3:8.1f} us/step  {100*ms/tot:5.1f}%")
-print(f"sum {tot/P*1e3:.1f} us/step")
+L.call("marl_spin_us", 3000, L.stream_ptr())
+learner.train(db, 10)
+rows = L.profile_timeline()
+L.profile_collect()
+L.profile(False)
+t0 = rows[0][1]
+for name, s, e in sorted(rows, key=lambda r: r[1]):
+    print(f"{s - t0:9.1f} {e - t0:9.1f} {e - s:8.1f}  {name}")
