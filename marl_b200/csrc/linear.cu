@@ -130,7 +130,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // x = hi + lo with both halves ROUNDED to TF32 (cvt.rna): unbiased, unlike the truncation the tensor core
 // applies to raw fp32 words, whose error grows linearly with the reduction length.
-__device__ __forceinline__ float tf32_rna(float x) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
+// (integer add + mask on the bit pattern = round to nearest, ties away, exactly what cvt.rna.tf32.f32 does for finite
+// inputs; cvt itself runs on the quarter-rate conversion pipe and was measured to bound the split pass)
+__device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) { hi = tf32_rna(x); lo = tf32_rna(x - hi); }
 
 // Per-thread share of one k-tile and where it lands in shared memory.
