@@ -28,7 +28,11 @@ SHAPE = dict(B=32, T=120, N=5, A=11, O=80, S=120)        # BASELINE.json configs
 FLOP_PER_STEP = 6.98e9                                   # SURVEY.md section 8(d), cfg 2 QMIX, B=32
 BYTES_PER_STEP = 18.71e6                                 # each batch element read once as fp32 (u int64)
 GRU_FWD_FLOP = 3 * 32 * 120 * 5 * 2 * (3 * 64 * 64)      # 3 unrolls x rows x (W_hh h): the sequential kernel
+GRU_FWD_BYTES = 32 * 120 * 5 * 4 * (3 * 192 + 3 * 64 + 256)   # gi in (3 unrolls), hidden out (3), saved gates out (eval unroll)
 ENV_BYTES = 140                                          # 16 B actions in + 124 B episode record out
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+NCU_TRAFFIC = {"gru_unroll_fwd_kernel": 44405504 + 4042240, "gru_unroll_bwd_kernel": 29583616 + 132096,
+               "linear_fwd_kernel": 7062784, "matrix_game_step_kernel": 268467712 + 2042848000}
 PAYOFF1 = [[8, -12, -12], [-12, 0, 0], [-12, 0, 0]]
 
 
@@ -166,7 +170,7 @@ def bench_env(torch, dist, world, n_envs, iters, hbm_peak):
     gbs = rate / world * ENV_BYTES / 1e9
     return {"n_envs_per_gpu": n_envs, "value": rate, "unit": "env-steps/s", "us_per_launch": ms * 1e3,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                         "traffic": None, "note": "per GPU"}}
+                         "traffic": NCU_TRAFFIC["matrix_game_step_kernel"] if n_envs == (1 << 24) else None, "note": "per GPU"}}
 
 
 def run_ours(opt):
@@ -248,6 +252,11 @@ def run_ours(opt):
     # same, with the next batch's H2D copy started (learner.prefetch) before the current train() call: the copy
     # of every step is still inside the timed region, it just overlaps the previous step's compute
     hv = [host_view(0), host_view(1)]
+    learner.prefetch(hv[0])                           # untimed: first use allocates the two prefetch staging slots
+    for i in range(4):
+        learner.prefetch(hv[(i + 1) & 1])
+        learner.train(hv[i & 1], step); step += 1
+    learner.train(hv[0], step); step += 1
     barrier()
     ev0.record()
     learner.prefetch(hv[0])
@@ -321,29 +330,68 @@ def run_ours(opt):
         cfg5 = {"workload": "4096 matrix-game envs (one kernel launch) -> QMIX train step on the emitted device batch",
                 "ms_per_iteration": ms5, "env_steps_per_s": 4096 / (ms5 * 1e-3), "episode_samples_per_s": 4096 / (ms5 * 1e-3)}
 
+    peaks_json = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    bf16_peak = peaks_json.get("bf16_tflops_sustained", 1400.0)      # kernels timed inside a long step: the sustained figure
+    # ---- larger batches of the same shape (device-resident): where the step leaves the latency-bound regime ----
+    sweep = None
+    if world == 1 and not opt.no_sweep:
+        sweep = []
+        for Bs in (256, 1024):
+            hb = synthetic_batch(7, **dict(SHAPE, B=Bs))
+            db = {k: torch.as_tensor(v, device="cuda") for k, v in hb.items()}
+            db = {k: (v.to(torch.int64) if k == "u" else v.to(torch.float32)).contiguous() for k, v in db.items()}
+            db["max_episode_len"] = SHAPE["T"]
+            for i in range(4):
+                learner.train(db, step); step += 1
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for i in range(10):
+                learner.train(db, step); step += 1
+            b_.record(); torch.cuda.synchronize()
+            msb = a_.elapsed_time(b_) / 10
+            tf = FLOP_PER_STEP * Bs / SHAPE["B"] / (msb * 1e-3) / 1e12
+            sweep.append({"batch": Bs, "ms_per_step": msb, "episode_samples_per_s": Bs / (msb * 1e-3), "fp32_tflops": tf,
+                          "frac_of_fp32_peak": tf / fp32_peak,
+                          "hbm_frac": BYTES_PER_STEP * Bs / SHAPE["B"] / (msb * 1e-3) / 1e9 / hbm_peak})
+            del db
+        learner._ws = {k: v for k, v in learner._ws.items() if k[0] == "stage" or k == (B, SHAPE["T"])}
+        torch.cuda.empty_cache()
+
     roofline = None
     if kernels:
-        # dominant kernel = the longest single launch of the step
+        # dominant kernel = the longest single launch of the step (it sits on the critical path): the recurrent part of
+        # the three agent unrolls.  Neither HBM nor the tensor pipe binds it: it is a dependent chain of 2L small
+        # (rows x 64 x 192) fp32 mat-vecs, so it is reported against the measured FP32-FMA peak, with the HBM and
+        # tensor-pipe fractions beside it for context.
         dom = max(kernels, key=lambda k: kernels[k]["us_per_step"] / max(kernels[k]["launches_per_step"], 1))
         dom_us = kernels[dom]["us_per_step"] / max(kernels[dom]["launches_per_step"], 1)
-        flop = GRU_FWD_FLOP if dom == "gru_unroll_fwd_kernel" else FLOP_PER_STEP * kernels[dom]["share"]
+        is_gru = dom == "gru_unroll_fwd_kernel"
+        flop = GRU_FWD_FLOP if is_gru else FLOP_PER_STEP * kernels[dom]["share"]
         ach = flop / (dom_us * 1e-6) / 1e12
-        roofline = {"kernel": dom, "bound": "fp32_fma; latency-bound at B=32 (160 rows x 240 dependent GRU steps, ~0.44 us/step)",
-                    "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": None,
-                    "us_per_launch": dom_us, "algorithmic_flop_per_launch": flop,
-                    "peak_source": "marl_fma_probe on this GPU (MEASURED_PEAKS.json has no fp32 figure)"}
+        gru_bytes = GRU_FWD_BYTES if is_gru else None
+        roofline = {"kernel": dom, "bound": "fp32",
+                    "bound_note": "dependent chain of 2L = 240 GRU steps on B*N = 160 rows (~1.1 rows per SM): latency-bound at "
+                                  "B=32; FP32 FMA is the nearest roof (HBM and tensor-pipe fractions given for context; see "
+                                  "batch_sweep for the fraction at larger batches)",
+                    "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
+                    "traffic": NCU_TRAFFIC.get(dom), "traffic_source": "profiles/r1_ncu_full_gru_fwd.txt (dram_read + dram_write, one --set full capture)",
+                    "us_per_launch": dom_us, "algorithmic_flop_per_launch": flop, "algorithmic_bytes_per_launch": gru_bytes,
+                    "hbm_frac": (gru_bytes / (dom_us * 1e-6) / 1e9 / hbm_peak) if gru_bytes else None,
+                    "peak_source": "marl_fma_probe on this GPU (MEASURED_PEAKS.json has no fp32 figure); hbm: " + peak_src}
     gemm_us = sum(v["us_per_step"] for k, v in kernels.items() if k.startswith("linear_"))
     gemm_flop = FLOP_PER_STEP - GRU_FWD_FLOP - GRU_FWD_FLOP / 3        # everything but the two recurrent kernels
-    bf16_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
     roofline_gemm = None
     if gemm_us:
         ach = gemm_flop / (gemm_us * 1e-6) / 1e12
         roofline_gemm = {"kernel": "linear_{fwd,dgrad,wgrad}_kernel (tcgen05 kind::tf32, 3xTF32)", "bound": "tensor",
-                         "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak, "traffic": None,
-                         "us_per_step": gemm_us,
-                         "note": "algorithmic fp32 FLOPs of all dense layers / summed launch time; the TF32 pipe peaks at "
-                                 "half the bf16 figure and every product is issued 3 times (3xTF32), so 1/6 of `peak` is the "
-                                 "ceiling of this scheme; at cfg-2 sizes (19200 x 64..192 outputs) the launches are latency-bound"}
+                         "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
+                         "traffic": NCU_TRAFFIC.get("linear_fwd_kernel"), "us_per_step": gemm_us,
+                         "note": "algorithmic fp32 FLOPs of all dense layers / summed launch time (launches on parallel streams "
+                                 "overlap, so the sum overstates the wall time); peak = measured sustained bf16; the TF32 pipe peaks "
+                                 "at half of it and every product is issued 3 times (3xTF32), so 1/6 of `peak` is the ceiling of "
+                                 "this scheme; at cfg-2 sizes each launch is a single wave of 150 CTAs x 3-6 k-tiles and is "
+                                 "bound by fixed per-launch latency and shared-memory bandwidth (profiles/README.md)"}
     step_tflops = FLOP_PER_STEP / (ms_dev * 1e-3) / 1e12
 
     cpu = None
@@ -375,6 +423,7 @@ def run_ours(opt):
                       "hbm_frac": BYTES_PER_STEP / (ms_dev * 1e-3) / 1e9 / hbm_peak, "hbm_peak_gbs": hbm_peak,
                       "peak_source": peak_src},
         "kernels": kernels,
+        "batch_sweep": sweep,
         "env": {"metric": "matrix-game env-steps/sec", "value": env_big["value"], "unit": "env-steps/s",
                 "bytes_per_env_step": ENV_BYTES, "cfg5_4096_envs": env_small, "bandwidth_regime_2^24_envs": env_big},
         "cfg5_env_plus_learner": cfg5,
@@ -391,6 +440,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-sweep", dest="no_sweep", action="store_true", help="skip the B=256/1024 legs")
     opt = ap.parse_args()
     if opt.impl == "reference":
         run_reference(opt)

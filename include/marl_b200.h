@@ -73,6 +73,12 @@ int marl_ingest_f64(const marl_episode_f64* src, int T_src, const marl_dims* d,
 int marl_ingest_f32(const marl_episode_f32* src, int T_src, const marl_dims* d,
                     const marl_episode_f32* dst, void* stream);
 
+/* ---- device replay buffer: common/replaybuffer.py:54-60 (sample) fused with the ingest ----
+ * Output episode b of the working set [B, L, ...] is episode episode_idx[b] (device int64, sampled with
+ * replacement by the host RNG exactly like the reference) of the ring [size, T_ring, ...], truncated to L. */
+int marl_replay_gather_f32(const marl_episode_f32* ring, int T_ring, const long long* episode_idx,
+                           const marl_dims* d, const marl_episode_f32* dst, void* stream);
+
 /* ---- agent: network/q_network.py:6-21 unrolled by controller/share_params.py:125-168 ---- */
 typedef struct marl_agent_params {
     const float* fc1_w;  /* [H, O+A+N] */  const float* fc1_b;  /* [H] */
@@ -137,6 +143,13 @@ int marl_q_select(const marl_dims* d, const float* q_evals, const long long* u, 
                   float* q_chosen, long long* a_star /*nullable*/, float* q_targets_chosen,
                   float* max_q_evals /*nullable*/, float* q_targets_max /*nullable*/,
                   float* a_star_onehot /*nullable, [B,L,N,A] one-hot of a* (q_learner.py:140-143)*/, void* stream);
+
+/* ---- acting: controller/share_params.py:62-72 for all (env, agent) rows at once ----
+ * action[i] = explore[i] ? random_action[i] : argmax_a(q[i, a] masked to -inf where avail[i, a] == 0) (first maximum);
+ * avail, explore / random_action and onehot are nullable.  explore / random_action are drawn on the host in the
+ * reference's RNG order (one uniform per agent, one choice only when exploring). */
+int marl_epsgreedy_select(int rows, int A, const float* q, const float* avail, const unsigned char* explore,
+                          const long long* random_action, long long* action, float* onehot, void* stream);
 
 /* ---- TD target + masked MSE: algorithm/q_learner.py:165-168 ----
  * y = r + gamma*q_tot_target*(1-terminated); d = (1-padded)*(y - q_tot);

@@ -108,6 +108,7 @@ _SIGNATURES = {
     "marl_matrix_game_validate_actions": ([c_ptr, C.c_int, C.c_longlong, c_ptr, c_ptr], C.c_int),
     "marl_ingest_f64": ([_P(EpisodeF64), C.c_int, _P(Dims), _P(EpisodeF32), c_ptr], C.c_int),
     "marl_ingest_f32": ([_P(EpisodeF32), C.c_int, _P(Dims), _P(EpisodeF32), c_ptr], C.c_int),
+    "marl_replay_gather_f32": ([_P(EpisodeF32), C.c_int, c_ptr, _P(Dims), _P(EpisodeF32), c_ptr], C.c_int),
     "marl_fma_probe": ([c_ptr, C.c_int, C.c_int, _P(C.c_double), c_ptr], C.c_int),
     "marl_agent_unroll_fwd": ([_P(Dims), _P(UnrollStream), C.c_int, c_ptr], C.c_int),
     "marl_agent_unroll_bwd": ([_P(Dims), _P(UnrollBwd), c_ptr], C.c_int),
@@ -129,6 +130,7 @@ _SIGNATURES = {
                            c_ptr, C.c_int, _P(QtranNetGrads), c_ptr], C.c_int),
     "marl_qtran_select": ([_P(Dims)] + [c_ptr] * 10 + [c_ptr], C.c_int),
     "marl_qtran_losses_fwd_bwd": ([_P(Dims)] + [c_ptr] * 12 + [C.c_float] * 3 + [c_ptr] * 5 + [c_ptr], C.c_int),
+    "marl_epsgreedy_select": ([C.c_int, C.c_int] + [c_ptr] * 6 + [c_ptr], C.c_int),
     "marl_optim_partials": ([], C.c_int),
     "marl_spin_us": ([C.c_int, c_ptr], C.c_int),
     "marl_profile_enable": ([C.c_int], C.c_int),

@@ -29,6 +29,7 @@ import torch as th
 from .. import _lib as L
 from ..flat import FlatBuffer, prefixed
 from ..parallel import shard_bounds, allreduce_flat
+from ..common.replaybuffer import DeviceEpisodeBatch
 from ..network.mixer import VDNMixer, QMixMixer, qmix_struct
 from ..network.q_network import agent_param_struct, AGENT_FLAT_ORDER
 
@@ -303,6 +304,26 @@ class QLearner:
         self.h2d_bytes_last = 0
         return ws["batch"], B, int(Lq), 1
 
+    def _stage_replay_batch(self, batch):
+        """``ReplayBuffer.sample()`` of the device-resident buffer (common/replaybuffer.py) -> working set: the
+        sampled ring rows are gathered and cut to the batch's max episode length in ONE launch."""
+        ring, Lq = batch.ring, batch.max_episode_len
+        B_glob = int(batch.idx.shape[0])
+        lo, hi = self._shard(B_glob)
+        B = hi - lo
+        ws = self._workspace(B, Lq)
+        src = L.EpisodeF32()
+        for k in BATCH_KEYS:
+            setattr(src, k, ring[k].data_ptr())
+        T_ring = ring["o"].shape[1]
+        d = self._dims(B, Lq)
+        dst = _episode_struct(ws["batch"])
+        idx = batch.idx[lo:hi]
+        L.call("marl_replay_gather_f32", C.byref(src), T_ring, idx.data_ptr(), C.byref(d), C.byref(dst), L.stream_ptr())
+        self._keep_alive = idx
+        self.h2d_bytes_last = 0
+        return ws["batch"], B, Lq, 1
+
     def _shard(self, B_glob):
         if self._dist is None:
             return 0, B_glob
@@ -490,8 +511,10 @@ class QLearner:
         drives the target sync exactly like the reference's ``train_step``."""
         if self._dev.type != "cuda":
             raise L.MarlLibraryError("QLearner.train needs a CUDA device: marl_b200 has no CPU path")
-        on_device = th.is_tensor(batch["o"]) and batch["o"].is_cuda
-        if on_device:
+        if isinstance(batch, DeviceEpisodeBatch):
+            bt, B, Lq, _ = self._stage_replay_batch(batch)
+            ws = self._workspace(B, Lq)
+        elif th.is_tensor(batch["o"]) and batch["o"].is_cuda:
             bt, B, Lq, _ = self._stage_device_batch(batch)
             ws = self._workspace(B, Lq)
         else:

@@ -1,0 +1,147 @@
+"""Device-resident episode replay buffer, drop-in for ``common/replaybuffer.py:5-80``.
+
+Same surface and semantics as the reference's ``ReplayBuffer`` -- 11 episode-major keys of shape
+``[buffer_size, episode_limit, ...]`` (``:19-30``), ``store_episode`` writing at the ring indices
+``_get_storage_idx`` hands out (``:35-51, :63-80``: contiguous, wrap-around, restart at 0 once full),
+``sample`` drawing ``batch_size`` episodes WITH replacement by ``np.random.randint(0, current_size,
+batch_size)`` (``:54-60``; the same host RNG call, so a seeded run samples the same episodes) -- but the
+ring lives in HBM as fp32 (``u`` int64), i.e. exactly what ``QLearner.train`` consumes:
+
+* ``store_episode`` pays the float64 -> fp32 cast and the host -> device copy ONCE per collected
+  episode (the reference pays both for every sampled batch inside ``train``, q_learner.py:74-91);
+* ``sample`` returns a :class:`DeviceEpisodeBatch`: the ring plus the drawn indices.  The learner gathers
+  (and truncates to the batch's ``max_episode_len``) straight into its working set with ONE
+  ``marl_replay_gather_f32`` launch; nothing is materialised unless somebody indexes the dict, in which
+  case the key is gathered on demand and behaves like the reference's array.
+
+The first-terminated index of every stored episode is kept on the host, so the episode-length cut of
+``get_max_episode_len`` (q_learner.py:49-66) needs no device synchronisation.
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+import torch as th
+
+KEYS = ("o", "u", "s", "r", "o_next", "s_next", "avail_u", "avail_u_next", "u_onehot", "padded", "terminated")
+
+
+class DeviceEpisodeBatch(dict):
+    """What ``ReplayBuffer.sample`` returns: lazily materialised view of the sampled episodes.
+
+    Behaves like the reference's dict of ``[batch, episode_limit, ...]`` arrays (keys are gathered on
+    first access as CUDA tensors); ``QLearner.train`` recognises it and skips the materialisation."""
+
+    def __init__(self, ring, idx_host, idx_dev, max_episode_len):
+        super().__init__()
+        self.ring, self.idx_host, self.idx = ring, idx_host, idx_dev
+        self.max_episode_len = int(max_episode_len)
+
+    def __missing__(self, key):
+        if key == "max_episode_len":
+            return self.max_episode_len
+        if key not in self.ring:
+            raise KeyError(key)
+        val = self.ring[key].index_select(0, self.idx)
+        self[key] = val
+        return val
+
+    def keys(self):
+        return list(KEYS)
+
+    def __contains__(self, key):
+        return key in KEYS or dict.__contains__(self, key)
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+    def __len__(self):
+        return len(KEYS)
+
+
+class ReplayBuffer:
+    def __init__(self, args, device=None):
+        self.args = args
+        self.n_actions = self.args.n_actions
+        self.n_agents = self.args.n_agents
+        self.state_shape = self.args.state_shape
+        self.obs_shape = self.args.obs_shape
+        self.size = self.args.buffer_size
+        self.episode_limit = self.args.episode_limit
+        # memory management
+        self.current_idx = 0
+        self.current_size = 0
+        if device is None:
+            if not th.cuda.is_available():
+                raise RuntimeError("marl_b200.ReplayBuffer keeps the episodes in HBM: no CUDA device")
+            device = th.device("cuda")
+        self.device = th.device(device)
+        S, T, N, A, O, St = self.size, self.episode_limit, self.n_agents, self.n_actions, self.obs_shape, self.state_shape
+        f = lambda *shape: th.zeros(*shape, dtype=th.float32, device=self.device)
+        self.buffers = {'o': f(S, T, N, O),
+                        'u': th.zeros(S, T, N, 1, dtype=th.int64, device=self.device),
+                        's': f(S, T, St),
+                        'r': f(S, T, 1),
+                        'o_next': f(S, T, N, O),
+                        's_next': f(S, T, St),
+                        'avail_u': f(S, T, N, A),
+                        'avail_u_next': f(S, T, N, A),
+                        'u_onehot': f(S, T, N, A),
+                        'padded': f(S, T, 1),
+                        'terminated': f(S, T, 1)}
+        # index of the first terminated == 1 per stored episode (-1: none), for the episode-length cut
+        self.first_terminated = np.full(self.size, -1, dtype=np.int64)
+        self.lock = threading.Lock()
+
+    # ---- store ------------------------------------------------------------------------------------
+    def store_episode(self, episode_batch):
+        batch_size = episode_batch['o'].shape[0]
+        with self.lock:
+            idxs = self._get_storage_idx(inc=batch_size)
+            idx_np = np.atleast_1d(np.asarray(idxs, dtype=np.int64))
+            idx_dev = th.from_numpy(idx_np).to(self.device)
+            for key in KEYS:
+                src = episode_batch[key]
+                want = th.int64 if key == 'u' else th.float32
+                if th.is_tensor(src):
+                    t = src.to(device=self.device)
+                    t = t.to(want) if t.dtype != want else t        # float -> int64 truncates toward zero like th.tensor(..., long)
+                else:
+                    a = np.ascontiguousarray(src)
+                    t = th.from_numpy(a).to(self.device, non_blocking=True).to(want)
+                self.buffers[key].index_copy_(0, idx_dev, t.reshape((batch_size,) + tuple(self.buffers[key].shape[1:])))
+            term = episode_batch['terminated']
+            term = term.detach().cpu().numpy() if th.is_tensor(term) else np.asarray(term)
+            term = term.reshape(batch_size, -1)[:, :self.episode_limit] == 1
+            first = np.where(term.any(axis=1), term.argmax(axis=1), -1)
+            self.first_terminated[idx_np] = first
+
+    # ---- sample -----------------------------------------------------------------------------------
+    def sample(self, batch_size):
+        idx = np.random.randint(0, self.current_size, batch_size)
+        return self.sample_at(idx)
+
+    def sample_at(self, idx):
+        """The batch made of the given ring rows (what ``sample`` does after drawing the indices)."""
+        idx = np.asarray(idx, dtype=np.int64)
+        ft = self.first_terminated[idx]
+        has = ft >= 0
+        max_len = int(ft[has].max()) + 1 if has.any() else int(self.episode_limit)   # q_learner.py:49-61
+        return DeviceEpisodeBatch(self.buffers, idx, th.from_numpy(idx).to(self.device, non_blocking=True), max_len)
+
+    # ---- ring indices (common/replaybuffer.py:63-80) -----------------------------------------------
+    def _get_storage_idx(self, inc=None):
+        """Ring positions of the next `inc` episodes.  Semantics of the reference, including its quirk that a
+        write ending exactly at the end of the ring leaves the cursor AT `size` (the next write restarts at 0):
+        contiguous while it fits, otherwise the tail of the ring followed by its head."""
+        n = inc or 1
+        start = self.current_idx if self.current_idx < self.size else 0
+        end = start + n
+        positions = (start + np.arange(n)) % self.size if end > self.size else np.arange(start, end)
+        self.current_idx = end if end <= self.size else end - self.size
+        self.current_size = min(self.size, self.current_size + n)
+        return positions[0] if n == 1 else positions

@@ -47,6 +47,29 @@ __global__ void __launch_bounds__(256) q_select_kernel(
     }
 }
 
+// Epsilon-greedy action of every (env, agent) row: controller/share_params.py:62-72.  Unavailable actions are masked
+// to -inf and the first maximum wins (th.argmax); rows whose host-drawn `explore` flag is set take the host-drawn
+// random available action instead (the reference draws np.random.uniform() / np.random.choice per agent; drawing them
+// on the host in the reference's order keeps the action stream bit-exact under a seed).
+__global__ void __launch_bounds__(256) epsgreedy_kernel(int rows, int A, const float* __restrict__ q,
+                                                        const float* __restrict__ avail, const unsigned char* __restrict__ explore,
+                                                        const long long* __restrict__ random_action,
+                                                        long long* __restrict__ action, float* __restrict__ onehot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const long long o = (long long)i * A;
+    int best = 0;
+    float bv = -INFINITY;
+    for (int a = 0; a < A; ++a) {
+        const float v = (avail && avail[o + a] == 0.0f) ? -INFINITY : q[o + a];
+        if (v > bv) { bv = v; best = a; }                     // strict: first maximum; all masked -> 0 like th.argmax
+    }
+    if (explore && explore[i]) best = (int)random_action[i];
+    action[i] = best;
+    if (onehot)
+        for (int a = 0; a < A; ++a) onehot[o + a] = (a == best) ? 1.0f : 0.0f;
+}
+
 // Block-wide sum of two values; thread 0 of the block adds them to out[0], out[1].
 __device__ __forceinline__ void block_accumulate2(float a, float b, float* out) {
     __shared__ float sa[32], sb[32];
@@ -104,14 +127,24 @@ __global__ void __launch_bounds__(256) vdn_td_kernel(int M, int N, int A, const 
 }
 
 struct IngestKey { const void* src; void* dst; int inner; int kind; };   // kind 0: f64->f32, 1: f64->i64, 2: i64->i64, 3: f32->f32
-struct IngestArgs { IngestKey k[11]; int B, L, T_src; };
+struct IngestArgs { IngestKey k[11]; int B, L, T_src; const long long* idx; };   // idx (nullable): source episode of output episode b
 
 __global__ void __launch_bounds__(256) ingest_kernel(IngestArgs a) {
     const IngestKey key = a.k[blockIdx.y];
     const long long per_b = (long long)a.L * key.inner, total = (long long)a.B * per_b;
     const long long src_b = (long long)a.T_src * key.inner;
     const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
-    if (a.T_src == a.L && (total & 3) == 0 && (key.kind == 0 || key.kind == 3)) {
+    if (a.idx && key.kind == 3 && (per_b & 3) == 0 && (src_b & 3) == 0) {
+        // gather of sampled episodes (device replay buffer): 128-bit copies, a quad never straddles two episodes
+        const long long qb = per_b >> 2, nq = (long long)a.B * qb;
+        const float4* s = (const float4*)key.src; float4* d = (float4*)key.dst;
+        for (long long i = tid0; i < nq; i += stride) {
+            const long long b = i / qb, rem = i - b * qb;
+            d[i] = __ldg(s + a.idx[b] * (src_b >> 2) + rem);
+        }
+        return;
+    }
+    if (!a.idx && a.T_src == a.L && (total & 3) == 0 && (key.kind == 0 || key.kind == 3)) {
         // no truncation: straight vectorised cast / copy
         const long long nq = total >> 2;
         if (key.kind == 0) {
@@ -127,7 +160,7 @@ __global__ void __launch_bounds__(256) ingest_kernel(IngestArgs a) {
         return;
     }
     for (long long i = tid0; i < total; i += stride) {
-        const long long b = i / per_b, rem = i - b * per_b, si = b * src_b + rem;
+        const long long b = i / per_b, rem = i - b * per_b, si = (a.idx ? a.idx[b] : b) * src_b + rem;
         if (key.kind == 0) ((float*)key.dst)[i] = (float)((const double*)key.src)[si];
         else if (key.kind == 1) ((long long*)key.dst)[i] = (long long)((const double*)key.src)[si];   // trunc toward zero
         else if (key.kind == 2) ((long long*)key.dst)[i] = ((const long long*)key.src)[si];
@@ -150,6 +183,16 @@ extern "C" int marl_q_select(const marl_dims* d, const float* q_evals, const lon
     if (rows <= 0) return MARL_OK;
     { ProfScope ps_("q_select_kernel", (cudaStream_t)stream); q_select_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, d->A, q_evals, u, q_evals_next, q_targets,
         avail_u_next, avail_u, q_chosen, a_star, q_targets_chosen, max_q_evals, q_targets_max, a_star_onehot); }
+    MARL_LAUNCH_CHECK();
+    return MARL_OK;
+}
+
+extern "C" int marl_epsgreedy_select(int rows, int A, const float* q, const float* avail, const unsigned char* explore,
+                                     const long long* random_action, long long* action, float* onehot, void* stream) {
+    if (rows < 0 || A <= 0 || !q || !action || (explore && !random_action)) return MARL_EINVAL;
+    if (rows == 0) return MARL_OK;
+    { ProfScope ps_("epsgreedy_kernel", (cudaStream_t)stream);
+      epsgreedy_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, A, q, avail, explore, random_action, action, onehot); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
@@ -206,11 +249,11 @@ extern "C" int marl_ingest_f64(const marl_episode_f64* s, int T_src, const marl_
     return MARL_OK;
 }
 
-extern "C" int marl_ingest_f32(const marl_episode_f32* s, int T_src, const marl_dims* d, const marl_episode_f32* o,
-                               void* stream) {
+static int ingest_f32_impl(const marl_episode_f32* s, int T_src, const long long* idx, const marl_dims* d,
+                           const marl_episode_f32* o, void* stream) {
     if (!s || !d || !o || T_src < d->L || d->B <= 0 || d->L <= 0) return MARL_EINVAL;
     IngestArgs a{};
-    a.B = d->B; a.L = d->L; a.T_src = T_src;
+    a.B = d->B; a.L = d->L; a.T_src = T_src; a.idx = idx;
     const int NO = d->N * d->O, NA = d->N * d->A;
     a.k[0] = {s->o, o->o, NO, 3};
     a.k[1] = {s->u, o->u, d->N, 2};
@@ -232,4 +275,15 @@ extern "C" int marl_ingest_f32(const marl_episode_f32* s, int T_src, const marl_
     { ProfScope ps_("ingest_kernel", (cudaStream_t)stream); ingest_kernel<<<dim3(bx, 11), 256, 0, (cudaStream_t)stream>>>(a); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
+}
+
+extern "C" int marl_ingest_f32(const marl_episode_f32* s, int T_src, const marl_dims* d, const marl_episode_f32* o,
+                               void* stream) {
+    return ingest_f32_impl(s, T_src, nullptr, d, o, stream);
+}
+
+extern "C" int marl_replay_gather_f32(const marl_episode_f32* ring, int T_ring, const long long* episode_idx,
+                                      const marl_dims* d, const marl_episode_f32* o, void* stream) {
+    if (!episode_idx) return MARL_EINVAL;
+    return ingest_f32_impl(ring, T_ring, episode_idx, d, o, stream);
 }
