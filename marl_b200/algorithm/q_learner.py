@@ -487,6 +487,9 @@ class QLearner:
                     self._device_step(bt, ws, B, Lq)
                 entry = (g,)
             else:
+                # two graphs around the NCCL call: capturing torch.distributed's all-reduce inside the step graph was
+                # tried on 2 x B200 and hung (test and bench both ran into their time limits), so the
+                # collective stays an ordinary stream-ordered launch between them
                 g1, g2 = th.cuda.CUDAGraph(), th.cuda.CUDAGraph()
                 with th.cuda.graph(g1):
                     self._launch_forward_backward(bt, ws, B, Lq)
