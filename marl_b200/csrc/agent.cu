@@ -51,6 +51,7 @@ struct GruFwdArgs {
     int chain_len[kMaxStreams];
     const float* h0[kMaxStreams];
     int n_chains, B, L, N;
+    unsigned short rows_of[kMaxStreams][kNumSMs];   // rows of chain c advanced by CTA i (balanced on the host, see plan_rows)
 };
 
 // One CTA advances R rows (b,n) of one chain through all its segments.  Thread (j, ks): hidden unit j,
@@ -100,6 +101,14 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
                 w[g][4 * i + 0] = v.x; w[g][4 * i + 1] = v.y; w[g][4 * i + 2] = v.z; w[g][4 * i + 3] = v.w;
             }
         const float bh_r = __ldg(S.b_hh + j), bh_z = __ldg(S.b_hh + MARL_H + j), bh_n = __ldg(S.b_hh + 2 * MARL_H + j);
+        // per-step output pointers of the rows this lane owns: advanced by one time step (N rows) per iteration
+        float* hp[OWN]; float* gp_out[OWN];
+#pragma unroll
+        for (int q = 0; q < OWN; ++q) {
+            hp[q] = S.hidden + base[q] * MARL_H + j;
+            gp_out[q] = S.gates ? S.gates + base[q] * (4 * MARL_H) + j : nullptr;
+        }
+        const long long hstep = (long long)N * MARL_H, gstep = (long long)N * 4 * MARL_H;
         auto issue = [&](int t) {
             if (t < L) {
 #pragma unroll
@@ -113,7 +122,11 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
         for (int t = 0; t < L; ++t) {
             cp_async_wait<kGiDepth - 2>();           // this thread's copies for step t have landed
             group_sync(bar_id);                      // ... the whole group's; also orders the h double buffer
-            issue(t + kGiDepth - 1);                 // refill the slot consumed in step t-1
+            // Few rows per CTA = latency-bound chain: the refill's address math and LSU hand-off (~150 cycles when it sat
+            // here, measured with clock64) go behind the FMAs, where they overlap the FMA drain.  Many rows per CTA =
+            // throughput-bound: keep the prefetch as early as possible.
+            constexpr bool kLateIssue = R <= 2;
+            if (!kLateIssue) issue(t + kGiDepth - 1);   // refill the slot consumed in step t-1
             float acc[3][R], acc2[3][R];          // two partial sums per dot product: short dependent FMA chains
 #pragma unroll
             for (int g = 0; g < 3; ++g)
@@ -132,6 +145,7 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
                         acc2[g][rr] = fmaf(w[g][4 * i + 3], hv.w, acc2[g][rr]);
                     }
                 }
+            if (kLateIssue) issue(t + kGiDepth - 1);
 #pragma unroll
             for (int g = 0; g < 3; ++g)
 #pragma unroll
@@ -157,13 +171,14 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
                     const float hold = hs[cur][rr][j];
                     const float hnew = fmaf(hold - n, z, n);
                     hs[cur ^ 1][rr][j] = hnew;
-                    const long long idx = base[q] + (long long)t * N;
-                    S.hidden[idx * MARL_H + j] = hnew;
-                    if (S.gates) {
-                        float* go = S.gates + idx * (4 * MARL_H);
-                        go[j] = r; go[MARL_H + j] = z; go[2 * MARL_H + j] = n; go[3 * MARL_H + j] = gh_n;
+                    *hp[q] = hnew;
+                    if (gp_out[q]) {
+                        float* go = gp_out[q];
+                        go[0] = r; go[MARL_H] = z; go[2 * MARL_H] = n; go[3 * MARL_H] = gh_n;
                     }
                 }
+                hp[q] += hstep;
+                if (gp_out[q]) gp_out[q] += gstep;
             }
             cur ^= 1;
         }
@@ -197,8 +212,9 @@ __global__ void __launch_bounds__(kGruThreads * kGruGroups) gru_unroll_fwd_kerne
     const int chain = blockIdx.y * kGruGroups + grp;
     if (chain >= a.n_chains) return;
     float* smem = gru_smem + grp * (gru_fwd_smem(kGruMaxRows) / sizeof(float));
-    int begin, count;
-    cta_rows(a.B * a.N, chain, begin, count);
+    int begin = 0;
+    for (int i = 0; i < (int)blockIdx.x; ++i) begin += a.rows_of[chain][i];
+    const int count = a.rows_of[chain][blockIdx.x];
     for (int off = 0; off < count; off += kGruMaxRows) {
         const int n = min(kGruMaxRows, count - off);
         if (n == 1) gru_chain_fwd<1>(a, chain, begin + off, n, smem, 1 + grp);
@@ -282,6 +298,14 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
         cp_async_commit();
     };
     for (int idx = tid; idx < 2 * R * MARL_G; idx += kGruThreads) (&sg[0][0][0])[idx] = 0.0f;
+    // per-step output pointers of the rows this lane owns, walked backwards one time step (N rows) per iteration
+    float* pi_[OWN]; float* ph_[OWN];
+#pragma unroll
+    for (int q = 0; q < OWN; ++q) {
+        pi_[q] = a.dgi + (base[q] + (long long)(L - 1) * N) * MARL_G + j;
+        ph_[q] = a.dgh + (base[q] + (long long)(L - 1) * N) * MARL_G + j;
+    }
+    const long long ostep = (long long)N * MARL_G;
 #pragma unroll
     for (int d = 0; d < D - 1; ++d) issue(L - 1 - d);
     cp_async_wait<D - 2>();
@@ -306,16 +330,19 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
                 const float dr_pre = dn_pre * g_hn * g_r * (1.0f - g_r);
                 const float dghn = dn_pre * g_r;
                 dh_dir[q] = dh * g_z;
-                const long long idx = base[q] + (long long)t * N;
-                float* pi = a.dgi + idx * MARL_G;
-                float* ph = a.dgh + idx * MARL_G;
-                pi[j] = dr_pre; pi[MARL_H + j] = dz_pre; pi[2 * MARL_H + j] = dn_pre;
-                ph[j] = dr_pre; ph[MARL_H + j] = dz_pre; ph[2 * MARL_H + j] = dghn;
+                float* pi = pi_[q];
+                float* ph = ph_[q];
+                pi[0] = dr_pre; pi[MARL_H] = dz_pre; pi[2 * MARL_H] = dn_pre;
+                ph[0] = dr_pre; ph[MARL_H] = dz_pre; ph[2 * MARL_H] = dghn;
                 sg[cur][rr][j] = dr_pre; sg[cur][rr][MARL_H + j] = dz_pre; sg[cur][rr][2 * MARL_H + j] = dghn;
             }
+            pi_[q] -= ostep; ph_[q] -= ostep;
         }
-        issue(t - (D - 1));              // refills the slot of step t+1, consumed before the previous barrier
-        cp_async_wait<D - 2>();          // this thread's copies for step t-1 have landed
+        // the refill of the slot of step t+1 (consumed before the previous barrier): early when many rows keep the CTA
+        // throughput-bound, behind the FMAs (see the forward kernel) when the chain is latency-bound
+        constexpr bool kLateIssue = R <= 2;
+        if (!kLateIssue) { issue(t - (D - 1)); cp_async_wait<D - 2>(); }
+        else cp_async_wait<D - 3>();     // only D-2 groups are pending here: step t-1 has landed
         __syncthreads();                 // dgh of step t visible; ring[t-1] visible
         float part[R], pb[R], pc[R], pd[R];     // four partial sums per row: short dependent FMA chains
 #pragma unroll
@@ -330,6 +357,7 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
                 pc[rr] = fmaf(wt[4 * i + 2], v.z, pc[rr]);
                 pd[rr] = fmaf(wt[4 * i + 3], v.w, pd[rr]);
             }
+        if (kLateIssue) issue(t - (D - 1));
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
             part[rr] = (part[rr] + pb[rr]) + (pc[rr] + pd[rr]);
@@ -363,6 +391,43 @@ __global__ void __launch_bounds__(kGruThreads) gru_unroll_bwd_kernel(GruBwdArgs 
         else if (n == 2) gru_rows_bwd<2>(a, begin + off, n, gru_smem);
         else if (n <= 4) gru_rows_bwd<4>(a, begin + off, n, gru_smem);
         else gru_rows_bwd<8>(a, begin + off, n, gru_smem);
+    }
+}
+
+// Rows of every chain per CTA.  The kernel ends when its slowest CTA does, and a CTA's time is roughly
+// (steps of the chain) x (rows it advances), so rows are dealt by water-filling on that weighted load: the first
+// chain evenly, every further chain onto the CTAs that carry the least so far.  At cfg 2 (160 rows, 148 CTAs) the 12
+// CTAs with two rows of the 240-step eval chain get no row of the 120-step target chain.
+static void plan_rows(GruFwdArgs& ga, int rows, int n_ctas) {
+    double load[kNumSMs] = {};
+    for (int c = 0; c < ga.n_chains; ++c) {
+        const double w = (double)ga.chain_len[c];
+        int cnt[kNumSMs] = {};
+        // water level by bisection: CTA i takes floor((level - load_i) / w) rows
+        double lo = 0.0, hi = 0.0;
+        for (int i = 0; i < n_ctas; ++i) hi = load[i] > hi ? load[i] : hi;
+        hi += w * (rows / n_ctas + 2);
+        for (int it = 0; it < 60; ++it) {
+            const double mid = 0.5 * (lo + hi);
+            long long tot = 0;
+            for (int i = 0; i < n_ctas; ++i) tot += mid > load[i] ? (long long)((mid - load[i]) / w) : 0;
+            if (tot >= rows) hi = mid; else lo = mid;
+        }
+        int tot = 0;
+        for (int i = 0; i < n_ctas; ++i) { cnt[i] = lo > load[i] ? (int)((lo - load[i]) / w) : 0; tot += cnt[i]; }
+        while (tot < rows) {                       // the remainder goes, one row each, to the least loaded CTAs
+            int best = 0;
+            for (int i = 1; i < n_ctas; ++i)
+                if (load[i] + w * cnt[i] < load[best] + w * cnt[best]) best = i;
+            ++cnt[best]; ++tot;
+        }
+        while (tot > rows) {                       // (bisection overshoot: take back from the most loaded)
+            int worst = -1;
+            for (int i = 0; i < n_ctas; ++i)
+                if (cnt[i] > 0 && (worst < 0 || load[i] + w * cnt[i] > load[worst] + w * cnt[worst])) worst = i;
+            --cnt[worst]; --tot;
+        }
+        for (int i = 0; i < n_ctas; ++i) { ga.rows_of[c][i] = (unsigned short)cnt[i]; load[i] += w * cnt[i]; }
     }
 }
 
@@ -445,7 +510,10 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         const size_t sm = kGruGroups * gru_fwd_smem(kGruMaxRows);
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(gru_unroll_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); attr_set = true; }
-        dim3 grid(rows < kNumSMs ? rows : kNumSMs, (ga.n_chains + kGruGroups - 1) / kGruGroups);
+        const int n_ctas = rows < kNumSMs ? rows : kNumSMs;
+        if ((rows + n_ctas - 1) / n_ctas + 2 > 65535) return MARL_EINVAL;
+        plan_rows(ga, rows, n_ctas);
+        dim3 grid(n_ctas, (ga.n_chains + kGruGroups - 1) / kGruGroups);
         gru_unroll_fwd_kernel<<<grid, kGruThreads * kGruGroups, sm, st>>>(ga);
     }
     MARL_LAUNCH_CHECK();
