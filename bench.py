@@ -273,7 +273,8 @@ def run_ours(opt):
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
         dist.all_reduce(ms_e2e_sync, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e, ms_e2e_sync = float(ms_dev) / K, float(ms_e2e) / K, float(ms_e2e_sync) / K
-    launches = learner.launches_per_step + 1          # + the ingest launch
+    launches = learner.launches_per_step + 1          # + the ingest launch (host-batch path; device batches in the
+                                                      # working-set layout are read in place: no ingest launch)
 
     # ---- per-kernel device time (eager pass, CUDA events around every launch of the library) ---------
     learner._use_graph = False
@@ -414,7 +415,7 @@ def run_ours(opt):
                 "how": "QLearner.train(host float64 dict) with learner.prefetch(next batch) issued before it: H2D of step "
                        "k+1 overlaps the compute of step k; every copy and every loss read-back is inside the timed region",
                 "without_prefetch": {"value": B * world / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync}},
-        "gpu_launches": int(launches * K * 2),
+        "gpu_launches": int((launches - 1) * K + launches * K),   # value leg (in place) + e2e leg (with ingest)
         "launches_per_step": int(launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -98,6 +98,8 @@ class QLearner:
         self._copy_stream, self._prefetched, self._slot_free, self._prefetch_seq = None, {}, {}, 0
         self.last = {}
         self.launches_per_step = 0
+        self.ingest_launches = 1
+        self._inplace_keep, self._max_inplace_graphs = {}, 32
 
     # ---- construction helpers ---------------------------------------------------------------------
     def _make_mixer(self, args):
@@ -290,18 +292,32 @@ class QLearner:
         B = hi - lo
         ws = self._workspace(B, int(Lq))
         src = L.EpisodeF32()
-        keep = []
+        keep, converted = [], 0
         for k in BATCH_KEYS:
             t = batch[k][lo:hi]
             want = th.int64 if k == "u" else th.float32
             if t.dtype != want or not t.is_contiguous():
                 t = t.to(want).contiguous()
+                converted += 1
             keep.append(t)
             setattr(src, k, t.data_ptr())
+        self.h2d_bytes_last = 0
+        if converted == 0 and T_src == int(Lq):
+            # already in the working-set layout (fp32 / int64, contiguous, no padding beyond L): the kernels read the
+            # caller's tensors in place.  The captured graph is then specific to these addresses, so it is cached
+            # per batch (the tensors are kept alive with it); past a few dozen distinct batches the copy path below
+            # takes over so that the cache stays bounded.
+            bt = dict(zip(BATCH_KEYS, keep))
+            key = (B, int(Lq)) + tuple(bt[k].data_ptr() for k in BATCH_KEYS)
+            if not self._use_graph or key in self._graphs or len(self._graphs) < self._max_inplace_graphs:
+                if self._use_graph:
+                    self._inplace_keep[key] = bt
+                self.ingest_launches = 0
+                return bt, B, int(Lq), 1
         d = self._dims(B, int(Lq))
         dst = _episode_struct(ws["batch"])
         L.call("marl_ingest_f32", C.byref(src), T_src, C.byref(d), C.byref(dst), L.stream_ptr())
-        self.h2d_bytes_last = 0
+        self.ingest_launches = 1
         return ws["batch"], B, int(Lq), 1
 
     def _stage_replay_batch(self, batch):
