@@ -263,6 +263,8 @@ int marl_qtran_losses_fwd_bwd(const marl_dims* d, const float* joint_q, const fl
  * g *= min(1, max_norm/(total_norm+1e-6)) (torch/nn/utils/clip_grad.py); grads is overwritten with the
  * clipped g (what p.grad holds after the reference's train()); loss_out[0] = loss_sum/mask_sum,
  * loss_out[1] = total_norm.  partials: workspace of marl_optim_partials() floats.
+ * Launches: n <= 4096: one CTA; n <= 2^18: one thread-block cluster of 8 CTAs exchanging the partial sums of
+ * squares through distributed shared memory; larger: a reduction launch + an update launch.  All deterministic.
  * Adam: the step count is `step` (>= 1), or -- when step_counter is non-NULL -- a device int32 that the
  * call itself pre-increments (so a captured CUDA graph can be replayed). */
 int marl_optim_partials(void);

@@ -475,7 +475,7 @@ class QLearner:
                    opt.exp_avg_sq.data_ptr(), fl.numel, fl.tail.data_ptr(), float(a.grad_norm_clip), float(self.lr),
                    0.9, 0.999, 1e-8, 0, opt.step_counter.data_ptr(), self._partials.data_ptr(),
                    self._loss_out.data_ptr(), sp)
-        return 2
+        return 1 if fl.numel <= (1 << 18) else 2      # one cluster launch up to 2^18 parameters (csrc/optim.cu)
 
     def _device_step(self, bt, ws, B, Lq):
         if self._dist is not None:

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "../../include/marl_b200.h"
 #include "profile.h"
+#include <cooperative_groups.h>
 
 namespace marl {
 
@@ -137,11 +138,102 @@ __global__ void __launch_bounds__(kFusedThreads) clip_step_fused_kernel(float* _
     }
 }
 
+// Mid-size parameter sets (cfg 2: 62,894 floats): ONE launch of one thread-block cluster.  Each of the 8 CTAs reduces
+// its slice of the squared gradient, the partial sums are exchanged through distributed shared memory (every CTA
+// reads the 8 partials in the same order, so the norm is bit-identical in all of them and deterministic), then each
+// CTA clips and updates its slice.  Replaces the sumsq + clip/update pair of launches on the step's critical path.
+constexpr long long kClusterMax = 1 << 18;
+constexpr int kClusterCtas = 8, kClusterThreads = 1024;
+
+template <bool ADAM>
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads)
+clip_step_cluster_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m1, float* __restrict__ m2, long long n,
+                         const float* __restrict__ scalars, float max_norm, float lr, float c1, float c2, float eps, int step,
+                         int* step_counter, float* loss_out) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float sw[kClusterThreads / 32];
+    __shared__ float s_part, s_scale;
+    const unsigned rank = cluster.block_rank();
+    // 128-bit accesses over the first n4 quads (all four buffers come from 16-byte aligned flat allocations), the
+    // <= 3 tail elements are handled by the first threads of CTA 0
+    const long long n4 = n >> 2, q0 = (long long)rank * kClusterThreads + threadIdx.x, qstride = (long long)kClusterCtas * kClusterThreads;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float acc = 0.f;
+#pragma unroll 2
+    for (long long q = q0; q < n4; q += qstride) {
+        const float4 v = g4[q];
+        acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+    }
+    const long long tail = (n4 << 2) + threadIdx.x;
+    const bool has_tail = rank == 0 && tail < n;
+    if (has_tail) { const float v = g[tail]; acc = fmaf(v, v, acc); }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < kClusterThreads / 32; ++w) t += sw[w];
+        s_part = t;
+        if (ADAM && step_counter && rank == 0) *step_counter += 1;      // graph-replayable Adam step count
+    }
+    cluster.sync();                                  // partials (and the step count) visible cluster-wide
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (unsigned r = 0; r < (unsigned)kClusterCtas; ++r) t += *cluster.map_shared_rank(&s_part, r);
+        const float inv = 1.0f / scalars[1];
+        const float total_norm = sqrtf(t) * inv;
+        float coef = max_norm / (total_norm + 1e-6f);
+        coef = coef > 1.0f ? 1.0f : coef;              // torch.clamp(clip_coef, max=1.0)
+        s_scale = inv * coef;
+        if (rank == 0 && loss_out) { loss_out[0] = scalars[0] * inv; loss_out[1] = total_norm; }
+    }
+    cluster.sync();                                  // nobody leaves (or overwrites s_part) while a peer still reads it
+    const float scale = s_scale;
+    float step_size = 0.f, bc2_sqrt = 1.f;
+    if (ADAM) {
+        const int stp = step_counter ? *step_counter : step;
+        step_size = (float)((double)lr / (1.0 - pow((double)c1, (double)stp)));
+        bc2_sqrt = (float)sqrt(1.0 - pow((double)c2, (double)stp));
+    }
+    auto update = [&](float& pv, float& gv, float& av, float& bv) {
+        const float gr = gv * scale;
+        gv = gr;
+        if (ADAM) {
+            const float a = av + (1.0f - c1) * (gr - av);              // exp_avg.lerp_(grad, 1-beta1)
+            const float b = c2 * bv + (1.0f - c2) * gr * gr;           // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
+            av = a; bv = b;
+            pv = pv - step_size * (a / (sqrtf(b) / bc2_sqrt + eps));
+        } else {
+            const float v = c1 * av + (1.0f - c1) * gr * gr;           // square_avg.mul_(alpha).addcmul_(g, g, 1-alpha)
+            av = v;
+            pv = pv - lr * (gr / (sqrtf(v) + eps));                    // p.addcdiv_(g, sqrt(v)+eps, -lr)
+        }
+    };
+    float4* p4 = reinterpret_cast<float4*>(p); float4* gw4 = reinterpret_cast<float4*>(g);
+    float4* a4 = reinterpret_cast<float4*>(m1); float4* b4 = reinterpret_cast<float4*>(m2);
+#pragma unroll 2
+    for (long long q = q0; q < n4; q += qstride) {
+        float4 pv = p4[q], gv = gw4[q], av = a4[q], bv = ADAM ? b4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        update(pv.x, gv.x, av.x, bv.x); update(pv.y, gv.y, av.y, bv.y); update(pv.z, gv.z, av.z, bv.z); update(pv.w, gv.w, av.w, bv.w);
+        p4[q] = pv; gw4[q] = gv; a4[q] = av;
+        if (ADAM) b4[q] = bv;
+    }
+    if (has_tail) {
+        float pv = p[tail], gv = g[tail], av = m1[tail], bv = ADAM ? m2[tail] : 0.f;
+        update(pv, gv, av, bv);
+        p[tail] = pv; g[tail] = gv; m1[tail] = av;
+        if (ADAM) m2[tail] = bv;
+    }
+}
+
 }  // namespace marl
 
 using namespace marl;
 
 extern "C" int marl_optim_partials(void) { return kOptBlocks; }
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int opt_grid(long long n) {
     long long b = (n + kOptThreads - 1) / kOptThreads;
@@ -157,6 +249,13 @@ extern "C" int marl_clip_rmsprop_step(float* params, float* grads, float* square
         { ProfScope ps_("clip_step_fused_kernel", st);
           clip_step_fused_kernel<false><<<1, kFusedThreads, 0, st>>>(params, grads, square_avg, nullptr, n, scalars, max_norm,
                                                                      lr, alpha, 0.f, eps, 0, nullptr, loss_out); }
+        MARL_LAUNCH_CHECK();
+        return MARL_OK;
+    }
+    if (n <= kClusterMax && aligned16(params) && aligned16(grads) && aligned16(square_avg)) {
+        { ProfScope ps_("clip_step_cluster_kernel", st);
+          clip_step_cluster_kernel<false><<<kClusterCtas, kClusterThreads, 0, st>>>(params, grads, square_avg, nullptr, n, scalars,
+                                                                                     max_norm, lr, alpha, 0.f, eps, 0, nullptr, loss_out); }
         MARL_LAUNCH_CHECK();
         return MARL_OK;
     }
@@ -178,6 +277,13 @@ extern "C" int marl_clip_adam_step(float* params, float* grads, float* exp_avg, 
         { ProfScope ps_("clip_step_fused_kernel", st);
           clip_step_fused_kernel<true><<<1, kFusedThreads, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, scalars, max_norm,
                                                                     lr, beta1, beta2, eps, step, step_counter, loss_out); }
+        MARL_LAUNCH_CHECK();
+        return MARL_OK;
+    }
+    if (n <= kClusterMax && aligned16(params) && aligned16(grads) && aligned16(exp_avg) && aligned16(exp_avg_sq)) {
+        { ProfScope ps_("clip_step_cluster_kernel", st);
+          clip_step_cluster_kernel<true><<<kClusterCtas, kClusterThreads, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, scalars,
+                                                                                    max_norm, lr, beta1, beta2, eps, step, step_counter, loss_out); }
         MARL_LAUNCH_CHECK();
         return MARL_OK;
     }
