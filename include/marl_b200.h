@@ -190,6 +190,29 @@ int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* p, const ma
 int marl_qmix_hyper_fwd(int M, int N, int S, const marl_qmix_params* p, const float* s, float* hy, void* stream);
 int marl_qmix_hyper_wgrad(int M, int N, int S, const float* s, const float* dhy, const marl_qmix_grads* g, void* stream);
 
+/* two_hyper_layers = True (network/mixer.py:36-43): hyper_w1 / hyper_w2 are Linear(S, hh) - ReLU - Linear(hh, .).
+ *   w_in [2 hh, S] = hyper_w1.0 | hyper_w2.0 (b_in likewise), w1_out [N*E, hh] = hyper_w1.2, w2_out [E, hh] = hyper_w2.2,
+ *   w_b1 [E, S] = hyper_b1, w_b20 [E, S] = hyper_b2.0.
+ * marl_qmix_hyper2_fwd fills the hy layout the mixing kernel reads ([w1 | b1 | w2 | b2.0], h [M, 2 hh] keeps the hidden
+ * layers); run marl_qmix_td_fwd_bwd / marl_qmix_fwd|bwd kernels with flags = 3 on that hy (their wcat / bcat are then
+ * unused) and finish with marl_qmix_hyper2_bwd(dhy) (dh [M, 2 hh] workspace; gradients are accumulated). */
+typedef struct marl_qmix_hyper2 {
+    const float* w_in; const float* b_in; const float* w1_out; const float* b1_out; const float* w2_out; const float* b2_out;
+    const float* w_b1; const float* b_b1; const float* w_b20; const float* b_b20; int hh;
+} marl_qmix_hyper2;
+typedef struct marl_qmix_hyper2_grads {
+    float* w_in; float* b_in; float* w1_out; float* b1_out; float* w2_out; float* b2_out;
+    float* w_b1; float* b_b1; float* w_b20; float* b_b20;
+} marl_qmix_hyper2_grads;
+int marl_qmix_hyper2_fwd(int M, int N, int S, const marl_qmix_hyper2* p, const float* s, float* h, float* hy, void* stream);
+int marl_qmix_hyper2_bwd(int M, int N, int S, const marl_qmix_hyper2* p, const float* s, const float* h, const float* dhy,
+                         float* dh, const marl_qmix_hyper2_grads* g, void* stream);
+/* Mixing only (q_tot from a filled hy; backward to dhy / dq / hyper_b2.2): the kernels behind marl_qmix_fwd / _bwd
+ * without their hyper-network GEMMs. */
+int marl_qmix_mix_fwd(int M, int N, const marl_qmix_params* p, const float* q, const float* hy, float* q_tot, void* stream);
+int marl_qmix_mix_bwd(int M, int N, const marl_qmix_params* p, const float* q, const float* hy, const float* dq_tot,
+                      float* dhy, float* dq, const marl_qmix_grads* g, void* stream);
+
 /* ---- QPLEX: DMAQer + DMAQ_SI_Weight, network/mixer.py:85-288 (adv_hypernet_layers = 3) ----
  * Parameters are passed layer-concatenated (the host lays them out that way), K = num_kernel,
  * he = hypernet_embed, ae = adv_hypernet_embed:

@@ -66,6 +66,17 @@ class QmixGrads(C.Structure):
     _fields_ = [(k, c_ptr) for k in ("wcat", "bcat", "wb2", "bb2")]
 
 
+QMIX_HYPER2_FIELDS = ("w_in", "b_in", "w1_out", "b1_out", "w2_out", "b2_out", "w_b1", "b_b1", "w_b20", "b_b20")
+
+
+class QmixHyper2(C.Structure):       # two_hyper_layers=True parameters (include/marl_b200.h: marl_qmix_hyper2)
+    _fields_ = [(k, c_ptr) for k in QMIX_HYPER2_FIELDS] + [("hh", C.c_int)]
+
+
+class QmixHyper2Grads(C.Structure):
+    _fields_ = [(k, c_ptr) for k in QMIX_HYPER2_FIELDS]
+
+
 class QplexDims(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("N", "A", "S", "he", "ae", "K", "weighted_head", "is_minus_one")]
 
@@ -120,6 +131,10 @@ _SIGNATURES = {
     "marl_qmix_td_fwd_bwd": ([_P(Dims), _P(QmixParams), _P(QmixParams)] + [c_ptr] * 8 + [C.c_float] + [c_ptr] * 6
                              + [_P(QmixGrads), c_ptr, C.c_int, c_ptr], C.c_int),
     "marl_qmix_hyper_fwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams), c_ptr, c_ptr, c_ptr], C.c_int),
+    "marl_qmix_hyper2_fwd": ([C.c_int, C.c_int, C.c_int, _P(QmixHyper2), c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
+    "marl_qmix_hyper2_bwd": ([C.c_int, C.c_int, C.c_int, _P(QmixHyper2), c_ptr, c_ptr, c_ptr, c_ptr, _P(QmixHyper2Grads), c_ptr], C.c_int),
+    "marl_qmix_mix_fwd": ([C.c_int, C.c_int, _P(QmixParams), c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
+    "marl_qmix_mix_bwd": ([C.c_int, C.c_int, _P(QmixParams)] + [c_ptr] * 5 + [_P(QmixGrads), c_ptr], C.c_int),
     "marl_qmix_hyper_wgrad": ([C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, _P(QmixGrads), c_ptr], C.c_int),
     "marl_qplex_fwd": ([C.c_int, _P(QplexDims), _P(QplexParams)] + [c_ptr] * 4 + [_P(QplexWs)] + [c_ptr] * 4, C.c_int),
     "marl_qplex_bwd": ([C.c_int, _P(QplexDims), _P(QplexParams)] + [c_ptr] * 4 + [_P(QplexWs), c_ptr, c_ptr, _P(QplexWs), c_ptr,

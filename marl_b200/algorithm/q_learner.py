@@ -30,7 +30,7 @@ from .. import _lib as L
 from ..flat import FlatBuffer, prefixed
 from ..parallel import shard_bounds, allreduce_flat
 from ..common.replaybuffer import DeviceEpisodeBatch
-from ..network.mixer import VDNMixer, QMixMixer, qmix_struct
+from ..network.mixer import VDNMixer, QMixMixer, qmix_struct, qmix2_struct, qmix_tail_struct, QMIX2_FLAT_ORDER
 from ..network.q_network import agent_param_struct, AGENT_FLAT_ORDER
 
 H = 64
@@ -190,6 +190,9 @@ class QLearner:
         if a.alg == "qmix":
             Ccols = N * 32 + 96
             ws.update(hy=f(M, Ccols), hy_t=f(M, Ccols), dhy=f(M, Ccols))
+            if getattr(a, "two_hyper_layers", False):
+                hh2 = 2 * a.hyper_hidden_dim
+                ws.update(hh=f(M, hh2), hh_t=f(M, hh2), dhh=f(M, hh2))
         if a.alg == "qplex":
             from ..network.qplex import qplex_workspace
             ws.update(qp=qplex_workspace(M, a, dev), qp_t=qplex_workspace(M, a, dev), dqp=qplex_workspace(M, a, dev),
@@ -364,19 +367,37 @@ class QLearner:
             # the hyper-networks only read the states: run them beside the (latency-bound) agent unrolls
             if self._side is None:
                 self._side = th.cuda.Stream()
-            qp = qmix_struct({n: self._flat.ptr("mixer." + n) for n in ("hyper_w1.weight", "hyper_w1.bias",
-                                                                        "hyper_b2.2.weight", "hyper_b2.2.bias")})
-            qpt = qmix_struct({n: self._tflat.ptr("mixer." + n) for n in ("hyper_w1.weight", "hyper_w1.bias",
-                                                                          "hyper_b2.2.weight", "hyper_b2.2.bias")})
-            qg = qmix_struct({n: self._flat.ptr("mixer." + n, self._flat.grad) for n in
-                              ("hyper_w1.weight", "hyper_w1.bias", "hyper_b2.2.weight", "hyper_b2.2.bias")}, L.QmixGrads)
+            two = bool(getattr(a, "two_hyper_layers", False))
+            if two:
+                hh = a.hyper_hidden_dim
+                qp = qmix_tail_struct({n: self._flat.ptr("mixer." + n) for n in ("hyper_b2.2.weight", "hyper_b2.2.bias")})
+                qpt = qmix_tail_struct({n: self._tflat.ptr("mixer." + n) for n in ("hyper_b2.2.weight", "hyper_b2.2.bias")})
+                qg = qmix_tail_struct({n: self._flat.ptr("mixer." + n, self._flat.grad) for n in
+                                       ("hyper_b2.2.weight", "hyper_b2.2.bias")}, L.QmixGrads)
+                q2 = qmix2_struct({n: self._flat.ptr("mixer." + n) for n in QMIX2_FLAT_ORDER}, hh)
+                q2t = qmix2_struct({n: self._tflat.ptr("mixer." + n) for n in QMIX2_FLAT_ORDER}, hh)
+                g2 = qmix2_struct({n: self._flat.ptr("mixer." + n, self._flat.grad) for n in QMIX2_FLAT_ORDER}, None,
+                                  L.QmixHyper2Grads)
+            else:
+                qp = qmix_struct({n: self._flat.ptr("mixer." + n) for n in ("hyper_w1.weight", "hyper_w1.bias",
+                                                                            "hyper_b2.2.weight", "hyper_b2.2.bias")})
+                qpt = qmix_struct({n: self._tflat.ptr("mixer." + n) for n in ("hyper_w1.weight", "hyper_w1.bias",
+                                                                              "hyper_b2.2.weight", "hyper_b2.2.bias")})
+                qg = qmix_struct({n: self._flat.ptr("mixer." + n, self._flat.grad) for n in
+                                  ("hyper_w1.weight", "hyper_w1.bias", "hyper_b2.2.weight", "hyper_b2.2.bias")}, L.QmixGrads)
             self._side.wait_stream(cur)
             with th.cuda.stream(self._side):
                 ssp = L.stream_ptr()
-                L.call("marl_qmix_hyper_fwd", B * Lq, a.n_agents, a.state_shape, C.byref(qp), bt["s"].data_ptr(),
-                       ws["hy"].data_ptr(), ssp)
-                L.call("marl_qmix_hyper_fwd", B * Lq, a.n_agents, a.state_shape, C.byref(qpt), bt["s_next"].data_ptr(),
-                       ws["hy_t"].data_ptr(), ssp)
+                if two:
+                    L.call("marl_qmix_hyper2_fwd", B * Lq, a.n_agents, a.state_shape, C.byref(q2), bt["s"].data_ptr(),
+                           ws["hh"].data_ptr(), ws["hy"].data_ptr(), ssp)
+                    L.call("marl_qmix_hyper2_fwd", B * Lq, a.n_agents, a.state_shape, C.byref(q2t), bt["s_next"].data_ptr(),
+                           ws["hh_t"].data_ptr(), ws["hy_t"].data_ptr(), ssp)
+                else:
+                    L.call("marl_qmix_hyper_fwd", B * Lq, a.n_agents, a.state_shape, C.byref(qp), bt["s"].data_ptr(),
+                           ws["hy"].data_ptr(), ssp)
+                    L.call("marl_qmix_hyper_fwd", B * Lq, a.n_agents, a.state_shape, C.byref(qpt), bt["s_next"].data_ptr(),
+                           ws["hy_t"].data_ptr(), ssp)
         n_streams = 3 if double_q else 2
         arr = (L.UnrollStream * 3)()
 
@@ -417,9 +438,13 @@ class QLearner:
             # ... and their weight gradient beside the BPTT
             self._side.wait_stream(cur)
             with th.cuda.stream(self._side):
-                L.call("marl_qmix_hyper_wgrad", B * Lq, a.n_agents, a.state_shape, bt["s"].data_ptr(), ws["dhy"].data_ptr(),
-                       C.byref(g), L.stream_ptr())
-            n_launch += 4
+                if two:
+                    L.call("marl_qmix_hyper2_bwd", B * Lq, a.n_agents, a.state_shape, C.byref(q2), bt["s"].data_ptr(),
+                           ws["hh"].data_ptr(), ws["dhy"].data_ptr(), ws["dhh"].data_ptr(), C.byref(g2), L.stream_ptr())
+                else:
+                    L.call("marl_qmix_hyper_wgrad", B * Lq, a.n_agents, a.state_shape, bt["s"].data_ptr(), ws["dhy"].data_ptr(),
+                           C.byref(g), L.stream_ptr())
+            n_launch += 18 if two else 4
         elif a.alg == "qplex":
             from ..network.qplex import qplex_struct, qplex_dims, ws_struct
             M = B * Lq

@@ -143,6 +143,63 @@ static int hyper_wgrad(int M, int N, int S, const float* s, const float* dhy, co
     return linear_wgrad(w, st);
 }
 
+// two_hyper_layers = True (network/mixer.py:36-43): hyper_w1 = Linear(S, hh) - ReLU - Linear(hh, N*E), hyper_w2 likewise
+// with E outputs; hyper_b1 / hyper_b2 keep one layer.  h [M, 2 hh] holds the two hidden layers (after the ReLU) for
+// the backward; the outputs land in the same hy layout [w1 | b1 | w2 | b2.0] the mixing kernel reads.
+static int hyper2_fwd(int M, int N, int S, const marl_qmix_hyper2* p, const float* s, float* h, float* hy, cudaStream_t st) {
+    const int hh = p->hh, C = N * E + 3 * E;
+    int rc;
+    LinearFwd f{};
+    f.in = plain_operand(s, S, S); f.w = p->w_in; f.ldw = S; f.bias = p->b_in;
+    f.y = h; f.ldy = 2 * hh; f.M = M; f.N = 2 * hh; f.relu = 1; f.batch = 1;
+    if ((rc = linear_fwd(f, st))) return rc;
+    LinearFwd a{};
+    a.in = plain_operand(h, 2 * hh, hh); a.w = p->w1_out; a.ldw = hh; a.bias = p->b1_out;
+    a.y = hy; a.ldy = C; a.M = M; a.N = N * E; a.batch = 1;
+    if ((rc = linear_fwd(a, st))) return rc;
+    LinearFwd b{};
+    b.in = plain_operand(h + hh, 2 * hh, hh); b.w = p->w2_out; b.ldw = hh; b.bias = p->b2_out;
+    b.y = hy + N * E + E; b.ldy = C; b.M = M; b.N = E; b.batch = 1;
+    if ((rc = linear_fwd(b, st))) return rc;
+    LinearFwd c{};
+    c.in = plain_operand(s, S, S); c.w = p->w_b1; c.ldw = S; c.bias = p->b_b1;
+    c.y = hy + N * E; c.ldy = C; c.M = M; c.N = E; c.batch = 1;
+    if ((rc = linear_fwd(c, st))) return rc;
+    LinearFwd e{};
+    e.in = plain_operand(s, S, S); e.w = p->w_b20; e.ldw = S; e.bias = p->b_b20;
+    e.y = hy + N * E + 2 * E; e.ldy = C; e.M = M; e.N = E; e.batch = 1;
+    return linear_fwd(e, st);
+}
+
+// gradients of everything in front of hy, given dhy [M, C]; dh [M, 2 hh] workspace
+static int hyper2_bwd(int M, int N, int S, const marl_qmix_hyper2* p, const float* s, const float* h, const float* dhy,
+                      float* dh, const marl_qmix_hyper2_grads* g, cudaStream_t st) {
+    const int hh = p->hh, C = N * E + 3 * E;
+    int rc;
+    LinearWgrad w{};                     // hyper_b1
+    w.dy = dhy + N * E; w.lddy = C; w.in = plain_operand(s, S, S); w.dw = g->w_b1; w.ldw = S; w.db = g->b_b1; w.M = M; w.N = E; w.batch = 1;
+    if ((rc = linear_wgrad(w, st))) return rc;
+    w.dy = dhy + N * E + 2 * E; w.dw = g->w_b20; w.db = g->b_b20;     // hyper_b2.0
+    if ((rc = linear_wgrad(w, st))) return rc;
+    LinearWgrad o1{};                    // hyper_w1.2
+    o1.dy = dhy; o1.lddy = C; o1.in = plain_operand(h, 2 * hh, hh); o1.dw = g->w1_out; o1.ldw = hh; o1.db = g->b1_out; o1.M = M; o1.N = N * E; o1.batch = 1;
+    if ((rc = linear_wgrad(o1, st))) return rc;
+    LinearWgrad o2{};                    // hyper_w2.2
+    o2.dy = dhy + N * E + E; o2.lddy = C; o2.in = plain_operand(h + hh, 2 * hh, hh); o2.dw = g->w2_out; o2.ldw = hh; o2.db = g->b2_out; o2.M = M; o2.N = E; o2.batch = 1;
+    if ((rc = linear_wgrad(o2, st))) return rc;
+    LinearDgrad d1{};                    // dh[:, :hh] = (dhy_w1 . W1.2) * (h > 0)
+    d1.dy = dhy; d1.lddy = C; d1.w = p->w1_out; d1.ldw = hh; d1.dx = dh; d1.lddx = 2 * hh; d1.relu_src = h; d1.ldrs = 2 * hh;
+    d1.M = M; d1.N = N * E; d1.K = hh; d1.batch = 1;
+    if ((rc = linear_dgrad(d1, st))) return rc;
+    LinearDgrad d2{};                    // dh[:, hh:] = (dhy_w2 . W2.2) * (h > 0)
+    d2.dy = dhy + N * E + E; d2.lddy = C; d2.w = p->w2_out; d2.ldw = hh; d2.dx = dh + hh; d2.lddx = 2 * hh; d2.relu_src = h + hh; d2.ldrs = 2 * hh;
+    d2.M = M; d2.N = E; d2.K = hh; d2.batch = 1;
+    if ((rc = linear_dgrad(d2, st))) return rc;
+    LinearWgrad i{};                     // the two first layers as one [2 hh, S] problem
+    i.dy = dh; i.lddy = 2 * hh; i.in = plain_operand(s, S, S); i.dw = g->w_in; i.ldw = S; i.db = g->b_in; i.M = M; i.N = 2 * hh; i.batch = 1;
+    return linear_wgrad(i, st);
+}
+
 static int mix_grid(int M) {
     int blocks = (M + kQmixWarps - 1) / kQmixWarps;
     return blocks < 1 ? 1 : (blocks > 4 * kNumSMs ? 4 * kNumSMs : blocks);
@@ -188,9 +245,11 @@ extern "C" int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* 
                                     const long long* u, const float* r, const float* terminated, const float* padded,
                                     float gamma, float* hy, float* hy_target, float* dhy, float* q_tot, float* q_tot_target,
                                     float* dq, const marl_qmix_grads* g, float* scalars, int flags, void* stream) {
-    if (!d || !qmix_params_ok(p) || !qmix_params_ok(pt) || !s || !s_next || !q_chosen || !q_tc || !r || !terminated ||
-        !padded || !hy || !hy_target || !dhy || !g || !scalars)
+    if (!d || !p || !pt || !p->wb2 || !p->bb2 || !pt->wb2 || !pt->bb2 || !s || !s_next || !q_chosen || !q_tc || !r ||
+        !terminated || !padded || !hy || !hy_target || !dhy || !g || !scalars)
         return MARL_EINVAL;
+    if (!(flags & 1) && (!p->wcat || !p->bcat || !pt->wcat || !pt->bcat)) return MARL_EINVAL;   // hyper GEMMs run here
+    if (!(flags & 2) && (!g->wcat || !g->bcat)) return MARL_EINVAL;
     if (dq && !u) return MARL_EINVAL;
     if (d->N < 1 || d->N > kQmixMaxAgents || d->S < 1) return MARL_EINVAL;
     const int M = d->B * d->L;
@@ -214,6 +273,52 @@ extern "C" int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* 
     MARL_LAUNCH_CHECK();
     if (flags & 2) return MARL_OK;
     return hyper_wgrad(M, d->N, d->S, s, dhy, g, st);
+}
+
+extern "C" int marl_qmix_mix_fwd(int M, int N, const marl_qmix_params* p, const float* q, const float* hy, float* q_tot,
+                                 void* stream) {
+    if (M < 0 || N < 1 || N > kQmixMaxAgents || !p || !p->wb2 || !p->bb2 || !q || !hy || !q_tot) return MARL_EINVAL;
+    if (M == 0) return MARL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    QmixMixArgs a{};
+    a.M = M; a.N = N; a.mode = QMIX_FWD; a.hy = hy; a.q = q; a.wb2 = p->wb2; a.bb2 = p->bb2; a.q_tot = q_tot;
+    { ProfScope ps_("qmix_mix_kernel", st); qmix_mix_kernel<<<mix_grid(M), kQmixWarps * 32, 0, st>>>(a); }
+    MARL_LAUNCH_CHECK();
+    return MARL_OK;
+}
+
+extern "C" int marl_qmix_mix_bwd(int M, int N, const marl_qmix_params* p, const float* q, const float* hy,
+                                 const float* dq_tot, float* dhy, float* dq, const marl_qmix_grads* g, void* stream) {
+    if (M < 0 || N < 1 || N > kQmixMaxAgents || !p || !p->wb2 || !p->bb2 || !q || !hy || !dq_tot || !dhy || !g) return MARL_EINVAL;
+    if (M == 0) return MARL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    QmixMixArgs a{};
+    a.M = M; a.N = N; a.mode = QMIX_BWD; a.hy = hy; a.q = q; a.wb2 = p->wb2; a.bb2 = p->bb2;
+    a.dq_tot_in = dq_tot; a.dhy = dhy; a.dq_small = dq; a.g_wb2 = g->wb2; a.g_bb2 = g->bb2;
+    { ProfScope ps_("qmix_mix_kernel", st); qmix_mix_kernel<<<mix_grid(M), kQmixWarps * 32, 0, st>>>(a); }
+    MARL_LAUNCH_CHECK();
+    return MARL_OK;
+}
+
+static bool hyper2_ok(const marl_qmix_hyper2* p) {
+    return p && p->hh > 0 && p->w_in && p->b_in && p->w1_out && p->b1_out && p->w2_out && p->b2_out && p->w_b1 && p->b_b1 &&
+           p->w_b20 && p->b_b20;
+}
+
+extern "C" int marl_qmix_hyper2_fwd(int M, int N, int S, const marl_qmix_hyper2* p, const float* s, float* h, float* hy,
+                                    void* stream) {
+    if (M < 0 || N < 1 || N > kQmixMaxAgents || S < 1 || !hyper2_ok(p) || !s || !h || !hy) return MARL_EINVAL;
+    if (M == 0) return MARL_OK;
+    return hyper2_fwd(M, N, S, p, s, h, hy, (cudaStream_t)stream);
+}
+
+extern "C" int marl_qmix_hyper2_bwd(int M, int N, int S, const marl_qmix_hyper2* p, const float* s, const float* h,
+                                    const float* dhy, float* dh, const marl_qmix_hyper2_grads* g, void* stream) {
+    if (M < 0 || N < 1 || N > kQmixMaxAgents || S < 1 || !hyper2_ok(p) || !s || !h || !dhy || !dh || !g || !g->w_in ||
+        !g->b_in || !g->w1_out || !g->b1_out || !g->w2_out || !g->b2_out || !g->w_b1 || !g->b_b1 || !g->w_b20 || !g->b_b20)
+        return MARL_EINVAL;
+    if (M == 0) return MARL_OK;
+    return hyper2_bwd(M, N, S, p, s, h, dhy, dh, g, (cudaStream_t)stream);
 }
 
 extern "C" int marl_qmix_hyper_fwd(int M, int N, int S, const marl_qmix_params* p, const float* s, float* hy, void* stream) {

@@ -63,8 +63,9 @@ def run_case(name, alg, batch, N, A, O, S, T, n_steps=3, seed=0, **kw):
            "meta/dims": np.array([N, A, O, S, T]), "meta/n_steps": np.array(n_steps),
            "meta/double_q": np.array(int(args.double_q)), "meta/lr": np.array(args.lr),
            "meta/target_update_cycle": np.array(args.target_update_cycle)}
-    for k in ("num_kernel", "adv_hypernet_embed", "hypernet_embed", "qtran_hidden_dim"):
+    for k in ("num_kernel", "adv_hypernet_embed", "hypernet_embed", "qtran_hidden_dim", "hyper_hidden_dim"):
         out[f"meta/{k}"] = np.array(getattr(args, k))
+    out["meta/two_hyper_layers"] = np.array(int(args.two_hyper_layers))
     for k, v in batch.items():
         out[f"batch/{k}"] = np.asarray(v)
     dump_sd("init/agent", mac.agent.state_dict(), out)
@@ -159,10 +160,13 @@ def env_case():
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    env_case()
     tiny = dict(N=3, A=4, O=5, S=6, T=6)
     tb = synthetic_batch(0, 4, tiny["T"], tiny["N"], tiny["A"], tiny["O"], tiny["S"])
     small_qplex = dict(num_kernel=2, adv_hypernet_embed=8, hypernet_embed=8)
+    if "two_hyper" in sys.argv[1:]:        # only the case added for SURVEY 8(f) N4 (the other fixtures stay as committed)
+        run_case("tiny_qmix_two_hyper", "qmix", tb, **tiny, target_update_cycle=2, two_hyper_layers=True, hyper_hidden_dim=16)
+        return
+    env_case()
     run_case("tiny_vdn_rms", "vdn", tb, **tiny, target_update_cycle=2)
     run_case("tiny_qmix_rms", "qmix", tb, **tiny, target_update_cycle=2)
     run_case("tiny_qmix_adam", "qmix", tb, **tiny, optimizer="Adam", target_update_cycle=2)
@@ -176,6 +180,7 @@ def main():
     # one ragged mid-size case: first episode shorter than the limit -> truncation L < T
     rb = synthetic_batch(3, 5, 9, 2, 5, 7, 4, full_length_first=False, min_len=2)
     run_case("ragged_qmix_rms", "qmix", rb, N=2, A=5, O=7, S=4, T=9, n_steps=2)
+    run_case("tiny_qmix_two_hyper", "qmix", tb, **tiny, target_update_cycle=2, two_hyper_layers=True, hyper_hidden_dim=16)
 
 
 if __name__ == "__main__":

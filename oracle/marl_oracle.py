@@ -76,8 +76,15 @@ def init_mixer(cfg, alg=None):
         return sd
     if alg == "qmix":  # mixer.py:45-55
         E = cfg.qmix_hidden_dim
-        _linear(sd, "hyper_w1", S, N * E)
-        _linear(sd, "hyper_w2", S, E)
+        if getattr(cfg, "two_hyper_layers", False):  # mixer.py:36-43
+            hh = cfg.hyper_hidden_dim
+            _linear(sd, "hyper_w1.0", S, hh)
+            _linear(sd, "hyper_w1.2", hh, N * E)
+            _linear(sd, "hyper_w2.0", S, hh)
+            _linear(sd, "hyper_w2.2", hh, E)
+        else:
+            _linear(sd, "hyper_w1", S, N * E)
+            _linear(sd, "hyper_w2", S, E)
         _linear(sd, "hyper_b1", S, E)
         _linear(sd, "hyper_b2.0", S, E)
         _linear(sd, "hyper_b2.2", E, 1)
@@ -173,15 +180,21 @@ def vdn_mix(q):  # mixer.py:16
 
 
 def qmix_mix(p, q, s, cfg):
-    """mixer.py:57-80 (two_hyper_layers=False)."""
+    """mixer.py:57-80; hyper_w1 / hyper_w2 are one Linear (:44-47) or Linear-ReLU-Linear (two_hyper_layers, :36-43)."""
     B = q.shape[0]
     N, E = cfg.n_agents, cfg.qmix_hidden_dim
     q = q.reshape(-1, 1, N)
     s = s.reshape(-1, cfg.state_shape)
-    w1 = torch.abs(F.linear(s, p["hyper_w1.weight"], p["hyper_w1.bias"])).view(-1, N, E)
+
+    def hyper(name):
+        if name + ".0.weight" in p:
+            return F.linear(F.relu(F.linear(s, p[name + ".0.weight"], p[name + ".0.bias"])), p[name + ".2.weight"], p[name + ".2.bias"])
+        return F.linear(s, p[name + ".weight"], p[name + ".bias"])
+
+    w1 = torch.abs(hyper("hyper_w1")).view(-1, N, E)
     b1 = F.linear(s, p["hyper_b1.weight"], p["hyper_b1.bias"]).view(-1, 1, E)
     hid = F.elu(torch.bmm(q, w1) + b1)
-    w2 = torch.abs(F.linear(s, p["hyper_w2.weight"], p["hyper_w2.bias"])).view(-1, E, 1)
+    w2 = torch.abs(hyper("hyper_w2")).view(-1, E, 1)
     b2 = F.linear(F.relu(F.linear(s, p["hyper_b2.0.weight"], p["hyper_b2.0.bias"])),
                   p["hyper_b2.2.weight"], p["hyper_b2.2.bias"]).view(-1, 1, 1)
     return (torch.bmm(hid, w2) + b2).view(B, -1, 1)

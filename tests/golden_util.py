@@ -32,7 +32,9 @@ def cfg_from(z):
                        obs_shape=O, state_shape=S, episode_limit=T, double_q=bool(int(z["meta/double_q"])),
                        lr=float(z["meta/lr"]), target_update_cycle=int(z["meta/target_update_cycle"]),
                        num_kernel=int(z["meta/num_kernel"]), adv_hypernet_embed=int(z["meta/adv_hypernet_embed"]),
-                       hypernet_embed=int(z["meta/hypernet_embed"]), qtran_hidden_dim=int(z["meta/qtran_hidden_dim"]))
+                       hypernet_embed=int(z["meta/hypernet_embed"]), qtran_hidden_dim=int(z["meta/qtran_hidden_dim"]),
+                       two_hyper_layers=bool(int(z["meta/two_hyper_layers"])) if "meta/two_hyper_layers" in z else False,
+                       hyper_hidden_dim=int(z["meta/hyper_hidden_dim"]) if "meta/hyper_hidden_dim" in z else 64)
 
 
 def init_params(z):

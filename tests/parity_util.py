@@ -30,7 +30,7 @@ def oracle_cfg(args):
         "alg", "optimizer", "n_agents", "n_actions", "obs_shape", "state_shape", "episode_limit", "double_q", "lr",
         "target_update_cycle", "num_kernel", "adv_hypernet_embed", "hypernet_embed", "qtran_hidden_dim", "gamma",
         "grad_norm_clip", "lambda_opt", "lambda_nopt", "weighted_head", "is_minus_one", "rnn_hidden_dim",
-        "qmix_hidden_dim")})
+        "qmix_hidden_dim", "two_hyper_layers", "hyper_hidden_dim")})
 
 
 def build_pair(args, params=None, seed=0, dtype=torch.float32):

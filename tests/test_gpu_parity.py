@@ -114,9 +114,10 @@ def test_single_step_module_forward_and_autograd():
 
 
 # ------------------------------------------------------------------------------------------ mixer
-def test_qmix_module_forward_backward():
+@pytest.mark.parametrize("two_hyper_layers", [False, True])
+def test_qmix_module_forward_backward(two_hyper_layers):
     from marl_b200.network.mixer import QMixMixer
-    args = PU.make_args("qmix", 5, 11, 80, 120, 10)
+    args = PU.make_args("qmix", 5, 11, 80, 120, 10, two_hyper_layers=two_hyper_layers)
     torch.manual_seed(0)
     mixer = QMixMixer(args)
     sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in mixer.state_dict().items()}
@@ -144,7 +145,8 @@ def test_learner_reproduces_reference_goldens(name):
     args = PU.make_args(cfg.alg, cfg.n_agents, cfg.n_actions, cfg.obs_shape, cfg.state_shape, cfg.episode_limit,
                         optimizer=cfg.optimizer, double_q=cfg.double_q, lr=cfg.lr, target_update_cycle=cfg.target_update_cycle,
                         num_kernel=cfg.num_kernel, adv_hypernet_embed=cfg.adv_hypernet_embed,
-                        hypernet_embed=cfg.hypernet_embed, qtran_hidden_dim=cfg.qtran_hidden_dim)
+                        hypernet_embed=cfg.hypernet_embed, qtran_hidden_dim=cfg.qtran_hidden_dim,
+                        two_hyper_layers=cfg.two_hyper_layers, hyper_hidden_dim=cfg.hyper_hidden_dim)
     learner, _ = PU.build_pair(args, GU.init_params(z))
     batch = GU.batch_of(z)
     losses = []
@@ -231,6 +233,12 @@ def _train_compare(args, batch, steps, graph, arbitrate=False):
             if f"{g}.{k}" in mine and info["clipped_grads"].get(f"{g}.{k}") is not None and not arbitrate:
                 PU.params_close(mine[f"{g}.{k}"], p, args.lr, step + 1, report, f"param@{step}[{g}.{k}]")
     assert not report, "\n".join(report)
+
+
+def test_learner_2s3z_shape_two_hyper_layers_vs_oracle():
+    """QMIX with two_hyper_layers=True (network/mixer.py:36-43) at the 2s3z shape, three steps, graph replay."""
+    args = PU.make_args("qmix", 5, 11, 80, 120, 120, two_hyper_layers=True)
+    _train_compare(args, synthetic_batch(0, 32, 120, 5, 11, 80, 120), 3, True)
 
 
 @pytest.mark.parametrize("alg", ["vdn", "qmix"])
