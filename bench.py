@@ -223,6 +223,11 @@ def run_ours(opt):
         torch.cuda.synchronize()
 
     step = 0
+    # resident batches are read in place, each through its own captured graph: run every batch through the eager
+    # call and the capture call before anything is timed (W warm-up replays follow)
+    for _ in range(2):
+        for b in dev_batches:
+            learner.train(b, step); step += 1
     for i in range(W):
         learner.train(dev_batches[i % NB], step); step += 1
     for i in range(max(W, 3)):
