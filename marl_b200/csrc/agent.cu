@@ -207,6 +207,7 @@ constexpr int kGruMaxRows = 8;     // rows per group and pass
 constexpr size_t gru_fwd_smem(int R) { return (size_t)(2 * R * MARL_H + kGiDepth * R * MARL_G) * sizeof(float); }
 
 __global__ void __launch_bounds__(kGruThreads * kGruGroups) gru_unroll_fwd_kernel(GruFwdArgs a) {
+    pdl_enter();
     extern __shared__ __align__(16) float gru_smem[];
     const int grp = threadIdx.x >> 7;
     const int chain = blockIdx.y * kGruGroups + grp;
@@ -382,6 +383,7 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
 constexpr size_t gru_bwd_smem_max() { return gru_bwd_smem(8) > gru_bwd_smem(4) ? gru_bwd_smem(8) : gru_bwd_smem(4); }
 
 __global__ void __launch_bounds__(kGruThreads) gru_unroll_bwd_kernel(GruBwdArgs a) {
+    pdl_enter();
     extern __shared__ __align__(16) float gru_smem[];
     int begin, count;
     cta_rows(a.B * a.N, 0, begin, count);
@@ -454,6 +456,7 @@ using namespace marl;
 extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_stream* s, int n_streams, void* stream) {
     if (check_dims(d) || !s || n_streams < 1 || n_streams > kMaxStreams) return MARL_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
+    pdl_scope((long long)d->B * d->L * d->N);
     const int rows_total = d->B * d->L * d->N;
     const int I = d->O + d->A + d->N;
     for (int i = 0; i < n_streams; ++i) {
@@ -514,7 +517,7 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         if ((rows + n_ctas - 1) / n_ctas + 2 > 65535) return MARL_EINVAL;
         plan_rows(ga, rows, n_ctas);
         dim3 grid(n_ctas, (ga.n_chains + kGruGroups - 1) / kGruGroups);
-        gru_unroll_fwd_kernel<<<grid, kGruThreads * kGruGroups, sm, st>>>(ga);
+        launch_pdl(gru_unroll_fwd_kernel, grid, dim3(kGruThreads * kGruGroups), sm, st, ga);
     }
     MARL_LAUNCH_CHECK();
     // phase C
@@ -537,6 +540,7 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
     if (check_dims(d) || !a || !a->hidden || !a->x || !a->gates || !a->dgi || !a->dgh || !a->dx) return MARL_EINVAL;
     if (a->dq && !a->dhext) return MARL_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
+    pdl_scope((long long)d->B * d->L * d->N);
     const int rows_total = d->B * d->L * d->N;
     const int I = d->O + d->A + d->N;
     int rc;
@@ -554,7 +558,7 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
         ProfScope ps_("gru_unroll_bwd_kernel", st);
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(gru_unroll_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gru_bwd_smem_max()); attr_set = true; }
-        gru_unroll_bwd_kernel<<<rows < kNumSMs ? rows : kNumSMs, kGruThreads, gru_bwd_smem_max(), st>>>(ga);
+        launch_pdl(gru_unroll_bwd_kernel, dim3(rows < kNumSMs ? rows : kNumSMs), dim3(kGruThreads), gru_bwd_smem_max(), st, ga);
     }
     MARL_LAUNCH_CHECK();
     // the four weight gradients and the dx chain are independent: fan them out

@@ -15,9 +15,46 @@
         if (e__ != cudaSuccess) return (int)e__;              \
     } while (0)
 
+#include <cstdlib>
+#include <utility>
+
 namespace marl {
 
 constexpr int kNumSMs = 148;
+
+// ---- programmatic dependent launch ------------------------------------------------------------------------
+// Kernels on the step's dependent chain start with pdl_enter(): wait until the grids they depend on have completed
+// and flushed (a no-op when launched normally), then let the NEXT kernel of the stream be scheduled early -- its CTAs
+// become resident and sit in their own pdl_enter() -- so that the ~2.5 us launch gap between two dependent kernels
+// of the captured graph is hidden.  (Kernels whose grids span several waves trigger late, pdl_wait() ... pdl_trigger(),
+// so that waiting dependents do not take SM residency from their own remaining CTAs.)  Nothing may touch global
+// memory before the wait, and every CTA must pass it
+// (even the ones that return early), otherwise completion of this grid would not imply completion of its predecessors.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// single-wave kernels: let the dependents become resident right away
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
+inline bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("MARL_B200_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+// Early residency of the next kernel only pays in the latency-bound regime (a few hundred CTAs per launch); with
+// many-wave grids the waiting CTAs take slots from the running kernel (measured: cfg 2 -4 %, cfg 3/4 +1.3..2.6 %).
+// The operator entry points set the regime from their problem size before they launch.
+inline bool& pdl_small_problem() { static bool v = true; return v; }
+inline void pdl_scope(long long rows) { pdl_small_problem() = rows <= 65536; }
+// <<<grid, block, smem, st>>> with the programmatic-stream-serialization attribute; only for kernels that call pdl_wait()
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (pdl_enabled() && pdl_small_problem()) ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -291,6 +291,7 @@ __device__ __forceinline__ void umma_epilogue(const UmmaCtx& c, int nsteps, F f)
 // y[M,N] (+)= act(in . w^T + bias)
 template <bool VEC_A, bool VEC_B>
 __global__ void __launch_bounds__(UT) linear_fwd_kernel(LinearFwd a) {
+    pdl_wait();
     extern __shared__ unsigned char umma_smem[];
     const int K = lin_width(a.in);
     const int nsteps = ((K + UK - 1) / UK) * (UK / 8);
@@ -302,6 +303,7 @@ __global__ void __launch_bounds__(UT) linear_fwd_kernel(LinearFwd a) {
     auto fb = [&](int n, int k) { return B.quad(n, k); };
     float unused[2][4];
     umma_loop<true, true, false>(c, fa, fb, m0, n0, 0, K, unused);
+    pdl_trigger();                       // main loop done: the next kernel's CTAs may take the freed slots
     const float* bias = a.bias ? a.bias + (long long)z * a.b_bs : nullptr;
     float* y = a.y + (long long)z * a.y_bs;
     const float bmul = a.bias_mul != 0.f ? a.bias_mul : 1.0f;
@@ -329,6 +331,7 @@ __global__ void __launch_bounds__(UT) linear_fwd_kernel(LinearFwd a) {
 // dx[M,K] (+)= (dy[M,N] . w[N, col0:col0+K]) * (relu_src > 0)
 template <bool VEC_A, bool VEC_B>
 __global__ void __launch_bounds__(UT) linear_dgrad_kernel(LinearDgrad a) {
+    pdl_wait();
     extern __shared__ unsigned char umma_smem[];
     const int nsteps = ((a.N + UK - 1) / UK) * (UK / 8);
     const UmmaCtx c = umma_setup(umma_smem, nsteps);
@@ -339,6 +342,7 @@ __global__ void __launch_bounds__(UT) linear_dgrad_kernel(LinearDgrad a) {
     auto fb = [&](int k, int n) { return B.quad(n, k); };
     float unused[2][4];
     umma_loop<true, false, false>(c, fa, fb, m0, k0, 0, a.N, unused);
+    pdl_trigger();                       // main loop done: the next kernel's CTAs may take the freed slots
     float* dx = a.dx + (long long)z * a.dx_bs;
     const float* rs = a.relu_src ? a.relu_src + (long long)z * a.rs_bs : nullptr;
     const bool vec_rs = rs && ((a.ldrs & 3) == 0) && ((reinterpret_cast<uintptr_t>(rs) & 15) == 0);
@@ -375,6 +379,7 @@ __global__ void __launch_bounds__(UT) linear_dgrad_kernel(LinearDgrad a) {
 // dw[N, 0:K] += dy^T . in ; db[N] += colsum(dy).  Split over the M rows (blockIdx.z), atomics on the output.
 template <bool VEC_A, bool VEC_B>
 __global__ void __launch_bounds__(UT) linear_wgrad_kernel(LinearWgrad a, int splits, int chunk) {
+    pdl_wait();
     extern __shared__ unsigned char umma_smem[];
     const int zb = blockIdx.z / splits, sp = blockIdx.z % splits;
     const int i0 = blockIdx.x * UM, j0 = blockIdx.y * UN;
@@ -390,6 +395,7 @@ __global__ void __launch_bounds__(UT) linear_wgrad_kernel(LinearWgrad a, int spl
     const bool want_bias = a.db != nullptr && blockIdx.y == 0;
     if (want_bias) umma_loop<false, false, true>(c, fa, fb, i0, j0, mbeg, mend, bsum);
     else umma_loop<false, false, false>(c, fa, fb, i0, j0, mbeg, mend, bsum);
+    pdl_trigger();                       // main loop done: the next kernel's CTAs may take the freed slots
     if (want_bias) {
         // the 16 reduction indices of a k-tile sit in 16 neighbouring lanes: fold them, lane r == 0 publishes
         const QuadMap<false, UM, 2> ma;
@@ -445,10 +451,10 @@ static bool vec_ok_mat(const float* p, int ld, long long bs, int col0 = 0) {
             cudaFuncSetAttribute(KERNEL<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem); \
             attr_done = true;                                                                              \
         }                                                                                                  \
-        if (VA && VB) KERNEL<true, true><<<GRID, UT, kUmmaSmem, ST>>>(__VA_ARGS__);                        \
-        else if (VA) KERNEL<true, false><<<GRID, UT, kUmmaSmem, ST>>>(__VA_ARGS__);                        \
-        else if (VB) KERNEL<false, true><<<GRID, UT, kUmmaSmem, ST>>>(__VA_ARGS__);                        \
-        else KERNEL<false, false><<<GRID, UT, kUmmaSmem, ST>>>(__VA_ARGS__);                               \
+        if (VA && VB) launch_pdl(KERNEL<true, true>, GRID, dim3(UT), kUmmaSmem, ST, __VA_ARGS__);               \
+        else if (VA) launch_pdl(KERNEL<true, false>, GRID, dim3(UT), kUmmaSmem, ST, __VA_ARGS__);               \
+        else if (VB) launch_pdl(KERNEL<false, true>, GRID, dim3(UT), kUmmaSmem, ST, __VA_ARGS__);               \
+        else launch_pdl(KERNEL<false, false>, GRID, dim3(UT), kUmmaSmem, ST, __VA_ARGS__);                      \
     } while (0)
 
 int linear_fwd(const LinearFwd& a, cudaStream_t st) {

@@ -150,6 +150,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
 clip_step_cluster_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m1, float* __restrict__ m2, long long n,
                          const float* __restrict__ scalars, float max_norm, float lr, float c1, float c2, float eps, int step,
                          int* step_counter, float* loss_out) {
+    pdl_enter();
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ float sw[kClusterThreads / 32];
@@ -254,8 +255,8 @@ extern "C" int marl_clip_rmsprop_step(float* params, float* grads, float* square
     }
     if (n <= kClusterMax && aligned16(params) && aligned16(grads) && aligned16(square_avg)) {
         { ProfScope ps_("clip_step_cluster_kernel", st);
-          clip_step_cluster_kernel<false><<<kClusterCtas, kClusterThreads, 0, st>>>(params, grads, square_avg, nullptr, n, scalars,
-                                                                                     max_norm, lr, alpha, 0.f, eps, 0, nullptr, loss_out); }
+          launch_pdl(clip_step_cluster_kernel<false>, dim3(kClusterCtas), dim3(kClusterThreads), 0, st, params, grads, square_avg,
+                     (float*)nullptr, n, scalars, max_norm, lr, alpha, 0.f, eps, 0, (int*)nullptr, loss_out); }
         MARL_LAUNCH_CHECK();
         return MARL_OK;
     }
@@ -282,8 +283,8 @@ extern "C" int marl_clip_adam_step(float* params, float* grads, float* exp_avg, 
     }
     if (n <= kClusterMax && aligned16(params) && aligned16(grads) && aligned16(exp_avg) && aligned16(exp_avg_sq)) {
         { ProfScope ps_("clip_step_cluster_kernel", st);
-          clip_step_cluster_kernel<true><<<kClusterCtas, kClusterThreads, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, scalars,
-                                                                                    max_norm, lr, beta1, beta2, eps, step, step_counter, loss_out); }
+          launch_pdl(clip_step_cluster_kernel<true>, dim3(kClusterCtas), dim3(kClusterThreads), 0, st, params, grads, exp_avg, exp_avg_sq,
+                     n, scalars, max_norm, lr, beta1, beta2, eps, step, step_counter, loss_out); }
         MARL_LAUNCH_CHECK();
         return MARL_OK;
     }

@@ -48,6 +48,7 @@ __device__ __forceinline__ float qmix_forward_lane(const float* __restrict__ y, 
 }
 
 __global__ void __launch_bounds__(kQmixWarps * 32) qmix_mix_kernel(QmixMixArgs a) {
+    pdl_enter();
     __shared__ float sdq[kQmixWarps][kQmixMaxAgents];
     __shared__ float sred[kQmixWarps][E + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -220,7 +221,7 @@ extern "C" int marl_qmix_fwd(int M, int N, int S, const marl_qmix_params* p, con
     if (rc) return rc;
     QmixMixArgs a{};
     a.M = M; a.N = N; a.mode = QMIX_FWD; a.hy = hy; a.q = q; a.wb2 = p->wb2; a.bb2 = p->bb2; a.q_tot = q_tot;
-    { ProfScope ps_("qmix_mix_kernel", st); qmix_mix_kernel<<<mix_grid(M), kQmixWarps * 32, 0, st>>>(a); }
+    { ProfScope ps_("qmix_mix_kernel", st); launch_pdl(qmix_mix_kernel, dim3(mix_grid(M)), dim3(kQmixWarps * 32), 0, st, a); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
@@ -235,7 +236,7 @@ extern "C" int marl_qmix_bwd(int M, int N, int S, const marl_qmix_params* p, con
     QmixMixArgs a{};
     a.M = M; a.N = N; a.mode = QMIX_BWD; a.hy = hy; a.q = q; a.wb2 = p->wb2; a.bb2 = p->bb2;
     a.dq_tot_in = dq_tot; a.dhy = dhy; a.dq_small = dq; a.g_wb2 = g->wb2; a.g_bb2 = g->bb2;
-    { ProfScope ps_("qmix_mix_kernel", st); qmix_mix_kernel<<<mix_grid(M), kQmixWarps * 32, 0, st>>>(a); }
+    { ProfScope ps_("qmix_mix_kernel", st); launch_pdl(qmix_mix_kernel, dim3(mix_grid(M)), dim3(kQmixWarps * 32), 0, st, a); }
     MARL_LAUNCH_CHECK();
     return hyper_wgrad(M, N, S, s, dhy, g, st);
 }
@@ -255,6 +256,7 @@ extern "C" int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* 
     const int M = d->B * d->L;
     if (M <= 0) return MARL_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    pdl_scope((long long)M * d->N);
     int rc;
     if (!(flags & 1)) {
         ForkJoin fj(st, 2);      // eval and target hyper-networks side by side
@@ -269,7 +271,7 @@ extern "C" int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* 
     a.r = r; a.term = terminated; a.padded = padded; a.gamma = gamma;
     a.q_tot = q_tot; a.q_tot_t = q_tot_target; a.dhy = dhy; a.u = u; a.dq_dense = dq;
     a.g_wb2 = g->wb2; a.g_bb2 = g->bb2; a.scalars = scalars;
-    { ProfScope ps_("qmix_mix_kernel", st); qmix_mix_kernel<<<mix_grid(M), kQmixWarps * 32, 0, st>>>(a); }
+    { ProfScope ps_("qmix_mix_kernel", st); launch_pdl(qmix_mix_kernel, dim3(mix_grid(M)), dim3(kQmixWarps * 32), 0, st, a); }
     MARL_LAUNCH_CHECK();
     if (flags & 2) return MARL_OK;
     return hyper_wgrad(M, d->N, d->S, s, dhy, g, st);
@@ -282,7 +284,7 @@ extern "C" int marl_qmix_mix_fwd(int M, int N, const marl_qmix_params* p, const 
     cudaStream_t st = (cudaStream_t)stream;
     QmixMixArgs a{};
     a.M = M; a.N = N; a.mode = QMIX_FWD; a.hy = hy; a.q = q; a.wb2 = p->wb2; a.bb2 = p->bb2; a.q_tot = q_tot;
-    { ProfScope ps_("qmix_mix_kernel", st); qmix_mix_kernel<<<mix_grid(M), kQmixWarps * 32, 0, st>>>(a); }
+    { ProfScope ps_("qmix_mix_kernel", st); launch_pdl(qmix_mix_kernel, dim3(mix_grid(M)), dim3(kQmixWarps * 32), 0, st, a); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
@@ -295,7 +297,7 @@ extern "C" int marl_qmix_mix_bwd(int M, int N, const marl_qmix_params* p, const 
     QmixMixArgs a{};
     a.M = M; a.N = N; a.mode = QMIX_BWD; a.hy = hy; a.q = q; a.wb2 = p->wb2; a.bb2 = p->bb2;
     a.dq_tot_in = dq_tot; a.dhy = dhy; a.dq_small = dq; a.g_wb2 = g->wb2; a.g_bb2 = g->bb2;
-    { ProfScope ps_("qmix_mix_kernel", st); qmix_mix_kernel<<<mix_grid(M), kQmixWarps * 32, 0, st>>>(a); }
+    { ProfScope ps_("qmix_mix_kernel", st); launch_pdl(qmix_mix_kernel, dim3(mix_grid(M)), dim3(kQmixWarps * 32), 0, st, a); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
@@ -324,6 +326,7 @@ extern "C" int marl_qmix_hyper2_bwd(int M, int N, int S, const marl_qmix_hyper2*
 extern "C" int marl_qmix_hyper_fwd(int M, int N, int S, const marl_qmix_params* p, const float* s, float* hy, void* stream) {
     if (M < 0 || N < 1 || N > kQmixMaxAgents || S < 1 || !qmix_params_ok(p) || !s || !hy) return MARL_EINVAL;
     if (M == 0) return MARL_OK;
+    pdl_scope((long long)M * N);
     return hyper_fwd(M, N, S, p, s, hy, (cudaStream_t)stream);
 }
 
@@ -331,5 +334,6 @@ extern "C" int marl_qmix_hyper_wgrad(int M, int N, int S, const float* s, const 
                                      void* stream) {
     if (M < 0 || N < 1 || N > kQmixMaxAgents || S < 1 || !s || !dhy || !g || !g->wcat || !g->bcat) return MARL_EINVAL;
     if (M == 0) return MARL_OK;
+    pdl_scope((long long)M * N);
     return hyper_wgrad(M, N, S, s, dhy, g, (cudaStream_t)stream);
 }

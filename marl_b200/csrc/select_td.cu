@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(256) q_select_kernel(
     const float* __restrict__ avail_next, const float* __restrict__ avail,
     float* __restrict__ q_chosen, long long* __restrict__ a_star, float* __restrict__ q_tc,
     float* __restrict__ max_q_evals, float* __restrict__ q_targets_max, float* __restrict__ a_star_onehot) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
     const long long o = (long long)i * A;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(256) vdn_td_kernel(int M, int N, int A, const 
                                                      const long long* u, const float* r, const float* term,
                                                      const float* padded, float gamma, float* q_tot, float* q_tot_t,
                                                      float* dq, float* scalars) {
+    pdl_enter();
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     float sq = 0.f, msk = 0.f;
     if (m < M) {
@@ -181,7 +183,8 @@ extern "C" int marl_q_select(const marl_dims* d, const float* q_evals, const lon
     if (max_q_evals && (!avail_u || !q_evals)) return MARL_EINVAL;
     const int rows = d->B * d->L * d->N;
     if (rows <= 0) return MARL_OK;
-    { ProfScope ps_("q_select_kernel", (cudaStream_t)stream); q_select_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, d->A, q_evals, u, q_evals_next, q_targets,
+    pdl_scope(rows);
+    { ProfScope ps_("q_select_kernel", (cudaStream_t)stream); launch_pdl(q_select_kernel, dim3((rows + 255) / 256), dim3(256), 0, (cudaStream_t)stream, rows, d->A, q_evals, u, q_evals_next, q_targets,
         avail_u_next, avail_u, q_chosen, a_star, q_targets_chosen, max_q_evals, q_targets_max, a_star_onehot); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
@@ -215,7 +218,8 @@ extern "C" int marl_vdn_td_fwd_bwd(const marl_dims* d, const float* q_chosen, co
     if (dq && !u) return MARL_EINVAL;
     const int M = d->B * d->L;
     if (M <= 0) return MARL_OK;
-    { ProfScope ps_("vdn_td_kernel", (cudaStream_t)stream); vdn_td_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(M, d->N, d->A, q_chosen, q_targets_chosen, u, r,
+    pdl_scope((long long)M * d->N);
+    { ProfScope ps_("vdn_td_kernel", (cudaStream_t)stream); launch_pdl(vdn_td_kernel, dim3((M + 255) / 256), dim3(256), 0, (cudaStream_t)stream, M, d->N, d->A, q_chosen, q_targets_chosen, u, r,
         terminated, padded, gamma, q_tot, q_tot_target, dq, scalars); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
