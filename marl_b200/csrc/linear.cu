@@ -291,11 +291,11 @@ __device__ __forceinline__ void umma_epilogue(const UmmaCtx& c, int nsteps, F f)
 // y[M,N] (+)= act(in . w^T + bias)
 template <bool VEC_A, bool VEC_B>
 __global__ void __launch_bounds__(UT) linear_fwd_kernel(LinearFwd a) {
-    pdl_wait();
     extern __shared__ unsigned char umma_smem[];
     const int K = lin_width(a.in);
     const int nsteps = ((K + UK - 1) / UK) * (UK / 8);
-    const UmmaCtx c = umma_setup(umma_smem, nsteps);
+    const UmmaCtx c = umma_setup(umma_smem, nsteps);       // barriers + TMEM: no global memory, overlaps the predecessor's tail
+    pdl_wait();
     const int z = blockIdx.z, m0 = blockIdx.x * UM, n0 = blockIdx.y * UN;
     const OpLin A{a.in, z, a.M, K, VEC_A, VEC_A && vec2_ok(a.in)};               // rows m, reduction k (contiguous)
     const OpMat B{a.w + (long long)z * a.w_bs, a.ldw, a.N, K, VEC_B};             // rows n, reduction k (contiguous)
@@ -331,10 +331,10 @@ __global__ void __launch_bounds__(UT) linear_fwd_kernel(LinearFwd a) {
 // dx[M,K] (+)= (dy[M,N] . w[N, col0:col0+K]) * (relu_src > 0)
 template <bool VEC_A, bool VEC_B>
 __global__ void __launch_bounds__(UT) linear_dgrad_kernel(LinearDgrad a) {
-    pdl_wait();
     extern __shared__ unsigned char umma_smem[];
     const int nsteps = ((a.N + UK - 1) / UK) * (UK / 8);
-    const UmmaCtx c = umma_setup(umma_smem, nsteps);
+    const UmmaCtx c = umma_setup(umma_smem, nsteps);       // barriers + TMEM: no global memory, overlaps the predecessor's tail
+    pdl_wait();
     const int z = blockIdx.z, m0 = blockIdx.x * UM, k0 = blockIdx.y * UN;
     const OpMat A{a.dy + (long long)z * a.dy_bs, a.lddy, a.M, a.N, VEC_A};               // rows m, reduction n (contiguous)
     const OpMat B{a.w + (long long)z * a.w_bs + a.w_col0, a.ldw, a.N, a.K, VEC_B};       // rows n (reduction), cols k (contiguous)
@@ -379,14 +379,14 @@ __global__ void __launch_bounds__(UT) linear_dgrad_kernel(LinearDgrad a) {
 // dw[N, 0:K] += dy^T . in ; db[N] += colsum(dy).  Split over the M rows (blockIdx.z), atomics on the output.
 template <bool VEC_A, bool VEC_B>
 __global__ void __launch_bounds__(UT) linear_wgrad_kernel(LinearWgrad a, int splits, int chunk) {
-    pdl_wait();
     extern __shared__ unsigned char umma_smem[];
     const int zb = blockIdx.z / splits, sp = blockIdx.z % splits;
     const int i0 = blockIdx.x * UM, j0 = blockIdx.y * UN;
     const int K = lin_width(a.in);
     const int mbeg = sp * chunk, mend = min(a.M, mbeg + chunk);
     const int nsteps = mend > mbeg ? ((mend - mbeg + UK - 1) / UK) * (UK / 8) : 0;
-    const UmmaCtx c = umma_setup(umma_smem, nsteps);
+    const UmmaCtx c = umma_setup(umma_smem, nsteps);       // barriers + TMEM: no global memory, overlaps the predecessor's tail
+    pdl_wait();
     const OpMat A{a.dy + (long long)zb * a.dy_bs, a.lddy, a.M, a.N, VEC_A};      // rows m (reduction), cols n
     const OpLin B{a.in, zb, a.M, K, VEC_B, VEC_B && vec2_ok(a.in)};             // rows m (reduction), cols k
     auto fa = [&](int n, int m) { return A.quad(m, n); };
