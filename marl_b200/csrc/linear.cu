@@ -17,7 +17,8 @@
 
 namespace marl {
 
-constexpr int UM = 128, UN = 64, UK = 16, UT = 256;   // CTA tile (UMMA M, N), k-tile, threads
+constexpr int UM = 128, UN = 64, UK = 16, UT = 256;   // CTA tile (UMMA M, N), k-tile, producer / epilogue threads
+constexpr int UTH = UT + 32;                          // + one warp whose lane 0 issues the MMAs
 constexpr int kKChunks = UK / 4;                       // 16-byte k-chunks per k-tile
 // Canonical K-major layout: element (row, k) at float offset (k/4)*PITCH + row*4 + k%4, i.e. 8 rows x 16 B
 // core matrices, SBO = 128 B between 8-row groups, LBO = PITCH*4 B between k-chunks.  PITCH = ROWS*4 + 8
@@ -220,6 +221,32 @@ __device__ __forceinline__ void umma_loop(const UmmaCtx& c, FA fa, FB fb, int i0
         for (int l = 0; l < 2; ++l) ra[set][l] = (kt < nk && r0 + ma.r[l] < rend) ? fa(i0 + ma.i[l], r0 + ma.r[l]) : zero4;
         rb[set] = (kt < nk && r0 + mb.r[0] < rend) ? fb(j0 + mb.i[0], r0 + mb.r[0]) : zero4;
     };
+    if (threadIdx.x >= UT) {
+        // ---- MMA warp.  A clock64 trace of the single-role version showed the issuing thread busy for 700-900 cycles
+        // per k-tile (six tcgen05.mma + descriptors) while the other 255 threads waited for it at the next barrier;
+        // here the producers only ARRIVE on a named barrier and go on fetching, this warp SYNCs on it and issues.
+        for (int kt = 0; kt < nk; ++kt) {
+            const int s = kt & 1;
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "n"(UTH) : "memory");      // stage s written and proxy-fenced by all producers
+            if (threadIdx.x == UT) {
+                UmmaStage& st = c.stages[s];
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k8 = 0; k8 < UK / 8; ++k8) {
+                    const uint32_t ao = (uint32_t)(2 * k8) * A_PITCH * 4, bo = (uint32_t)(2 * k8) * B_PITCH * 4;
+                    const uint64_t dah = umma_desc(smem_u32(st.a_hi) + ao, A_PITCH * 4, 128), dal = umma_desc(smem_u32(st.a_lo) + ao, A_PITCH * 4, 128);
+                    const uint64_t dbh = umma_desc(smem_u32(st.b_hi) + bo, B_PITCH * 4, 128), dbl = umma_desc(smem_u32(st.b_lo) + bo, B_PITCH * 4, 128);
+                    const int step = kt * (UK / 8) + k8;                       // global k8 index of this CTA
+                    umma_tf32(c.tmem + nmain * UN, dal, dbh, step ? 1u : 0u);      // corrections
+                    umma_tf32(c.tmem + nmain * UN, dah, dbl, 1u);
+                    umma_tf32(c.tmem + (step % nmain) * UN, dah, dbh, step >= nmain ? 1u : 0u);
+                }
+                umma_commit(&c.bars[s]);
+            }
+            __syncwarp();
+        }
+        return;
+    }
     fetch(0, 0);
     fetch(1, 1);
     for (int kt = 0; kt < nk; ++kt) {
@@ -235,21 +262,7 @@ __device__ __forceinline__ void umma_loop(const UmmaCtx& c, FA fa, FB fb, int i0
         QuadMap<B_RED, UN, 1>::store(st.b_hi, st.b_lo, B_PITCH, mb.i[0], mb.r[0], s ? rb[1] : rb[0]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int k8 = 0; k8 < UK / 8; ++k8) {
-                const uint32_t ao = (uint32_t)(2 * k8) * A_PITCH * 4, bo = (uint32_t)(2 * k8) * B_PITCH * 4;
-                const uint64_t dah = umma_desc(smem_u32(st.a_hi) + ao, A_PITCH * 4, 128), dal = umma_desc(smem_u32(st.a_lo) + ao, A_PITCH * 4, 128);
-                const uint64_t dbh = umma_desc(smem_u32(st.b_hi) + bo, B_PITCH * 4, 128), dbl = umma_desc(smem_u32(st.b_lo) + bo, B_PITCH * 4, 128);
-                const int step = kt * (UK / 8) + k8;                       // global k8 index of this CTA
-                umma_tf32(c.tmem + nmain * UN, dal, dbh, step ? 1u : 0u);      // corrections
-                umma_tf32(c.tmem + nmain * UN, dah, dbl, 1u);
-                umma_tf32(c.tmem + (step % nmain) * UN, dah, dbh, step >= nmain ? 1u : 0u);
-            }
-            umma_commit(&c.bars[s]);
-        }
+        asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "n"(UTH) : "memory");   // hand the stage to the MMA warp, do not wait for it
         if (s) fetch(kt + 2, 1); else fetch(kt + 2, 0);       // refill the register set just consumed
     }
     // all MMAs done: the last commit of each stage covers everything issued before it
@@ -262,6 +275,7 @@ __device__ __forceinline__ void umma_loop(const UmmaCtx& c, FA fa, FB fb, int i0
 // f(row_in_tile, col_in_tile, v[4]) is called for each group of 4 consecutive columns.
 template <class F>
 __device__ __forceinline__ void umma_epilogue(const UmmaCtx& c, int nsteps, F f) {
+    if (threadIdx.x >= UT) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = (warp & 3) * 32 + lane, c0 = (warp >> 2) * 32;
     const int nmain = acc_main_count(nsteps);
@@ -290,7 +304,7 @@ __device__ __forceinline__ void umma_epilogue(const UmmaCtx& c, int nsteps, F f)
 
 // y[M,N] (+)= act(in . w^T + bias)
 template <bool VEC_A, bool VEC_B>
-__global__ void __launch_bounds__(UT) linear_fwd_kernel(LinearFwd a) {
+__global__ void __launch_bounds__(UTH) linear_fwd_kernel(LinearFwd a) {
     extern __shared__ unsigned char umma_smem[];
     const int K = lin_width(a.in);
     const int nsteps = ((K + UK - 1) / UK) * (UK / 8);
@@ -330,7 +344,7 @@ __global__ void __launch_bounds__(UT) linear_fwd_kernel(LinearFwd a) {
 
 // dx[M,K] (+)= (dy[M,N] . w[N, col0:col0+K]) * (relu_src > 0)
 template <bool VEC_A, bool VEC_B>
-__global__ void __launch_bounds__(UT) linear_dgrad_kernel(LinearDgrad a) {
+__global__ void __launch_bounds__(UTH) linear_dgrad_kernel(LinearDgrad a) {
     extern __shared__ unsigned char umma_smem[];
     const int nsteps = ((a.N + UK - 1) / UK) * (UK / 8);
     const UmmaCtx c = umma_setup(umma_smem, nsteps);       // barriers + TMEM: no global memory, overlaps the predecessor's tail
@@ -378,7 +392,7 @@ __global__ void __launch_bounds__(UT) linear_dgrad_kernel(LinearDgrad a) {
 
 // dw[N, 0:K] += dy^T . in ; db[N] += colsum(dy).  Split over the M rows (blockIdx.z), atomics on the output.
 template <bool VEC_A, bool VEC_B>
-__global__ void __launch_bounds__(UT) linear_wgrad_kernel(LinearWgrad a, int splits, int chunk) {
+__global__ void __launch_bounds__(UTH) linear_wgrad_kernel(LinearWgrad a, int splits, int chunk) {
     extern __shared__ unsigned char umma_smem[];
     const int zb = blockIdx.z / splits, sp = blockIdx.z % splits;
     const int i0 = blockIdx.x * UM, j0 = blockIdx.y * UN;
@@ -396,7 +410,7 @@ __global__ void __launch_bounds__(UT) linear_wgrad_kernel(LinearWgrad a, int spl
     if (want_bias) umma_loop<false, false, true>(c, fa, fb, i0, j0, mbeg, mend, bsum);
     else umma_loop<false, false, false>(c, fa, fb, i0, j0, mbeg, mend, bsum);
     pdl_trigger();                       // main loop done: the next kernel's CTAs may take the freed slots
-    if (want_bias) {
+    if (want_bias && threadIdx.x < UT) {
         // the 16 reduction indices of a k-tile sit in 16 neighbouring lanes: fold them, lane r == 0 publishes
         const QuadMap<false, UM, 2> ma;
         const float bmul = a.db_mul != 0.f ? a.db_mul : 1.0f;
@@ -451,10 +465,10 @@ static bool vec_ok_mat(const float* p, int ld, long long bs, int col0 = 0) {
             cudaFuncSetAttribute(KERNEL<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem); \
             attr_done = true;                                                                              \
         }                                                                                                  \
-        if (VA && VB) launch_pdl(KERNEL<true, true>, GRID, dim3(UT), kUmmaSmem, ST, __VA_ARGS__);               \
-        else if (VA) launch_pdl(KERNEL<true, false>, GRID, dim3(UT), kUmmaSmem, ST, __VA_ARGS__);               \
-        else if (VB) launch_pdl(KERNEL<false, true>, GRID, dim3(UT), kUmmaSmem, ST, __VA_ARGS__);               \
-        else launch_pdl(KERNEL<false, false>, GRID, dim3(UT), kUmmaSmem, ST, __VA_ARGS__);                      \
+        if (VA && VB) launch_pdl(KERNEL<true, true>, GRID, dim3(UTH), kUmmaSmem, ST, __VA_ARGS__);               \
+        else if (VA) launch_pdl(KERNEL<true, false>, GRID, dim3(UTH), kUmmaSmem, ST, __VA_ARGS__);               \
+        else if (VB) launch_pdl(KERNEL<false, true>, GRID, dim3(UTH), kUmmaSmem, ST, __VA_ARGS__);               \
+        else launch_pdl(KERNEL<false, false>, GRID, dim3(UTH), kUmmaSmem, ST, __VA_ARGS__);                      \
     } while (0)
 
 int linear_fwd(const LinearFwd& a, cudaStream_t st) {
