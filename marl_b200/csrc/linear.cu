@@ -48,6 +48,35 @@ constexpr size_t kUmmaSmem = kUmmaStages * sizeof(UmmaStage) + 128;
 // Operand described by a LinOperand: logical matrix [rows, width], contiguous along the column index.
 struct OpLin {
     LinOperand o; int z; int rows; int width; bool vec; bool vec2;
+    // everything that depends on the row only (pointers into the two sources, the one-hot column): computed once per
+    // thread when the row is fixed for the whole k-loop -- the per-tile fetch is then a range test and a load
+    struct Row { const float* xr; const float* x2r; int hot; bool valid; };
+    __device__ __forceinline__ Row row(int i) const {
+        Row rw{nullptr, nullptr, -1, i < rows};
+        if (!rw.valid) return rw;
+        if (o.x) rw.xr = o.x + (long long)z * o.x_bs + (long long)i * o.ldx;
+        if (o.K2 > 0 && !(o.x2_shift && (i % o.x2_period) < o.x2_shift))
+            rw.x2r = o.x2 + (long long)z * o.x2_bs + (long long)(i - o.x2_shift) * o.ldx2 - o.K1;
+        if (o.onehot_mod) rw.hot = o.K1 + o.K2 + (i % o.onehot_mod);
+        return rw;
+    }
+    __device__ __forceinline__ float4 quad_at(const Row& rw, int r) const {   // elements (row, r..r+3)
+        if (!rw.valid) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec && r + 3 < o.K1) return __ldg(reinterpret_cast<const float4*>(rw.xr + r));
+        if (vec2 && r >= o.K1 && r + 3 < o.K1 + o.K2)
+            return rw.x2r ? __ldg(reinterpret_cast<const float4*>(rw.x2r + r)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float e[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int k = r + c;
+            float val = 0.f;
+            if (k < o.K1) val = __ldg(rw.xr + k);
+            else if (k < o.K1 + o.K2) { if (rw.x2r) val = __ldg(rw.x2r + k); }
+            else if (k == rw.hot) val = 1.0f;
+            e[c] = val;
+        }
+        return make_float4(e[0], e[1], e[2], e[3]);
+    }
     __device__ __forceinline__ float4 quad(int i, int r) const {   // elements (i, r..r+3)
         if (i >= rows) return make_float4(0.f, 0.f, 0.f, 0.f);
         if (vec && r + 3 < o.K1)
@@ -82,6 +111,19 @@ struct OpLin {
 // Plain row-major matrix P[rows, cols] (ld), fetched along its contiguous (column) dimension.
 struct OpMat {
     const float* p; int ld; int rows; int cols; bool vec;
+    struct Row { const float* q; };      // row pointer (null beyond the matrix): hoisted out of the k-loop when the row is fixed
+    __device__ __forceinline__ Row row(int r) const { return Row{r < rows ? p + (long long)r * ld : nullptr}; }
+    __device__ __forceinline__ float4 quad_at(const Row& rw, int col) const {
+        if (!rw.q) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* q = rw.q + col;
+        if (vec && col + 3 < cols) return __ldg(reinterpret_cast<const float4*>(q));
+        float4 v;
+        v.x = col + 0 < cols ? __ldg(q + 0) : 0.f;
+        v.y = col + 1 < cols ? __ldg(q + 1) : 0.f;
+        v.z = col + 2 < cols ? __ldg(q + 2) : 0.f;
+        v.w = col + 3 < cols ? __ldg(q + 3) : 0.f;
+        return v;
+    }
     __device__ __forceinline__ float4 quad(int row, int col) const {   // elements (row, col..col+3)
         if (row >= rows) return make_float4(0.f, 0.f, 0.f, 0.f);
         const float* q = p + (long long)row * ld + col;
@@ -207,19 +249,30 @@ __device__ __forceinline__ void umma_teardown(const UmmaCtx& c, int nsteps) {
 // Main loop over the reduction range [rbeg, rend): global -> registers (two k-tiles ahead) -> shared (hi, lo)
 // -> tcgen05.mma.  FA(i, r) / FB(j, r) return the operand quad as a float4.  BIAS (weight gradient only)
 // also accumulates the column sums of the A operand into bsum.
-template <bool A_RED, bool B_RED, bool BIAS, class FA, class FB>
-__device__ __forceinline__ void umma_loop(const UmmaCtx& c, FA fa, FB fb, int i0, int j0, int rbeg, int rend, float (&bsum)[2][4]) {
+template <bool A_RED, bool B_RED, bool BIAS, class OA, class OB>
+__device__ __forceinline__ void umma_loop(const UmmaCtx& c, const OA& A, const OB& B, int i0, int j0, int rbeg, int rend, float (&bsum)[2][4]) {
     const QuadMap<A_RED, UM, 2> ma;
     const QuadMap<B_RED, UN, 1> mb;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int nk = (rend - rbeg + UK - 1) / UK;
     const int nmain = acc_main_count(nk * (UK / 8));
     float4 ra[2][2], rb[2];            // two register sets: tiles kt and kt+1 in flight
+    // RED operands (operand row = tile row, contiguous along the reduction): row context hoisted out of the loop;
+    // otherwise the operand row IS the reduction index and changes with every tile
+    typename OA::Row arow[2]; typename OB::Row brow;
+    if (threadIdx.x < UT) {
+        if (A_RED) { arow[0] = A.row(i0 + ma.i[0]); arow[1] = A.row(i0 + ma.i[1]); }
+        if (B_RED) brow = B.row(j0 + mb.i[0]);
+    }
     auto fetch = [&](int kt, int set) {
         const int r0 = rbeg + kt * UK;
 #pragma unroll
-        for (int l = 0; l < 2; ++l) ra[set][l] = (kt < nk && r0 + ma.r[l] < rend) ? fa(i0 + ma.i[l], r0 + ma.r[l]) : zero4;
-        rb[set] = (kt < nk && r0 + mb.r[0] < rend) ? fb(j0 + mb.i[0], r0 + mb.r[0]) : zero4;
+        for (int l = 0; l < 2; ++l) {
+            const int r = r0 + ma.r[l];
+            ra[set][l] = (kt < nk && r < rend) ? (A_RED ? A.quad_at(arow[l], r) : A.quad(r, i0 + ma.i[l])) : zero4;
+        }
+        const int r = r0 + mb.r[0];
+        rb[set] = (kt < nk && r < rend) ? (B_RED ? B.quad_at(brow, r) : B.quad(r, j0 + mb.i[0])) : zero4;
     };
     if (threadIdx.x >= UT) {
         // ---- MMA warp.  A clock64 trace of the single-role version showed the issuing thread busy for 700-900 cycles
@@ -313,10 +366,8 @@ __global__ void __launch_bounds__(UTH) linear_fwd_kernel(LinearFwd a) {
     const int z = blockIdx.z, m0 = blockIdx.x * UM, n0 = blockIdx.y * UN;
     const OpLin A{a.in, z, a.M, K, VEC_A, VEC_A && vec2_ok(a.in)};               // rows m, reduction k (contiguous)
     const OpMat B{a.w + (long long)z * a.w_bs, a.ldw, a.N, K, VEC_B};             // rows n, reduction k (contiguous)
-    auto fa = [&](int m, int k) { return A.quad(m, k); };
-    auto fb = [&](int n, int k) { return B.quad(n, k); };
     float unused[2][4];
-    umma_loop<true, true, false>(c, fa, fb, m0, n0, 0, K, unused);
+    umma_loop<true, true, false>(c, A, B, m0, n0, 0, K, unused);
     pdl_trigger();                       // main loop done: the next kernel's CTAs may take the freed slots
     const float* bias = a.bias ? a.bias + (long long)z * a.b_bs : nullptr;
     float* y = a.y + (long long)z * a.y_bs;
@@ -352,10 +403,8 @@ __global__ void __launch_bounds__(UTH) linear_dgrad_kernel(LinearDgrad a) {
     const int z = blockIdx.z, m0 = blockIdx.x * UM, k0 = blockIdx.y * UN;
     const OpMat A{a.dy + (long long)z * a.dy_bs, a.lddy, a.M, a.N, VEC_A};               // rows m, reduction n (contiguous)
     const OpMat B{a.w + (long long)z * a.w_bs + a.w_col0, a.ldw, a.N, a.K, VEC_B};       // rows n (reduction), cols k (contiguous)
-    auto fa = [&](int m, int n) { return A.quad(m, n); };
-    auto fb = [&](int k, int n) { return B.quad(n, k); };
     float unused[2][4];
-    umma_loop<true, false, false>(c, fa, fb, m0, k0, 0, a.N, unused);
+    umma_loop<true, false, false>(c, A, B, m0, k0, 0, a.N, unused);
     pdl_trigger();                       // main loop done: the next kernel's CTAs may take the freed slots
     float* dx = a.dx + (long long)z * a.dx_bs;
     const float* rs = a.relu_src ? a.relu_src + (long long)z * a.rs_bs : nullptr;
@@ -403,12 +452,10 @@ __global__ void __launch_bounds__(UTH) linear_wgrad_kernel(LinearWgrad a, int sp
     pdl_wait();
     const OpMat A{a.dy + (long long)zb * a.dy_bs, a.lddy, a.M, a.N, VEC_A};      // rows m (reduction), cols n
     const OpLin B{a.in, zb, a.M, K, VEC_B, VEC_B && vec2_ok(a.in)};             // rows m (reduction), cols k
-    auto fa = [&](int n, int m) { return A.quad(m, n); };
-    auto fb = [&](int k, int m) { return B.quad(m, k); };
     float bsum[2][4] = {};
     const bool want_bias = a.db != nullptr && blockIdx.y == 0;
-    if (want_bias) umma_loop<false, false, true>(c, fa, fb, i0, j0, mbeg, mend, bsum);
-    else umma_loop<false, false, false>(c, fa, fb, i0, j0, mbeg, mend, bsum);
+    if (want_bias) umma_loop<false, false, true>(c, A, B, i0, j0, mbeg, mend, bsum);
+    else umma_loop<false, false, false>(c, A, B, i0, j0, mbeg, mend, bsum);
     pdl_trigger();                       // main loop done: the next kernel's CTAs may take the freed slots
     if (want_bias && threadIdx.x < UT) {
         // the 16 reduction indices of a k-tile sit in 16 neighbouring lanes: fold them, lane r == 0 publishes

@@ -12,10 +12,10 @@ for _ in range(5):
 torch.cuda.synchronize()
 lib = L.load(); lib.marl_gemm_trace.argtypes = [C.c_void_p]; lib.marl_gemm_trace.restype = C.c_int
 buf = (C.c_longlong * 128)(); lib.marl_gemm_trace(C.cast(buf, C.c_void_p))
-t = list(buf); t0 = t[0]
-print("entry 0 | setup+wait", t[1]-t0, "| before fetch", t[5]-t0, "| after fetch issue", t[6]-t0, "| epilogue done", t[3]-t0, "| teardown", t[4]-t0)
+t = list(buf); t0 = t[8]
 for kt in range(8):
-    b = 8 + 6*kt
+    b = 8 + 4*kt
     if not t[b]: break
-    r = [x - t0 for x in t[b:b+6]]
-    print(f"kt {kt}: top {r[0]:6d} stage-free +{r[1]-r[0]:5d} split+store +{r[2]-r[1]:5d} fence +{r[3]-r[2]:5d} sync +{r[4]-r[3]:5d} mma-issue +{r[5]-r[4]:5d}")
+    r = [x - t0 for x in t[b:b+4]]
+    m = [t[64+2*kt]-t0, t[65+2*kt]-t0]
+    print(f"kt {kt}: top {r[0]:6d} stage-free +{r[1]-r[0]:5d} split+store+fence+arrive +{r[2]-r[1]:5d} fetch +{r[3]-r[2]:5d} | mma: synced {m[0]:6d} issue +{m[1]-m[0]:5d}")
