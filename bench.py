@@ -31,8 +31,8 @@ GRU_FWD_FLOP = 3 * 32 * 120 * 5 * 2 * (3 * 64 * 64)      # 3 unrolls x rows x (W
 GRU_FWD_BYTES = 32 * 120 * 5 * 4 * (3 * 192 + 3 * 64 + 256)   # gi in (3 unrolls), hidden out (3), saved gates out (eval unroll)
 ENV_BYTES = 140                                          # 16 B actions in + 124 B episode record out
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {"gru_unroll_fwd_kernel": 44411648 + 4326912, "gru_unroll_bwd_kernel": 29584128 + 343040,
-               "linear_fwd_kernel": 7062784, "matrix_game_step_kernel": 268475136 + 2043086000}   # profiles/r1b_ncu_full_*.txt
+NCU_TRAFFIC = {"gru_unroll_fwd_kernel": 44405504 + 3192832, "gru_unroll_bwd_kernel": 29584128 + 183808,
+               "linear_fwd_kernel": 7062784, "matrix_game_step_kernel": 268475136 + 2043086000}   # profiles/r1c_ncu_full_gru.txt, r1b_ncu_full_env.txt
 PAYOFF1 = [[8, -12, -12], [-12, 0, 0], [-12, 0, 0]]
 
 
@@ -381,7 +381,7 @@ def run_ours(opt):
                                   "B=32; FP32 FMA is the nearest roof (HBM and tensor-pipe fractions given for context; see "
                                   "batch_sweep for the fraction at larger batches)",
                     "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
-                    "traffic": NCU_TRAFFIC.get(dom), "traffic_source": "profiles/r1b_ncu_full_gru.txt (dram_read + dram_write, one --set full capture)",
+                    "traffic": NCU_TRAFFIC.get(dom), "traffic_source": "profiles/r1c_ncu_full_gru.txt (dram_read + dram_write, one --set full capture)",
                     "us_per_launch": dom_us, "algorithmic_flop_per_launch": flop, "algorithmic_bytes_per_launch": gru_bytes,
                     "hbm_frac": (gru_bytes / (dom_us * 1e-6) / 1e9 / hbm_peak) if gru_bytes else None,
                     "peak_source": "marl_fma_probe on this GPU (MEASURED_PEAKS.json has no fp32 figure); hbm: " + peak_src}
