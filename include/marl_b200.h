@@ -129,6 +129,7 @@ typedef struct marl_unroll_bwd {
     float* dhext; float* dgi; float* dgh; float* dx;
     float* dh0;              /* out [B*N,H] dL/dh0, or NULL */
     marl_agent_grads grads;
+    int dhext_ready;         /* != 0: dhext already holds dq . fc2_w (marl_qmix_td_fwd_bwd wrote it); skip that product */
 } marl_unroll_bwd;
 
 int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* a, void* stream);
@@ -178,12 +179,23 @@ int marl_qmix_fwd(int M, int N, int S, const marl_qmix_params* p, const float* q
 int marl_qmix_bwd(int M, int N, int S, const marl_qmix_params* p, const float* q, const float* s,
                   const float* hy, const float* dq_tot, float* dhy, float* dq, const marl_qmix_grads* g, void* stream);
 /* Learner fusion (q_learner.py:161-168 + backward): eval mixer on (q_chosen, s), target mixer on
- * (q_targets_chosen, s_next), TD loss, gradient to the eval mixer parameters and dense dq [B,L,N,A]. */
+ * (q_targets_chosen, s_next), TD loss, gradient to the eval mixer parameters and dense dq [B,L,N,A].
+ * With fc2_w / dhext the kernel also emits dhext = dq . fc2_w (dq has one non-zero per row, so this is one scaled row
+ * of fc2_w per agent): pass it on with marl_unroll_bwd.dhext_ready = 1.
+ * With sel the kernel also does marl_q_select's work (q_learner.py:100-117: gather, in-place mask of q_targets, double-Q
+ * arg-max) for its own sample: q_chosen / q_targets_chosen are then OUTPUTS and no marl_q_select call is needed
+ * (MARL_EINVAL when 64 N A bytes of staging exceed 160 KB: call marl_q_select yourself then). */
+typedef struct marl_qmix_select {   /* inputs of marl_q_select, for the fused form below */
+    const float* q_evals; const float* q_evals_next /*nullable: no double-Q*/; float* q_targets; const float* avail_u_next;
+    long long* a_star /*nullable out*/;
+} marl_qmix_select;
 int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* p, const marl_qmix_params* p_target,
-                         const float* s, const float* s_next, const float* q_chosen, const float* q_targets_chosen,
+                         const float* s, const float* s_next, float* q_chosen, float* q_targets_chosen,
                          const long long* u, const float* r, const float* terminated, const float* padded, float gamma,
                          float* hy, float* hy_target, float* dhy, float* q_tot, float* q_tot_target,
-                         float* dq, const marl_qmix_grads* g, float* scalars, int flags, void* stream);
+                         float* dq, const marl_qmix_grads* g, float* scalars, int flags,
+                         const float* fc2_w /*nullable, [A,H]*/, float* dhext /*nullable, [B,L,N,H]*/,
+                         const marl_qmix_select* sel /*nullable*/, void* stream);
 /* The state-only halves of the QMIX step, so that a caller can overlap them with the agent unrolls:
  * flags bit 0 of marl_qmix_td_fwd_bwd = hy / hy_target were already filled by marl_qmix_hyper_fwd,
  * bit 1 = leave dwcat/dbcat to a later marl_qmix_hyper_wgrad(dhy). */

@@ -55,7 +55,11 @@ class UnrollBwd(C.Structure):
     _fields_ = [("obs", c_ptr), ("onehot", c_ptr), ("shift_onehot", C.c_int), ("full_input", C.c_int),
                 ("params", AgentParams), ("hidden", c_ptr), ("x", c_ptr), ("gates", c_ptr), ("h0", c_ptr), ("dq", c_ptr),
                 ("dhidden", c_ptr), ("dhext", c_ptr), ("dgi", c_ptr), ("dgh", c_ptr), ("dx", c_ptr), ("dh0", c_ptr),
-                ("grads", AgentGrads)]
+                ("grads", AgentGrads), ("dhext_ready", C.c_int)]
+
+
+class QmixSelect(C.Structure):
+    _fields_ = [(k, c_ptr) for k in ("q_evals", "q_evals_next", "q_targets", "avail_u_next", "a_star")]
 
 
 class QmixParams(C.Structure):
@@ -129,7 +133,7 @@ _SIGNATURES = {
     "marl_qmix_fwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "marl_qmix_bwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams)] + [c_ptr] * 6 + [_P(QmixGrads), c_ptr], C.c_int),
     "marl_qmix_td_fwd_bwd": ([_P(Dims), _P(QmixParams), _P(QmixParams)] + [c_ptr] * 8 + [C.c_float] + [c_ptr] * 6
-                             + [_P(QmixGrads), c_ptr, C.c_int, c_ptr], C.c_int),
+                             + [_P(QmixGrads), c_ptr, C.c_int, c_ptr, c_ptr, _P(QmixSelect), c_ptr], C.c_int),
     "marl_qmix_hyper_fwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams), c_ptr, c_ptr, c_ptr], C.c_int),
     "marl_qmix_hyper2_fwd": ([C.c_int, C.c_int, C.c_int, _P(QmixHyper2), c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "marl_qmix_hyper2_bwd": ([C.c_int, C.c_int, C.c_int, _P(QmixHyper2), c_ptr, c_ptr, c_ptr, c_ptr, _P(QmixHyper2Grads), c_ptr], C.c_int),

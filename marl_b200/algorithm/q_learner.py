@@ -415,13 +415,17 @@ class QLearner:
         L.call("marl_agent_unroll_fwd", C.byref(d), arr, n_streams, sp)
         n_launch += 3 * n_streams + 1
         qplex = a.alg == "qplex"
-        L.call("marl_q_select", C.byref(d), ws["q"][0].data_ptr(), bt["u"].data_ptr(),
-               ws["q"][2].data_ptr() if double_q else None, ws["q"][1].data_ptr(), bt["avail_u_next"].data_ptr(),
-               bt["avail_u"].data_ptr() if qplex else None, ws["q_chosen"].data_ptr(), ws["a_star"].data_ptr(),
-               ws["q_tc"].data_ptr(), ws["max_q"].data_ptr() if qplex else None,
-               ws["qt_max"].data_ptr() if qplex else None, ws["oh_star"].data_ptr() if qplex else None, sp)
-        n_launch += 1
+        # the QMIX mixing kernel gathers / arg-maxes its own sample (2 [N, A] slabs per warp staged in shared memory)
+        fused_select = a.alg == "qmix" and 64 * a.n_agents * a.n_actions <= 160 * 1024
+        if not fused_select:
+            L.call("marl_q_select", C.byref(d), ws["q"][0].data_ptr(), bt["u"].data_ptr(),
+                   ws["q"][2].data_ptr() if double_q else None, ws["q"][1].data_ptr(), bt["avail_u_next"].data_ptr(),
+                   bt["avail_u"].data_ptr() if qplex else None, ws["q_chosen"].data_ptr(), ws["a_star"].data_ptr(),
+                   ws["q_tc"].data_ptr(), ws["max_q"].data_ptr() if qplex else None,
+                   ws["qt_max"].data_ptr() if qplex else None, ws["oh_star"].data_ptr() if qplex else None, sp)
+            n_launch += 1
         scalars = self._flat.tail.data_ptr()
+        dhext_fused = False
         if a.alg == "vdn":
             L.call("marl_vdn_td_fwd_bwd", C.byref(d), ws["q_chosen"].data_ptr(), ws["q_tc"].data_ptr(), bt["u"].data_ptr(),
                    bt["r"].data_ptr(), bt["terminated"].data_ptr(), bt["padded"].data_ptr(), float(self.gamma),
@@ -429,21 +433,21 @@ class QLearner:
             n_launch += 1
         elif a.alg == "qmix":
             p, ptg, g = qp, qpt, qg
+            # dq has one non-zero per agent row: the mixing kernel writes dq . fc2_w itself (no dgrad launch)
+            fc2_w = self._flat.ptr("agent.fc2.weight")
+            dhext_fused = fc2_w % 8 == 0
+            sel = L.QmixSelect()
+            sel.q_evals, sel.q_targets = ws["q"][0].data_ptr(), ws["q"][1].data_ptr()
+            sel.q_evals_next = ws["q"][2].data_ptr() if double_q else None
+            sel.avail_u_next, sel.a_star = bt["avail_u_next"].data_ptr(), ws["a_star"].data_ptr()
             cur.wait_stream(self._side)
             L.call("marl_qmix_td_fwd_bwd", C.byref(d), C.byref(p), C.byref(ptg), bt["s"].data_ptr(), bt["s_next"].data_ptr(),
                    ws["q_chosen"].data_ptr(), ws["q_tc"].data_ptr(), bt["u"].data_ptr(), bt["r"].data_ptr(),
                    bt["terminated"].data_ptr(), bt["padded"].data_ptr(), float(self.gamma), ws["hy"].data_ptr(),
                    ws["hy_t"].data_ptr(), ws["dhy"].data_ptr(), ws["q_tot"].data_ptr(), ws["q_tot_t"].data_ptr(),
-                   ws["dq"].data_ptr(), C.byref(g), scalars, 3, sp)
-            # ... and their weight gradient beside the BPTT
-            self._side.wait_stream(cur)
-            with th.cuda.stream(self._side):
-                if two:
-                    L.call("marl_qmix_hyper2_bwd", B * Lq, a.n_agents, a.state_shape, C.byref(q2), bt["s"].data_ptr(),
-                           ws["hh"].data_ptr(), ws["dhy"].data_ptr(), ws["dhh"].data_ptr(), C.byref(g2), L.stream_ptr())
-                else:
-                    L.call("marl_qmix_hyper_wgrad", B * Lq, a.n_agents, a.state_shape, bt["s"].data_ptr(), ws["dhy"].data_ptr(),
-                           C.byref(g), L.stream_ptr())
+                   ws["dq"].data_ptr(), C.byref(g), scalars, 3, fc2_w if dhext_fused else None,
+                   ws["dhext"].data_ptr() if dhext_fused else None, C.byref(sel) if fused_select else None, sp)
+            # ... and their weight gradient beside the BPTT (see _hyper_wgrad below)
             n_launch += 18 if two else 4
         elif a.alg == "qplex":
             from ..network.qplex import qplex_struct, qplex_dims, ws_struct
@@ -481,13 +485,29 @@ class QLearner:
         bw.h0, bw.dq, bw.dhidden = None, ws["dq"].data_ptr(), None
         bw.dhext, bw.dgi, bw.dgh, bw.dx = (ws[k].data_ptr() for k in ("dhext", "dgi", "dgh", "dx"))
         bw.dh0 = None
+        bw.dhext_ready = int(dhext_fused)
         bw.grads = agent_param_struct({n: self._flat.ptr("agent." + n, self._flat.grad) for n in AGENT_FLAT_ORDER},
                                       L.AgentGrads)
+        if a.alg == "qmix":
+            # the hyper-network weight gradient runs beside the BPTT (whose kernel is launched at a higher priority)
+            self._hyper_wgrad(cur, two, B * Lq, bt, ws, qg, q2 if two else None, g2 if two else None)
         L.call("marl_agent_unroll_bwd", C.byref(d), C.byref(bw), sp)
         if a.alg == "qmix":
             cur.wait_stream(self._side)
-        n_launch += 7
+        n_launch += 7 - int(dhext_fused)
         return n_launch
+
+    def _hyper_wgrad(self, cur, two, M, bt, ws, g, q2, g2):
+        """QMIX hyper-network weight gradient on the side stream, after what `cur` holds so far."""
+        a = self.args
+        self._side.wait_stream(cur)
+        with th.cuda.stream(self._side):
+            if two:
+                L.call("marl_qmix_hyper2_bwd", M, a.n_agents, a.state_shape, C.byref(q2), bt["s"].data_ptr(),
+                       ws["hh"].data_ptr(), ws["dhy"].data_ptr(), ws["dhh"].data_ptr(), C.byref(g2), L.stream_ptr())
+            else:
+                L.call("marl_qmix_hyper_wgrad", M, a.n_agents, a.state_shape, bt["s"].data_ptr(), ws["dhy"].data_ptr(),
+                       C.byref(g), L.stream_ptr())
 
     def _launch_optimizer(self):
         a, fl, opt, sp = self.args, self._flat, self.optimizer, L.stream_ptr()

@@ -20,6 +20,7 @@
 namespace marl {
 
 constexpr int kMaxStreams = 4;
+constexpr int kGruPrio = -1;        // launch priority of the recurrence kernels (see launch_pdl_prio)
 constexpr int kGruThreads = 128;   // 64 hidden units x 2-way split of the reduction, one warp per SM sub-partition
 constexpr int kGiDepth = 4;        // cp.async ring depth (time steps) of the forward's input gates
 
@@ -517,7 +518,7 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         if ((rows + n_ctas - 1) / n_ctas + 2 > 65535) return MARL_EINVAL;
         plan_rows(ga, rows, n_ctas);
         dim3 grid(n_ctas, (ga.n_chains + kGruGroups - 1) / kGruGroups);
-        launch_pdl(gru_unroll_fwd_kernel, grid, dim3(kGruThreads * kGruGroups), sm, st, ga);
+        launch_pdl_prio(kGruPrio, gru_unroll_fwd_kernel, grid, dim3(kGruThreads * kGruGroups), sm, st, ga);
     }
     MARL_LAUNCH_CHECK();
     // phase C
@@ -544,7 +545,7 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
     const int rows_total = d->B * d->L * d->N;
     const int I = d->O + d->A + d->N;
     int rc;
-    if (a->dq) {
+    if (a->dq && !a->dhext_ready) {
         // q = W2 h + b2:  dh_ext = dq . W2 ;  dW2 += dq^T h ; db2 += colsum(dq)
         LinearDgrad g{};
         g.dy = a->dq; g.lddy = d->A; g.w = a->params.fc2_w; g.ldw = MARL_H; g.w_col0 = 0;
@@ -558,7 +559,12 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
         ProfScope ps_("gru_unroll_bwd_kernel", st);
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(gru_unroll_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gru_bwd_smem_max()); attr_set = true; }
-        launch_pdl(gru_unroll_bwd_kernel, dim3(rows < kNumSMs ? rows : kNumSMs), dim3(kGruThreads), gru_bwd_smem_max(), st, ga);
+        const bool keep_ = pdl_small_problem();
+        // measured: launched programmatically the 148 recurrence CTAs come up while the producer still runs and the
+        // step gets 10-27 us slower on every config; a plain launch here, PDL for its consumers
+        pdl_small_problem() = false;
+        launch_pdl_prio(kGruPrio, gru_unroll_bwd_kernel, dim3(rows < kNumSMs ? rows : kNumSMs), dim3(kGruThreads), gru_bwd_smem_max(), st, ga);
+        pdl_small_problem() = keep_;
     }
     MARL_LAUNCH_CHECK();
     // the four weight gradients and the dx chain are independent: fan them out

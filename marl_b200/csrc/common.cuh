@@ -45,15 +45,27 @@ inline bool pdl_enabled() {
 inline bool& pdl_small_problem() { static bool v = true; return v; }
 inline void pdl_scope(long long rows) { pdl_small_problem() = rows <= 65536; }
 // <<<grid, block, smem, st>>> with the programmatic-stream-serialization attribute; only for kernels that call pdl_wait()
+// prio < 0: launch-priority attribute (numerically lower = scheduled first), so that the one-CTA-per-SM recurrence
+// kernels get their CTAs placed ahead of GEMM CTAs from sibling streams that became ready at the same moment
 template <class... KArgs, class... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+inline cudaError_t launch_pdl_prio(int prio, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = (pdl_enabled() && pdl_small_problem()) ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (prio < 0) {
+        attr[1].id = cudaLaunchAttributePriority;
+        attr[1].val.priority = prio;
+        cfg.numAttrs = 2;
+    }
     return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    return launch_pdl_prio(0, kern, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
