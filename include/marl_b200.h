@@ -160,10 +160,20 @@ int marl_td_loss(int M, const float* q_tot, const float* q_tot_target, const flo
                  const float* padded, float gamma, float* dq_tot, float* scalars, void* stream);
 
 /* ---- VDN: network/mixer.py:15-16 fused with the TD loss and its gradient ----
- * dq [B,L,N,A] receives dL/dq_evals (dense: dq_tot at the chosen action, 0 elsewhere). */
-int marl_vdn_td_fwd_bwd(const marl_dims* d, const float* q_chosen, const float* q_targets_chosen,
+ * dq [B,L,N,A] receives dL/dq_evals (dense: dq_tot at the chosen action, 0 elsewhere).
+ * Learner fusions (all nullable; the same as marl_qmix_td_fwd_bwd's):
+ *   fc2_w [A,H] + dhext [B,L,N,H]: also emit dhext = dq . fc2_w (one scaled row of fc2_w per agent, dq has one non-zero
+ *     per row); pass it on with marl_unroll_bwd.dhext_ready = 1;
+ *   sel: also do marl_q_select's work (q_learner.py:100-117: gather, in-place mask of q_targets, double-Q arg-max);
+ *     q_chosen / q_targets_chosen are then OUTPUTS (MARL_EINVAL when 64 N A bytes of staging exceed 160 KB). */
+typedef struct marl_select_fused {   /* inputs of marl_q_select, for the fused forms of the mixers below */
+    const float* q_evals; const float* q_evals_next /*nullable: no double-Q*/; float* q_targets; const float* avail_u_next;
+    long long* a_star /*nullable out*/;
+} marl_select_fused;
+int marl_vdn_td_fwd_bwd(const marl_dims* d, float* q_chosen, float* q_targets_chosen,
                         const long long* u, const float* r, const float* terminated, const float* padded,
-                        float gamma, float* q_tot, float* q_tot_target, float* dq, float* scalars, void* stream);
+                        float gamma, float* q_tot, float* q_tot_target, float* dq, float* scalars,
+                        const float* fc2_w, float* dhext, const marl_select_fused* sel, void* stream);
 
 /* ---- QMIX: network/mixer.py:57-80 ----
  * Hyper-network weights are passed concatenated (the host lays the parameters out that way):
@@ -185,17 +195,13 @@ int marl_qmix_bwd(int M, int N, int S, const marl_qmix_params* p, const float* q
  * With sel the kernel also does marl_q_select's work (q_learner.py:100-117: gather, in-place mask of q_targets, double-Q
  * arg-max) for its own sample: q_chosen / q_targets_chosen are then OUTPUTS and no marl_q_select call is needed
  * (MARL_EINVAL when 64 N A bytes of staging exceed 160 KB: call marl_q_select yourself then). */
-typedef struct marl_qmix_select {   /* inputs of marl_q_select, for the fused form below */
-    const float* q_evals; const float* q_evals_next /*nullable: no double-Q*/; float* q_targets; const float* avail_u_next;
-    long long* a_star /*nullable out*/;
-} marl_qmix_select;
 int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* p, const marl_qmix_params* p_target,
                          const float* s, const float* s_next, float* q_chosen, float* q_targets_chosen,
                          const long long* u, const float* r, const float* terminated, const float* padded, float gamma,
                          float* hy, float* hy_target, float* dhy, float* q_tot, float* q_tot_target,
                          float* dq, const marl_qmix_grads* g, float* scalars, int flags,
                          const float* fc2_w /*nullable, [A,H]*/, float* dhext /*nullable, [B,L,N,H]*/,
-                         const marl_qmix_select* sel /*nullable*/, void* stream);
+                         const marl_select_fused* sel /*nullable*/, void* stream);
 /* The state-only halves of the QMIX step, so that a caller can overlap them with the agent unrolls:
  * flags bit 0 of marl_qmix_td_fwd_bwd = hy / hy_target were already filled by marl_qmix_hyper_fwd,
  * bit 1 = leave dwcat/dbcat to a later marl_qmix_hyper_wgrad(dhy). */

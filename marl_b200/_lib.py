@@ -58,7 +58,7 @@ class UnrollBwd(C.Structure):
                 ("grads", AgentGrads), ("dhext_ready", C.c_int)]
 
 
-class QmixSelect(C.Structure):
+class SelectFused(C.Structure):
     _fields_ = [(k, c_ptr) for k in ("q_evals", "q_evals_next", "q_targets", "avail_u_next", "a_star")]
 
 
@@ -129,11 +129,12 @@ _SIGNATURES = {
     "marl_agent_unroll_bwd": ([_P(Dims), _P(UnrollBwd), c_ptr], C.c_int),
     "marl_q_select": ([_P(Dims)] + [c_ptr] * 12 + [c_ptr], C.c_int),
     "marl_td_loss": ([C.c_int] + [c_ptr] * 5 + [C.c_float, c_ptr, c_ptr, c_ptr], C.c_int),
-    "marl_vdn_td_fwd_bwd": ([_P(Dims)] + [c_ptr] * 6 + [C.c_float] + [c_ptr] * 4 + [c_ptr], C.c_int),
+    "marl_vdn_td_fwd_bwd": ([_P(Dims)] + [c_ptr] * 6 + [C.c_float] + [c_ptr] * 4 + [c_ptr, c_ptr, _P(SelectFused), c_ptr],
+                            C.c_int),
     "marl_qmix_fwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "marl_qmix_bwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams)] + [c_ptr] * 6 + [_P(QmixGrads), c_ptr], C.c_int),
     "marl_qmix_td_fwd_bwd": ([_P(Dims), _P(QmixParams), _P(QmixParams)] + [c_ptr] * 8 + [C.c_float] + [c_ptr] * 6
-                             + [_P(QmixGrads), c_ptr, C.c_int, c_ptr, c_ptr, _P(QmixSelect), c_ptr], C.c_int),
+                             + [_P(QmixGrads), c_ptr, C.c_int, c_ptr, c_ptr, _P(SelectFused), c_ptr], C.c_int),
     "marl_qmix_hyper_fwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams), c_ptr, c_ptr, c_ptr], C.c_int),
     "marl_qmix_hyper2_fwd": ([C.c_int, C.c_int, C.c_int, _P(QmixHyper2), c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "marl_qmix_hyper2_bwd": ([C.c_int, C.c_int, C.c_int, _P(QmixHyper2), c_ptr, c_ptr, c_ptr, c_ptr, _P(QmixHyper2Grads), c_ptr], C.c_int),

@@ -415,38 +415,39 @@ class QLearner:
         L.call("marl_agent_unroll_fwd", C.byref(d), arr, n_streams, sp)
         n_launch += 3 * n_streams + 1
         qplex = a.alg == "qplex"
-        # the QMIX mixing kernel gathers / arg-maxes its own sample (2 [N, A] slabs per warp staged in shared memory)
-        fused_select = a.alg == "qmix" and 64 * a.n_agents * a.n_actions <= 160 * 1024
-        if not fused_select:
+        # VDN / QMIX: the mixing kernel gathers / arg-maxes its own sample (2 [N, A] slabs per warp staged in shared
+        # memory) and, dq having one non-zero per agent row, writes dq . fc2_w itself: no q_select, no dgrad launch
+        fused_select = a.alg in ("vdn", "qmix") and 64 * a.n_agents * a.n_actions <= 160 * 1024
+        fc2_w = self._flat.ptr("agent.fc2.weight")
+        dhext_fused = a.alg in ("vdn", "qmix") and fc2_w % 8 == 0
+        if fused_select:
+            sel = L.SelectFused()
+            sel.q_evals, sel.q_targets = ws["q"][0].data_ptr(), ws["q"][1].data_ptr()
+            sel.q_evals_next = ws["q"][2].data_ptr() if double_q else None
+            sel.avail_u_next, sel.a_star = bt["avail_u_next"].data_ptr(), ws["a_star"].data_ptr()
+        else:
             L.call("marl_q_select", C.byref(d), ws["q"][0].data_ptr(), bt["u"].data_ptr(),
                    ws["q"][2].data_ptr() if double_q else None, ws["q"][1].data_ptr(), bt["avail_u_next"].data_ptr(),
                    bt["avail_u"].data_ptr() if qplex else None, ws["q_chosen"].data_ptr(), ws["a_star"].data_ptr(),
                    ws["q_tc"].data_ptr(), ws["max_q"].data_ptr() if qplex else None,
                    ws["qt_max"].data_ptr() if qplex else None, ws["oh_star"].data_ptr() if qplex else None, sp)
             n_launch += 1
+        fused_tail = (fc2_w if dhext_fused else None, ws["dhext"].data_ptr() if dhext_fused else None,
+                      C.byref(sel) if fused_select else None)
         scalars = self._flat.tail.data_ptr()
-        dhext_fused = False
         if a.alg == "vdn":
             L.call("marl_vdn_td_fwd_bwd", C.byref(d), ws["q_chosen"].data_ptr(), ws["q_tc"].data_ptr(), bt["u"].data_ptr(),
                    bt["r"].data_ptr(), bt["terminated"].data_ptr(), bt["padded"].data_ptr(), float(self.gamma),
-                   ws["q_tot"].data_ptr(), ws["q_tot_t"].data_ptr(), ws["dq"].data_ptr(), scalars, sp)
+                   ws["q_tot"].data_ptr(), ws["q_tot_t"].data_ptr(), ws["dq"].data_ptr(), scalars, *fused_tail, sp)
             n_launch += 1
         elif a.alg == "qmix":
             p, ptg, g = qp, qpt, qg
-            # dq has one non-zero per agent row: the mixing kernel writes dq . fc2_w itself (no dgrad launch)
-            fc2_w = self._flat.ptr("agent.fc2.weight")
-            dhext_fused = fc2_w % 8 == 0
-            sel = L.QmixSelect()
-            sel.q_evals, sel.q_targets = ws["q"][0].data_ptr(), ws["q"][1].data_ptr()
-            sel.q_evals_next = ws["q"][2].data_ptr() if double_q else None
-            sel.avail_u_next, sel.a_star = bt["avail_u_next"].data_ptr(), ws["a_star"].data_ptr()
             cur.wait_stream(self._side)
             L.call("marl_qmix_td_fwd_bwd", C.byref(d), C.byref(p), C.byref(ptg), bt["s"].data_ptr(), bt["s_next"].data_ptr(),
                    ws["q_chosen"].data_ptr(), ws["q_tc"].data_ptr(), bt["u"].data_ptr(), bt["r"].data_ptr(),
                    bt["terminated"].data_ptr(), bt["padded"].data_ptr(), float(self.gamma), ws["hy"].data_ptr(),
                    ws["hy_t"].data_ptr(), ws["dhy"].data_ptr(), ws["q_tot"].data_ptr(), ws["q_tot_t"].data_ptr(),
-                   ws["dq"].data_ptr(), C.byref(g), scalars, 3, fc2_w if dhext_fused else None,
-                   ws["dhext"].data_ptr() if dhext_fused else None, C.byref(sel) if fused_select else None, sp)
+                   ws["dq"].data_ptr(), C.byref(g), scalars, 3, *fused_tail, sp)
             # ... and their weight gradient beside the BPTT (see _hyper_wgrad below)
             n_launch += 18 if two else 4
         elif a.alg == "qplex":

@@ -466,20 +466,23 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
     }
     // phase A: the streams are independent -> one lane each
     ForkJoin fa(st, n_streams);
-    for (int i = 0; i < n_streams; ++i) {
-        cudaStream_t st = fa.lane(i);
-        LinearFwd f{};
-        f.in = agent_input(d, s[i].obs, s[i].onehot, s[i].shift_onehot, s[i].full_input);
-        f.w = s[i].params.fc1_w; f.ldw = I; f.bias = s[i].params.fc1_b;
-        f.y = s[i].x; f.ldy = MARL_H; f.M = rows_total; f.N = MARL_H; f.relu = 1; f.batch = 1;
-        int rc = linear_fwd(f, st);
-        if (rc) return rc;
-        LinearFwd g{};
-        g.in = plain_operand(s[i].x, MARL_H, MARL_H);
-        g.w = s[i].params.w_ih; g.ldw = MARL_H; g.bias = s[i].params.b_ih;
-        g.y = s[i].gi; g.ldy = MARL_G; g.M = rows_total; g.N = MARL_G; g.batch = 1;
-        rc = linear_fwd(g, st);
-        if (rc) return rc;
+    {
+        LinearPrio prio_(kGruPrio);   // placed ahead of the GEMMs other streams issue at the same moment (the mixer's hyper-networks)
+        for (int i = 0; i < n_streams; ++i) {
+            cudaStream_t st = fa.lane(i);
+            LinearFwd f{};
+            f.in = agent_input(d, s[i].obs, s[i].onehot, s[i].shift_onehot, s[i].full_input);
+            f.w = s[i].params.fc1_w; f.ldw = I; f.bias = s[i].params.fc1_b;
+            f.y = s[i].x; f.ldy = MARL_H; f.M = rows_total; f.N = MARL_H; f.relu = 1; f.batch = 1;
+            int rc = linear_fwd(f, st);
+            if (rc) return rc;
+            LinearFwd g{};
+            g.in = plain_operand(s[i].x, MARL_H, MARL_H);
+            g.w = s[i].params.w_ih; g.ldw = MARL_H; g.bias = s[i].params.b_ih;
+            g.y = s[i].gi; g.ldy = MARL_G; g.M = rows_total; g.N = MARL_G; g.batch = 1;
+            rc = linear_fwd(g, st);
+            if (rc) return rc;
+        }
     }
     fa.join();
     // phase B: build chains (a stream whose h0_from == j continues chain of j; j must be a chain tail)

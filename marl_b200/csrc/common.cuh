@@ -63,6 +63,13 @@ inline cudaError_t launch_pdl_prio(int prio, void (*kern)(KArgs...), dim3 grid, 
     }
     return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
+// launch priority of the GEMM launches issued while a LinearPrio is alive (host calls are single-threaded)
+inline int& linear_prio() { static int v = 0; return v; }
+struct LinearPrio {
+    int keep;
+    explicit LinearPrio(int p) : keep(linear_prio()) { linear_prio() = p; }
+    ~LinearPrio() { linear_prio() = keep; }
+};
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     return launch_pdl_prio(0, kern, grid, block, smem, st, std::forward<Args>(args)...);

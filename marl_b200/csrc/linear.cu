@@ -512,10 +512,10 @@ static bool vec_ok_mat(const float* p, int ld, long long bs, int col0 = 0) {
             cudaFuncSetAttribute(KERNEL<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem); \
             attr_done = true;                                                                              \
         }                                                                                                  \
-        if (VA && VB) launch_pdl(KERNEL<true, true>, GRID, dim3(UTH), kUmmaSmem, ST, __VA_ARGS__);               \
-        else if (VA) launch_pdl(KERNEL<true, false>, GRID, dim3(UTH), kUmmaSmem, ST, __VA_ARGS__);               \
-        else if (VB) launch_pdl(KERNEL<false, true>, GRID, dim3(UTH), kUmmaSmem, ST, __VA_ARGS__);               \
-        else launch_pdl(KERNEL<false, false>, GRID, dim3(UTH), kUmmaSmem, ST, __VA_ARGS__);                      \
+        if (VA && VB) launch_pdl_prio(linear_prio(), KERNEL<true, true>, GRID, dim3(UTH), kUmmaSmem, ST, __VA_ARGS__);               \
+        else if (VA) launch_pdl_prio(linear_prio(), KERNEL<true, false>, GRID, dim3(UTH), kUmmaSmem, ST, __VA_ARGS__);               \
+        else if (VB) launch_pdl_prio(linear_prio(), KERNEL<false, true>, GRID, dim3(UTH), kUmmaSmem, ST, __VA_ARGS__);               \
+        else launch_pdl_prio(linear_prio(), KERNEL<false, false>, GRID, dim3(UTH), kUmmaSmem, ST, __VA_ARGS__);                      \
     } while (0)
 
 int linear_fwd(const LinearFwd& a, cudaStream_t st) {
@@ -541,7 +541,7 @@ int linear_wgrad(const LinearWgrad& a, cudaStream_t st) {
     const int K = lin_width(a.in);
     const int tiles = cdiv(a.N, UM) * cdiv(K, UN) * a.batch;
     int splits = cdiv(2 * kNumSMs, tiles);
-    splits = max(1, min(splits, cdiv(a.M, 256)));
+    splits = max(1, min(splits, cdiv(a.M, 256)));   // 128 / 512 rows per split measured slower (r1d)
     int chunk = cdiv(cdiv(a.M, splits), UK) * UK;
     splits = cdiv(a.M, chunk);
     dim3 grid(cdiv(a.N, UM), cdiv(K, UN), a.batch * splits);

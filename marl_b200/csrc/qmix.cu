@@ -11,14 +11,13 @@
 #include "forkjoin.h"
 #include "../../include/marl_b200.h"
 #include "profile.h"
+#include "select.cuh"
 
 namespace marl {
 
 constexpr int E = MARL_QMIX_EMBED;
 constexpr int kQmixWarps = 8;
 constexpr int kQmixMaxAgents = 64;
-constexpr float kNegBigQ = -9999999.0f;   // algorithm/q_learner.py:105,112
-constexpr size_t kQmixSelSmemMax = 160 * 1024;   // fused selection stages 2 [N, A] slabs per warp
 
 enum { QMIX_FWD = 0, QMIX_BWD = 1, QMIX_TD = 2 };
 
@@ -33,9 +32,7 @@ struct QmixMixArgs {
     float* dq_small;              // [M,N] or null
     const long long* u; float* dq_dense;   // [M,N,A] or null
     const float* fc2_w; float* dhext;      // agent head W2 [A,H] and dL/dh through it [M,N,H], or null
-    // fused action-value selection (TD mode): q / q_t are then OUTPUTS, gathered here from the agents' heads
-    const float* sel_q; const float* sel_qn; float* sel_qt; const float* sel_avail_next; float* q_out; float* qt_out;
-    long long* sel_a_star;
+    SelectArgs sel;                        // fused action-value selection (TD mode): q / q_t are then OUTPUTS
     float* g_wb2; float* g_bb2; float* scalars;
 };
 
@@ -69,44 +66,8 @@ __global__ void __launch_bounds__(kQmixWarps * 32) qmix_mix_kernel(QmixMixArgs a
         const float* y = a.hy + (long long)m * C;
         const float* q = a.q + (long long)m * N;
         const float* qt = a.q_t + (long long)m * N;
-        if (a.sel_q) {
-            // q_learner.py:100-117 for this sample's agents (same arithmetic as q_select_kernel).  The [N, A] slabs are
-            // staged coalesced (mask folded in, q_targets masked in place), then lane = agent scans shared memory.
-            const int A = a.A, NA = N * A;
-            const long long o = (long long)m * NA;
-            float* sn = ssel_dyn + (size_t)warp * 2 * NA;
-            float* stt = sn + NA;
-            for (int i = lane; i < NA; i += 32) {
-                const bool off = a.sel_avail_next[o + i] == 0.0f;
-                float v = a.sel_qt[o + i];
-                if (off) { v = kNegBigQ; a.sel_qt[o + i] = v; }
-                stt[i] = v;
-                if (a.sel_qn) sn[i] = off ? kNegBigQ : a.sel_qn[o + i];
-            }
-            __syncwarp();
-            for (int n = lane; n < N; n += 32) {
-                const long long i = (long long)m * N + n;
-                const float qc = a.sel_q[i * A + a.u[i]];
-                int best = 0;
-                float tmax = 0.f, tsel = 0.f;
-                if (a.sel_qn) {
-                    float bv = 0.f;
-                    for (int c = 0; c < A; ++c) {
-                        const float v = sn[n * A + c];
-                        if (c == 0 || v > bv) { bv = v; best = c; }
-                    }
-                }
-                for (int c = 0; c < A; ++c) {
-                    const float v = stt[n * A + c];
-                    if (c == 0 || v > tmax) tmax = v;
-                    if (c == best) tsel = v;
-                }
-                const float tc = a.sel_qn ? tsel : tmax;
-                ssel[warp][0][n] = qc; ssel[warp][1][n] = tc;
-                a.q_out[i] = qc; a.qt_out[i] = tc;
-                if (a.sel_a_star) a.sel_a_star[i] = a.sel_qn ? best : -1;
-            }
-            __syncwarp();
+        if (a.sel.q) {
+            warp_select(a.sel, m, N, a.A, lane, ssel_dyn + (size_t)warp * 2 * N * a.A, ssel[warp][0], ssel[warp][1]);
             q = ssel[warp][0]; qt = ssel[warp][1];
         }
         float pre, hid, w2raw, hb2;
@@ -153,15 +114,7 @@ __global__ void __launch_bounds__(kQmixWarps * 32) qmix_mix_kernel(QmixMixArgs a
                 a.dq_dense[(long long)m * N * A + i] = (c == (int)a.u[(long long)m * N + n]) ? sdq[warp][n] : 0.0f;
             }
         }
-        if (a.dhext) {
-            // dq has one non-zero per agent row, so dq . W2 is that row of W2 scaled: saves the [M*N, H, A] dgrad launch
-#pragma unroll 4
-            for (int n = 0; n < N; ++n) {
-                const float g = sdq[warp][n];
-                const float2 w = __ldg((const float2*)(a.fc2_w + __ldg(a.u + (long long)m * N + n) * MARL_H) + lane);
-                ((float2*)(a.dhext + ((long long)m * N + n) * MARL_H))[lane] = make_float2(g * w.x, g * w.y);
-            }
-        }
+        if (a.dhext) warp_dhext(a.fc2_w, a.u, m, N, lane, sdq[warp], a.dhext);
         __syncwarp();
     }
     if (a.mode == QMIX_FWD) return;
@@ -304,14 +257,14 @@ extern "C" int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* 
                                     const long long* u, const float* r, const float* terminated, const float* padded,
                                     float gamma, float* hy, float* hy_target, float* dhy, float* q_tot, float* q_tot_target,
                                     float* dq, const marl_qmix_grads* g, float* scalars, int flags, const float* fc2_w,
-                                    float* dhext, const marl_qmix_select* sel, void* stream) {
+                                    float* dhext, const marl_select_fused* sel, void* stream) {
     if (!d || !p || !pt || !p->wb2 || !p->bb2 || !pt->wb2 || !pt->bb2 || !s || !s_next || !q_chosen || !q_tc || !r ||
         !terminated || !padded || !hy || !hy_target || !dhy || !g || !scalars)
         return MARL_EINVAL;
     if (!(flags & 1) && (!p->wcat || !p->bcat || !pt->wcat || !pt->bcat)) return MARL_EINVAL;   // hyper GEMMs run here
     if (!(flags & 2) && (!g->wcat || !g->bcat)) return MARL_EINVAL;
     if ((dq || dhext || sel) && !u) return MARL_EINVAL;
-    if (sel && (!sel->q_evals || !sel->q_targets || !sel->avail_u_next)) return MARL_EINVAL;
+    if (sel && !select_ok(sel)) return MARL_EINVAL;
     if (dhext && (!fc2_w || ((uintptr_t)fc2_w & 7) || ((uintptr_t)dhext & 7))) return MARL_EINVAL;
     if (d->N < 1 || d->N > kQmixMaxAgents || d->S < 1) return MARL_EINVAL;
     const int M = d->B * d->L;
@@ -332,16 +285,13 @@ extern "C" int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* 
     a.r = r; a.term = terminated; a.padded = padded; a.gamma = gamma;
     a.q_tot = q_tot; a.q_tot_t = q_tot_target; a.dhy = dhy; a.u = u; a.dq_dense = dq;
     a.fc2_w = fc2_w; a.dhext = dhext;
-    if (sel) {
-        a.sel_q = sel->q_evals; a.sel_qn = sel->q_evals_next; a.sel_qt = sel->q_targets; a.sel_avail_next = sel->avail_u_next;
-        a.q_out = q_chosen; a.qt_out = q_tc; a.sel_a_star = sel->a_star;
-    }
+    if (sel) a.sel = select_args(sel, u, q_chosen, q_tc);
     a.g_wb2 = g->wb2; a.g_bb2 = g->bb2; a.scalars = scalars;
-    const size_t dyn = sel ? (size_t)kQmixWarps * 2 * d->N * d->A * sizeof(float) : 0;
-    if (dyn > kQmixSelSmemMax) return MARL_EINVAL;
+    const size_t dyn = sel ? select_smem(kQmixWarps, d->N, d->A) : 0;
+    if (dyn > kSelectSmemMax) return MARL_EINVAL;
     if (dyn > 40 * 1024) {
         static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(qmix_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQmixSelSmemMax); attr_set = true; }
+        if (!attr_set) { cudaFuncSetAttribute(qmix_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelectSmemMax); attr_set = true; }
     }
     { ProfScope ps_("qmix_mix_kernel", st); launch_pdl(qmix_mix_kernel, dim3(mix_grid(M)), dim3(kQmixWarps * 32), dyn, st, a); }
     MARL_LAUNCH_CHECK();

@@ -2,10 +2,9 @@
 #include "common.cuh"
 #include "../../include/marl_b200.h"
 #include "profile.h"
+#include "select.cuh"
 
 namespace marl {
-
-constexpr float kNegBig = -9999999.0f;   // algorithm/q_learner.py:105,112,126
 
 __global__ void __launch_bounds__(256) q_select_kernel(
     int rows, int A, const float* __restrict__ q_evals, const long long* __restrict__ u,
@@ -128,6 +127,52 @@ __global__ void __launch_bounds__(256) vdn_td_kernel(int M, int N, int A, const 
     block_accumulate2(sq, msk, scalars);
 }
 
+// The same with one warp per sample, for the learner: optionally does the action-value selection itself (warp_select) and
+// emits dL/dh through the agents' head (warp_dhext), so that neither q_select nor the fc2 dgrad GEMM is launched.
+constexpr int kVdnWarps = 8;
+constexpr int kVdnMaxAgents = 64;
+struct VdnFusedArgs {
+    int M, N, A;
+    const float* q_chosen; const float* q_tc; const long long* u;
+    const float* r; const float* term; const float* padded; float gamma;
+    float* q_tot; float* q_tot_t; float* dq; float* scalars;
+    const float* fc2_w; float* dhext;
+    SelectArgs sel;
+};
+
+__global__ void __launch_bounds__(kVdnWarps * 32) vdn_td_fused_kernel(VdnFusedArgs a) {
+    pdl_enter();
+    __shared__ float ssel[kVdnWarps][3][kVdnMaxAgents];
+    extern __shared__ float ssel_dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, N = a.N, A = a.A;
+    float sq = 0.f, msk = 0.f;
+    for (long long m = blockIdx.x * kVdnWarps + warp; m < a.M; m += (long long)gridDim.x * kVdnWarps) {
+        const float* q = a.q_chosen + m * N;
+        const float* qt = a.q_tc + m * N;
+        if (a.sel.q) {
+            warp_select(a.sel, m, N, A, lane, ssel_dyn + (size_t)warp * 2 * N * A, ssel[warp][0], ssel[warp][1]);
+            q = ssel[warp][0]; qt = ssel[warp][1];
+        }
+        float tot = 0.f, tot_t = 0.f;
+        for (int n = 0; n < N; ++n) { tot += q[n]; tot_t += qt[n]; }                     // mixer.py:16, agent order
+        float s1, s2;
+        const float g = td_grad(tot, tot_t, a.r[m], a.term[m], a.padded[m], a.gamma, s1, s2);
+        if (lane == 0) { a.q_tot[m] = tot; a.q_tot_t[m] = tot_t; sq += s1; msk += s2; }
+        if (a.dq)
+            for (int i = lane; i < N * A; i += 32) {
+                const int n = i / A, c = i - n * A;
+                a.dq[m * N * A + i] = (c == (int)a.u[m * N + n]) ? g : 0.0f;
+            }
+        if (a.dhext) {
+            for (int n = lane; n < N; n += 32) ssel[warp][2][n] = g;
+            __syncwarp();
+            warp_dhext(a.fc2_w, a.u, m, N, lane, ssel[warp][2], a.dhext);
+        }
+        __syncwarp();
+    }
+    block_accumulate2(sq, msk, a.scalars);
+}
+
 struct IngestKey { const void* src; void* dst; int inner; int kind; };   // kind 0: f64->f32, 1: f64->i64, 2: i64->i64, 3: f32->f32
 struct IngestArgs { IngestKey k[11]; int B, L, T_src; const long long* idx; };   // idx (nullable): source episode of output episode b
 
@@ -210,17 +255,41 @@ extern "C" int marl_td_loss(int M, const float* q_tot, const float* q_tot_target
     return MARL_OK;
 }
 
-extern "C" int marl_vdn_td_fwd_bwd(const marl_dims* d, const float* q_chosen, const float* q_targets_chosen,
+extern "C" int marl_vdn_td_fwd_bwd(const marl_dims* d, float* q_chosen, float* q_targets_chosen,
                                    const long long* u, const float* r, const float* terminated, const float* padded,
-                                   float gamma, float* q_tot, float* q_tot_target, float* dq, float* scalars, void* stream) {
+                                   float gamma, float* q_tot, float* q_tot_target, float* dq, float* scalars,
+                                   const float* fc2_w, float* dhext, const marl_select_fused* sel, void* stream) {
     if (!d || !q_chosen || !q_targets_chosen || !r || !terminated || !padded || !q_tot || !q_tot_target || !scalars)
         return MARL_EINVAL;
-    if (dq && !u) return MARL_EINVAL;
+    if ((dq || dhext || sel) && !u) return MARL_EINVAL;
+    if (dhext && (!fc2_w || ((uintptr_t)fc2_w & 7) || ((uintptr_t)dhext & 7))) return MARL_EINVAL;
+    if (sel && !select_ok(sel)) return MARL_EINVAL;
     const int M = d->B * d->L;
     if (M <= 0) return MARL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
     pdl_scope((long long)M * d->N);
-    { ProfScope ps_("vdn_td_kernel", (cudaStream_t)stream); launch_pdl(vdn_td_kernel, dim3((M + 255) / 256), dim3(256), 0, (cudaStream_t)stream, M, d->N, d->A, q_chosen, q_targets_chosen, u, r,
-        terminated, padded, gamma, q_tot, q_tot_target, dq, scalars); }
+    if (!sel && !dhext) {
+        ProfScope ps_("vdn_td_kernel", st);
+        launch_pdl(vdn_td_kernel, dim3((M + 255) / 256), dim3(256), 0, st, M, d->N, d->A, (const float*)q_chosen,
+                   (const float*)q_targets_chosen, u, r, terminated, padded, gamma, q_tot, q_tot_target, dq, scalars);
+    } else {
+        if (d->N > kVdnMaxAgents) return MARL_EINVAL;
+        const size_t dyn = sel ? select_smem(kVdnWarps, d->N, d->A) : 0;
+        if (dyn > kSelectSmemMax) return MARL_EINVAL;
+        if (dyn > 40 * 1024) {
+            static bool attr_set = false;
+            if (!attr_set) { cudaFuncSetAttribute(vdn_td_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelectSmemMax); attr_set = true; }
+        }
+        VdnFusedArgs a{};
+        a.M = M; a.N = d->N; a.A = d->A; a.q_chosen = q_chosen; a.q_tc = q_targets_chosen; a.u = u;
+        a.r = r; a.term = terminated; a.padded = padded; a.gamma = gamma;
+        a.q_tot = q_tot; a.q_tot_t = q_tot_target; a.dq = dq; a.scalars = scalars; a.fc2_w = fc2_w; a.dhext = dhext;
+        if (sel) a.sel = select_args(sel, u, q_chosen, q_targets_chosen);
+        int blocks = (M + kVdnWarps - 1) / kVdnWarps;
+        blocks = blocks > 4 * kNumSMs ? 4 * kNumSMs : blocks;
+        ProfScope ps_("vdn_td_fused_kernel", st);
+        launch_pdl(vdn_td_fused_kernel, dim3(blocks), dim3(kVdnWarps * 32), dyn, st, a);
+    }
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
