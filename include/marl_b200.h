@@ -167,8 +167,14 @@ int marl_td_loss(int M, const float* q_tot, const float* q_tot_target, const flo
  *   sel: also do marl_q_select's work (q_learner.py:100-117: gather, in-place mask of q_targets, double-Q arg-max);
  *     q_chosen / q_targets_chosen are then OUTPUTS (MARL_EINVAL when 64 N A bytes of staging exceed 160 KB). */
 typedef struct marl_select_fused {   /* inputs of marl_q_select, for the fused forms of the mixers below */
-    const float* q_evals; const float* q_evals_next /*nullable: no double-Q*/; float* q_targets; const float* avail_u_next;
+    float* q_evals; float* q_evals_next /*nullable: no double-Q*/; float* q_targets; const float* avail_u_next;
     long long* a_star /*nullable out*/;
+    /* hidden_evals != NULL: the agents' heads are evaluated here as well (q = fc2_w h + fc2_b, network/q_network.py:21-22):
+     * q_evals / q_evals_next / q_targets [B,L,N,A] are then OUTPUTS (q_targets masked as the reference leaves it), computed
+     * from the hidden states [B,L,N,H] of the eval net on o, the target net on o_next and (double-Q) the eval net on
+     * o_next -- run marl_agent_unroll_fwd with q = NULL.  All seven pointers 16-byte aligned. */
+    const float* hidden_evals; const float* hidden_targets; const float* hidden_evals_next;
+    const float* fc2_w; const float* fc2_b; const float* fc2_w_target; const float* fc2_b_target;
 } marl_select_fused;
 int marl_vdn_td_fwd_bwd(const marl_dims* d, float* q_chosen, float* q_targets_chosen,
                         const long long* u, const float* r, const float* terminated, const float* padded,

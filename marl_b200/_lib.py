@@ -59,7 +59,9 @@ class UnrollBwd(C.Structure):
 
 
 class SelectFused(C.Structure):
-    _fields_ = [(k, c_ptr) for k in ("q_evals", "q_evals_next", "q_targets", "avail_u_next", "a_star")]
+    _fields_ = [(k, c_ptr) for k in ("q_evals", "q_evals_next", "q_targets", "avail_u_next", "a_star", "hidden_evals",
+                                     "hidden_targets", "hidden_evals_next", "fc2_w", "fc2_b", "fc2_w_target",
+                                     "fc2_b_target")]
 
 
 class QmixParams(C.Structure):

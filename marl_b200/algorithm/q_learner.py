@@ -400,12 +400,22 @@ class QLearner:
                            ws["hy_t"].data_ptr(), ssp)
         n_streams = 3 if double_q else 2
         arr = (L.UnrollStream * 3)()
+        # VDN / QMIX: the mixing kernel gathers / arg-maxes its own sample (the [N, A] slabs of a warp's sample staged in
+        # shared memory), evaluates the agents' heads q = fc2(h) on the way (no head GEMMs after the unroll) and, dq having
+        # one non-zero per agent row, writes dq . fc2_w itself: no q_select, no dgrad launch
+        NA = a.n_agents * a.n_actions
+        fc2_w, fc2_wt = self._flat.ptr("agent.fc2.weight"), self._tflat.ptr("agent.fc2.weight")
+        fused_select = a.alg in ("vdn", "qmix") and 64 * NA <= 160 * 1024
+        fused_heads = (fused_select and (8 * (3 * NA + 3 + 3 * a.n_agents * 68) + 2 * a.n_actions * 69) * 4 <= 160 * 1024
+                       and fc2_w % 16 == 0 and fc2_wt % 16 == 0)
+        dhext_fused = a.alg in ("vdn", "qmix") and fc2_w % 8 == 0
 
         def fill(i, obs, shift, params, h0_from, gates):
             s = arr[i]
             s.obs, s.onehot, s.shift_onehot, s.full_input = obs.data_ptr(), bt["u_onehot"].data_ptr(), shift, 0
             s.h0_from, s.h0, s.params = h0_from, None, params
-            s.q, s.hidden, s.h_last = ws["q"][i].data_ptr(), ws["hidden"][i].data_ptr(), ws["h_last"][i].data_ptr()
+            s.q = None if fused_heads else ws["q"][i].data_ptr()
+            s.hidden, s.h_last = ws["hidden"][i].data_ptr(), ws["h_last"][i].data_ptr()
             s.x, s.gi, s.gates = ws["x"][i].data_ptr(), ws["gi"][i].data_ptr(), gates
 
         fill(0, bt["o"], 1, pe, -1, ws["gates"].data_ptr())          # eval net on o          (q_learner.py:96-97)
@@ -413,18 +423,18 @@ class QLearner:
         if double_q:
             fill(2, bt["o_next"], 0, pe, 0, None)                     # eval net on o_next, hidden carried (:110)
         L.call("marl_agent_unroll_fwd", C.byref(d), arr, n_streams, sp)
-        n_launch += 3 * n_streams + 1
+        n_launch += (2 if fused_heads else 3) * n_streams + 1
         qplex = a.alg == "qplex"
-        # VDN / QMIX: the mixing kernel gathers / arg-maxes its own sample (2 [N, A] slabs per warp staged in shared
-        # memory) and, dq having one non-zero per agent row, writes dq . fc2_w itself: no q_select, no dgrad launch
-        fused_select = a.alg in ("vdn", "qmix") and 64 * a.n_agents * a.n_actions <= 160 * 1024
-        fc2_w = self._flat.ptr("agent.fc2.weight")
-        dhext_fused = a.alg in ("vdn", "qmix") and fc2_w % 8 == 0
         if fused_select:
             sel = L.SelectFused()
             sel.q_evals, sel.q_targets = ws["q"][0].data_ptr(), ws["q"][1].data_ptr()
             sel.q_evals_next = ws["q"][2].data_ptr() if double_q else None
             sel.avail_u_next, sel.a_star = bt["avail_u_next"].data_ptr(), ws["a_star"].data_ptr()
+            if fused_heads:
+                sel.hidden_evals, sel.hidden_targets = ws["hidden"][0].data_ptr(), ws["hidden"][1].data_ptr()
+                sel.hidden_evals_next = ws["hidden"][2].data_ptr() if double_q else None
+                sel.fc2_w, sel.fc2_b = fc2_w, self._flat.ptr("agent.fc2.bias")
+                sel.fc2_w_target, sel.fc2_b_target = fc2_wt, self._tflat.ptr("agent.fc2.bias")
         else:
             L.call("marl_q_select", C.byref(d), ws["q"][0].data_ptr(), bt["u"].data_ptr(),
                    ws["q"][2].data_ptr() if double_q else None, ws["q"][1].data_ptr(), bt["avail_u_next"].data_ptr(),

@@ -41,6 +41,7 @@ __device__ __forceinline__ float qmix_forward_lane(const float* __restrict__ y, 
                                                    float wb2e, float bb2, int lane, float& pre, float& hid,
                                                    float& w2raw, float& hb2) {
     float acc = y[N * E + lane];                                   // hyper_b1
+#pragma unroll 4
     for (int n = 0; n < N; ++n) acc = fmaf(q[n], fabsf(y[n * E + lane]), acc);   // bmm(q, |w1|) + b1, mixer.py:64-70
     pre = acc;
     hid = acc > 0.0f ? acc : (expf(acc) - 1.0f);                   // F.elu
@@ -50,12 +51,19 @@ __device__ __forceinline__ float qmix_forward_lane(const float* __restrict__ y, 
     return warp_sum(part) + bb2;
 }
 
-__global__ void __launch_bounds__(kQmixWarps * 32) qmix_mix_kernel(QmixMixArgs a) {
+__global__ void __launch_bounds__(kQmixWarps * 32, 4) qmix_mix_kernel(QmixMixArgs a) {
     pdl_enter();
     __shared__ float sdq[kQmixWarps][kQmixMaxAgents];
     __shared__ float sred[kQmixWarps][E + 1];
     __shared__ float ssel[kQmixWarps][2][kQmixMaxAgents];
-    extern __shared__ float ssel_dyn[];                       // fused selection: [warps][2][N*A]
+    extern __shared__ __align__(16) float ssel_dyn[];         // fused selection: select_warp_floats() per warp
+    const float* heads = nullptr;
+    if (a.sel.q && a.sel.heads) {
+        float* h = ssel_dyn + kQmixWarps * select_warp_floats(a.N, a.A, true);
+        stage_heads(a.sel, a.A, h);
+        heads = h;
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = a.N, C = N * E + 3 * E;
     const float wb2e = a.wb2[lane], bb2 = a.bb2[0];
@@ -63,11 +71,11 @@ __global__ void __launch_bounds__(kQmixWarps * 32) qmix_mix_kernel(QmixMixArgs a
     if (a.mode == QMIX_TD) { wb2te = a.wb2_t[lane]; bb2t = a.bb2_t[0]; }
     float acc_wb2 = 0.f, acc_bb2 = 0.f, acc_sq = 0.f, acc_mask = 0.f;
     for (int m = blockIdx.x * kQmixWarps + warp; m < a.M; m += gridDim.x * kQmixWarps) {
-        const float* y = a.hy + (long long)m * C;
+        const float* __restrict__ y = a.hy + (long long)m * C;
         const float* q = a.q + (long long)m * N;
         const float* qt = a.q_t + (long long)m * N;
         if (a.sel.q) {
-            warp_select(a.sel, m, N, a.A, lane, ssel_dyn + (size_t)warp * 2 * N * a.A, ssel[warp][0], ssel[warp][1]);
+            warp_select(a.sel, m, N, a.A, lane, ssel_dyn + warp * select_warp_floats(N, a.A, a.sel.heads), ssel[warp][0], ssel[warp][1], heads);
             q = ssel[warp][0]; qt = ssel[warp][1];
         }
         float pre, hid, w2raw, hb2;
@@ -89,7 +97,7 @@ __global__ void __launch_bounds__(kQmixWarps * 32) qmix_mix_kernel(QmixMixArgs a
             G = a.dq_tot_in[m];
         }
         // backward
-        float* dy = a.dhy + (long long)m * C;
+        float* __restrict__ dy = a.dhy + (long long)m * C;
         const float dpre = G * fabsf(w2raw) * (pre > 0.0f ? 1.0f : (hid + 1.0f));   // elu'(x) = exp(x) for x <= 0
         const float sgn2 = (w2raw > 0.0f) ? 1.0f : (w2raw < 0.0f ? -1.0f : 0.0f);
         dy[N * E + lane] = dpre;                                                    // d hyper_b1
@@ -97,6 +105,7 @@ __global__ void __launch_bounds__(kQmixWarps * 32) qmix_mix_kernel(QmixMixArgs a
         dy[N * E + 2 * E + lane] = (hb2 > 0.0f) ? G * wb2e : 0.0f;                  // d hyper_b2.0 (through relu)
         acc_wb2 += G * fmaxf(hb2, 0.0f);
         acc_bb2 += G;
+#pragma unroll 4
         for (int n = 0; n < N; ++n) {
             const float w1raw = y[n * E + lane];
             const float sgn1 = (w1raw > 0.0f) ? 1.0f : (w1raw < 0.0f ? -1.0f : 0.0f);
@@ -287,7 +296,7 @@ extern "C" int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* 
     a.fc2_w = fc2_w; a.dhext = dhext;
     if (sel) a.sel = select_args(sel, u, q_chosen, q_tc);
     a.g_wb2 = g->wb2; a.g_bb2 = g->bb2; a.scalars = scalars;
-    const size_t dyn = sel ? select_smem(kQmixWarps, d->N, d->A) : 0;
+    const size_t dyn = sel ? select_smem(kQmixWarps, d->N, d->A, sel->hidden_evals != nullptr) : 0;
     if (dyn > kSelectSmemMax) return MARL_EINVAL;
     if (dyn > 40 * 1024) {
         static bool attr_set = false;

@@ -11,36 +11,120 @@ namespace marl {
 constexpr float kNegBig = -9999999.0f;   // algorithm/q_learner.py:105,112,126
 
 struct SelectArgs {
-    const float* q; const float* qn; float* qt; const float* avail_next; const long long* u;
+    float* q; float* qn; float* qt; const float* avail_next; const long long* u;
     float* q_out; float* qt_out; long long* a_star;
+    // heads != 0: q / qn / qt are OUTPUTS too, computed here from the agents' hidden states (q = W2 h + b2,
+    // network/q_network.py:21-22) -- the three [B*L*N, A, H] head GEMMs of the unroll are then not launched
+    int heads;
+    const float* h_e; const float* h_t; const float* h_n;          // hidden of eval(o), target(o_next), eval(o_next)
+    const float* w2; const float* b2; const float* w2t; const float* b2t;
 };
 
 inline SelectArgs select_args(const marl_select_fused* s, const long long* u, float* q_chosen, float* q_tc) {
-    return SelectArgs{s->q_evals, s->q_evals_next, s->q_targets, s->avail_u_next, u, q_chosen, q_tc, s->a_star};
+    SelectArgs a{};
+    a.q = s->q_evals; a.qn = s->q_evals_next; a.qt = s->q_targets; a.avail_next = s->avail_u_next; a.u = u;
+    a.q_out = q_chosen; a.qt_out = q_tc; a.a_star = s->a_star;
+    a.heads = s->hidden_evals != nullptr;
+    a.h_e = s->hidden_evals; a.h_t = s->hidden_targets; a.h_n = s->hidden_evals_next;
+    a.w2 = s->fc2_w; a.b2 = s->fc2_b; a.w2t = s->fc2_w_target; a.b2t = s->fc2_b_target;
+    return a;
 }
-inline bool select_ok(const marl_select_fused* s) { return s->q_evals && s->q_targets && s->avail_u_next; }
-// dynamic shared memory the staging needs for `warps` warps per CTA
-inline size_t select_smem(int warps, int N, int A) { return (size_t)warps * 2 * N * A * sizeof(float); }
+inline bool select_ok(const marl_select_fused* s) {
+    if (!s->q_evals || !s->q_targets || !s->avail_u_next) return false;
+    if (!s->hidden_evals) return true;
+    if (!s->hidden_targets || !s->fc2_w || !s->fc2_b || !s->fc2_w_target || !s->fc2_b_target) return false;
+    if ((s->q_evals_next != nullptr) != (s->hidden_evals_next != nullptr)) return false;
+    return (((uintptr_t)s->hidden_evals | (uintptr_t)s->hidden_targets | (uintptr_t)s->hidden_evals_next |
+             (uintptr_t)s->fc2_w | (uintptr_t)s->fc2_w_target) & 15) == 0;
+}
+constexpr int kHeadLd = MARL_H + 4;    // padded row of the staged head weights / hidden slabs (floats)
+// floats of one warp's staging area: [N, A] slabs (2, or 3 with heads) rounded up to 16 bytes, then (heads) the sample's
+// three hidden slabs [N][kHeadLd]
+__host__ __device__ inline size_t select_warp_floats(int N, int A, bool heads) {
+    const size_t slabs = (((size_t)(heads ? 3 : 2) * N * A) + 3) & ~(size_t)3;
+    return slabs + (heads ? 3 * (size_t)N * kHeadLd : 0);
+}
+// dynamic shared memory for `warps` warps per CTA (+ both head matrices and biases when heads)
+inline size_t select_smem(int warps, int N, int A, bool heads) {
+    return ((size_t)warps * select_warp_floats(N, A, heads) + (heads ? 2 * (size_t)A * (kHeadLd + 1) : 0)) * sizeof(float);
+}
 constexpr size_t kSelectSmemMax = 160 * 1024;
 
+// Block-wide, once per CTA (followed by __syncthreads()): both head matrices + biases into shared memory (read through
+// L1 instead, the 2 A distinct rows a warp touches per load made the kernel 20 us slower).
+// Layout at `dst` (16-byte aligned): w2 [A][kHeadLd] | w2t [A][kHeadLd] | b2 [A] | b2t [A]
+__device__ __forceinline__ void stage_heads(const SelectArgs& s, int A, float* dst) {
+    for (int i = threadIdx.x; i < A * MARL_H; i += blockDim.x) {
+        const int a = i / MARL_H, k = i - a * MARL_H;
+        dst[a * kHeadLd + k] = s.w2[i];
+        dst[(A + a) * kHeadLd + k] = s.w2t[i];
+    }
+    for (int i = threadIdx.x; i < A; i += blockDim.x) {
+        dst[2 * A * kHeadLd + i] = s.b2[i];
+        dst[2 * A * kHeadLd + A + i] = s.b2t[i];
+    }
+}
+
 // stage: 2 * N * A floats of this warp; qc / tc: N floats each of this warp (q_chosen, q_targets_chosen on return)
+// heads: the staged head matrices (stage_heads) when s.heads, else unused.
 __device__ __forceinline__ void warp_select(const SelectArgs& s, long long m, int N, int A, int lane, float* stage,
-                                            float* qc, float* tc) {
+                                            float* qc, float* tc, const float* heads) {
     const int NA = N * A;
     const long long o = m * NA;
     float* sn = stage;
     float* st = stage + NA;
-    for (int i = lane; i < NA; i += 32) {
-        const bool off = s.avail_next[o + i] == 0.0f;
-        float v = s.qt[o + i];
-        if (off) { v = kNegBig; s.qt[o + i] = v; }                     // in place, q_learner.py:105
-        st[i] = v;
-        if (s.qn) sn[i] = off ? kNegBig : s.qn[o + i];                 // :112
+    float* se = stage + 2 * NA;                                        // only with heads
+    if (s.heads) {
+        // the sample's hidden rows first, all loads in flight at once (rows padded: agents land in different banks)
+        constexpr int Q = MARL_H / 4, LQ = kHeadLd / 4;
+        float4* she = (float4*)(stage + ((3 * NA + 3) & ~3));
+        float4* sht = she + N * LQ;
+        float4* shn = sht + N * LQ;
+        const float4* ge = (const float4*)(s.h_e + m * N * MARL_H);
+        const float4* gt = (const float4*)(s.h_t + m * N * MARL_H);
+        const float4* gn = s.h_n ? (const float4*)(s.h_n + m * N * MARL_H) : ge;
+        for (int i = lane; i < N * Q; i += 32) {
+            const int n = i / Q, k = i - n * Q;
+            she[n * LQ + k] = __ldg(ge + i); sht[n * LQ + k] = __ldg(gt + i); shn[n * LQ + k] = __ldg(gn + i);
+        }
+        __syncwarp();
+        for (int i = lane; i < NA; i += 32) {
+            const int n = i / A, a = i - n * A;
+            const float4* w = (const float4*)(heads + a * kHeadLd);
+            const float4* wt = (const float4*)(heads + (A + a) * kHeadLd);
+            const float4* he = she + n * LQ;
+            const float4* ht = sht + n * LQ;
+            const float4* hn = shn + n * LQ;
+            float4 ce = make_float4(0.f, 0.f, 0.f, 0.f), cn = ce, ct = ce;     // 12 independent FMA chains
+#pragma unroll 4
+            for (int k = 0; k < Q; ++k) {
+                const float4 a4 = w[k], b4 = wt[k], e4 = he[k], t4 = ht[k], n4 = hn[k];
+                ce.x = fmaf(a4.x, e4.x, ce.x); ce.y = fmaf(a4.y, e4.y, ce.y); ce.z = fmaf(a4.z, e4.z, ce.z); ce.w = fmaf(a4.w, e4.w, ce.w);
+                cn.x = fmaf(a4.x, n4.x, cn.x); cn.y = fmaf(a4.y, n4.y, cn.y); cn.z = fmaf(a4.z, n4.z, cn.z); cn.w = fmaf(a4.w, n4.w, cn.w);
+                ct.x = fmaf(b4.x, t4.x, ct.x); ct.y = fmaf(b4.y, t4.y, ct.y); ct.z = fmaf(b4.z, t4.z, ct.z); ct.w = fmaf(b4.w, t4.w, ct.w);
+            }
+            float qe = (ce.x + ce.y) + (ce.z + ce.w), qn = (cn.x + cn.y) + (cn.z + cn.w), qt = (ct.x + ct.y) + (ct.z + ct.w);
+            const float be = heads[2 * A * kHeadLd + a], bt = heads[2 * A * kHeadLd + A + a];
+            qe += be; qn += be; qt += bt;
+            const bool off = s.avail_next[o + i] == 0.0f;
+            if (off) qt = kNegBig;                                     // q_learner.py:105
+            s.q[o + i] = qe; s.qt[o + i] = qt;
+            se[i] = qe; st[i] = qt;
+            if (s.qn) { s.qn[o + i] = qn; sn[i] = off ? kNegBig : qn; }     // :110-112 (the masked copy is not kept)
+        }
+    } else {
+        for (int i = lane; i < NA; i += 32) {
+            const bool off = s.avail_next[o + i] == 0.0f;
+            float v = s.qt[o + i];
+            if (off) { v = kNegBig; s.qt[o + i] = v; }                 // in place, q_learner.py:105
+            st[i] = v;
+            if (s.qn) sn[i] = off ? kNegBig : s.qn[o + i];             // :112
+        }
     }
     __syncwarp();
     for (int n = lane; n < N; n += 32) {
         const long long i = m * N + n;
-        const float c = s.q[i * A + s.u[i]];                           // :100
+        const float c = s.heads ? se[n * A + (int)s.u[i]] : s.q[i * A + s.u[i]];   // :100
         int best = 0;
         float tmax = 0.f, tsel = 0.f;
         if (s.qn) {

@@ -143,14 +143,21 @@ struct VdnFusedArgs {
 __global__ void __launch_bounds__(kVdnWarps * 32) vdn_td_fused_kernel(VdnFusedArgs a) {
     pdl_enter();
     __shared__ float ssel[kVdnWarps][3][kVdnMaxAgents];
-    extern __shared__ float ssel_dyn[];
+    extern __shared__ __align__(16) float ssel_dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, N = a.N, A = a.A;
+    const float* heads = nullptr;
+    if (a.sel.q && a.sel.heads) {
+        float* h = ssel_dyn + kVdnWarps * select_warp_floats(N, A, true);
+        stage_heads(a.sel, A, h);
+        heads = h;
+        __syncthreads();
+    }
     float sq = 0.f, msk = 0.f;
     for (long long m = blockIdx.x * kVdnWarps + warp; m < a.M; m += (long long)gridDim.x * kVdnWarps) {
         const float* q = a.q_chosen + m * N;
         const float* qt = a.q_tc + m * N;
         if (a.sel.q) {
-            warp_select(a.sel, m, N, A, lane, ssel_dyn + (size_t)warp * 2 * N * A, ssel[warp][0], ssel[warp][1]);
+            warp_select(a.sel, m, N, A, lane, ssel_dyn + warp * select_warp_floats(N, A, a.sel.heads), ssel[warp][0], ssel[warp][1], heads);
             q = ssel[warp][0]; qt = ssel[warp][1];
         }
         float tot = 0.f, tot_t = 0.f;
@@ -274,7 +281,7 @@ extern "C" int marl_vdn_td_fwd_bwd(const marl_dims* d, float* q_chosen, float* q
                    (const float*)q_targets_chosen, u, r, terminated, padded, gamma, q_tot, q_tot_target, dq, scalars);
     } else {
         if (d->N > kVdnMaxAgents) return MARL_EINVAL;
-        const size_t dyn = sel ? select_smem(kVdnWarps, d->N, d->A) : 0;
+        const size_t dyn = sel ? select_smem(kVdnWarps, d->N, d->A, sel->hidden_evals != nullptr) : 0;
         if (dyn > kSelectSmemMax) return MARL_EINVAL;
         if (dyn > 40 * 1024) {
             static bool attr_set = false;
