@@ -405,10 +405,11 @@ class QLearner:
         # one non-zero per agent row, writes dq . fc2_w itself: no q_select, no dgrad launch
         NA = a.n_agents * a.n_actions
         fc2_w, fc2_wt = self._flat.ptr("agent.fc2.weight"), self._tflat.ptr("agent.fc2.weight")
-        fused_select = a.alg in ("vdn", "qmix") and 64 * NA <= 160 * 1024
+        fuse = a.alg in ("vdn", "qmix") and bool(getattr(a, "fused_mixer_kernel", True))   # False: one kernel per stage
+        fused_select = fuse and 64 * NA <= 160 * 1024
         fused_heads = (fused_select and (8 * (3 * NA + 3 + 3 * a.n_agents * 68) + 2 * a.n_actions * 69) * 4 <= 160 * 1024
                        and fc2_w % 16 == 0 and fc2_wt % 16 == 0)
-        dhext_fused = a.alg in ("vdn", "qmix") and fc2_w % 8 == 0
+        dhext_fused = fuse and fc2_w % 8 == 0
 
         def fill(i, obs, shift, params, h0_from, gates):
             s = arr[i]

@@ -249,6 +249,37 @@ def test_learner_2s3z_shape_vs_oracle(alg, graph):
     _train_compare(args, batch, 3, graph)
 
 
+@pytest.mark.parametrize("alg", ["vdn", "qmix"])
+@pytest.mark.parametrize("double_q", [True, False])
+def test_learner_unfused_mixer_path_vs_oracle_and_fused(alg, double_q):
+    """The fused VDN / QMIX kernel (selection + agent heads + mixer + TD + fc2 data-gradient in one launch) against
+    the one-kernel-per-stage path (marl_q_select, head GEMMs, dgrad GEMM) it replaces: both match the oracle, the
+    integer outputs agree bit for bit and the float ones to rounding."""
+    batch = synthetic_batch(1, 8, 40, 5, 11, 80, 120)
+    out = {}
+    for fused in (True, False):
+        args = PU.make_args(alg, 5, 11, 80, 120, 40)
+        args.double_q = double_q
+        args.fused_mixer_kernel = fused
+        args.cuda_graph = False
+        torch.manual_seed(0)
+        learner, st = PU.build_pair(args)
+        loss = learner.train({k: v.copy() for k, v in batch.items()}, 0)
+        oloss, _ = MO.train_step(st, batch, 0)
+        assert abs(loss - oloss) <= TOL * abs(oloss)
+        ws = learner.last["ws"]
+        out[fused] = (loss, {k: ws[k].clone() for k in ("a_star", "q_chosen", "q_tc", "q_tot", "dhext")},
+                      [q.clone() for q in ws["q"]], learner._flat.grad.clone())
+    (lf, wf, qf, gf), (lu, wu, qu, gu) = out[True], out[False]
+    assert abs(lf - lu) <= 1e-6 * abs(lu)
+    assert torch.equal(wf["a_star"], wu["a_star"])
+    for k in ("q_chosen", "q_tc", "q_tot", "dhext"):
+        assert PU.rel_err(wf[k].reshape(-1), wu[k].reshape(-1)) < 1e-5, k
+    for i in range(3 if double_q else 2):
+        assert PU.rel_err(qf[i].reshape(-1), qu[i].reshape(-1)) < 1e-5
+    assert PU.rel_err(gf, gu) < 1e-5
+
+
 @pytest.mark.parametrize("double_q", [True, False])
 def test_learner_qplex_vs_oracle(double_q):
     """QPLEX at a reduced 3s5z-like shape (8 agents, 14 actions, full-size mixer: 10 heads, embed 64)."""
