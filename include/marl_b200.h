@@ -17,6 +17,8 @@
 #ifndef MARL_B200_H
 #define MARL_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -322,6 +324,34 @@ int marl_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_
                         const float* scalars, float max_norm, float lr, float beta1, float beta2, float eps,
                         int step, int* step_counter /*nullable, device*/, float* partials, float* loss_out,
                         void* stream);
+
+/* ---- data parallel without a library collective: SURVEY.md section 8(e) ----
+ * The one exchange of the data-parallel step -- sum of the flat [grad | loss_sum | mask_sum] buffer over the ranks -- done
+ * INSIDE the clip + optimiser launch over NVLink peer memory (one GPU per process, one node):
+ *   marl_peer_alloc:  cudaMalloc'd, zeroed, cudaIpc-exportable memory; every rank puts its gradient buffer
+ *                     (n + 2 floats) and a flag array (2 * MARL_PEER_MAX_WORLD uint32) there;
+ *   marl_peer_export / _open / _close: the 64-byte cudaIpc handle of an allocation / map a peer's allocation;
+ *   marl_clip_step_peer: what marl_clip_rmsprop_step / marl_clip_adam_step do AFTER an all-reduce, but reading the
+ *     W gradient buffers directly (summed in rank order on every rank: replicas stay bit-identical), between two
+ *     flag barriers ("gradients complete" / "done reading").  n <= 2^18, n % 4 == 0, 16-byte aligned buffers,
+ *     grads == pg->grads[pg->rank].  epoch / error: device words of the caller (zero-initialised); *error becomes 1
+ *     when a peer does not arrive within ~3 s (the step's results are then invalid).  Graph-capturable. */
+#define MARL_PEER_MAX_WORLD 8
+#define MARL_PEER_HANDLE_BYTES 64
+typedef struct marl_peer_group {
+    int world, rank;
+    const float* grads[MARL_PEER_MAX_WORLD];
+    unsigned* flags[MARL_PEER_MAX_WORLD];
+    unsigned* epoch; int* error;
+} marl_peer_group;
+int marl_peer_alloc(size_t bytes, void** ptr);
+int marl_peer_free(void* ptr);
+int marl_peer_export(const void* ptr, unsigned char* handle /* MARL_PEER_HANDLE_BYTES */);
+int marl_peer_open(const unsigned char* handle, void** ptr);
+int marl_peer_close(void* ptr);
+int marl_clip_step_peer(int adam, float* params, float* grads, float* m1, float* m2 /*Adam only*/, long long n,
+                        float max_norm, float lr, float c1 /*alpha | beta1*/, float c2 /*beta2*/, float eps,
+                        int* step_counter /*Adam only, device*/, float* loss_out, const marl_peer_group* pg, void* stream);
 
 /* ---- built-in launch profiler (bench.py roofline leg) ----
  * When enabled, every kernel launch of the library is bracketed by CUDA events on its stream.

@@ -58,6 +58,11 @@ class UnrollBwd(C.Structure):
                 ("grads", AgentGrads), ("dhext_ready", C.c_int)]
 
 
+class PeerGroup(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("grads", c_ptr * 8), ("flags", c_ptr * 8), ("epoch", c_ptr),
+                ("error", c_ptr)]
+
+
 class SelectFused(C.Structure):
     _fields_ = [(k, c_ptr) for k in ("q_evals", "q_evals_next", "q_targets", "avail_u_next", "a_star", "hidden_evals",
                                      "hidden_targets", "hidden_evals_next", "fc2_w", "fc2_b", "fc2_w_target",
@@ -137,6 +142,13 @@ _SIGNATURES = {
     "marl_qmix_bwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams)] + [c_ptr] * 6 + [_P(QmixGrads), c_ptr], C.c_int),
     "marl_qmix_td_fwd_bwd": ([_P(Dims), _P(QmixParams), _P(QmixParams)] + [c_ptr] * 8 + [C.c_float] + [c_ptr] * 6
                              + [_P(QmixGrads), c_ptr, C.c_int, c_ptr, c_ptr, _P(SelectFused), c_ptr], C.c_int),
+    "marl_peer_alloc": ([C.c_size_t, _P(c_ptr)], C.c_int),
+    "marl_peer_free": ([c_ptr], C.c_int),
+    "marl_peer_export": ([c_ptr, C.c_char_p], C.c_int),
+    "marl_peer_open": ([C.c_char_p, _P(c_ptr)], C.c_int),
+    "marl_peer_close": ([c_ptr], C.c_int),
+    "marl_clip_step_peer": ([C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, C.c_longlong] + [C.c_float] * 5
+                            + [c_ptr, c_ptr, _P(PeerGroup), c_ptr], C.c_int),
     "marl_qmix_hyper_fwd": ([C.c_int, C.c_int, C.c_int, _P(QmixParams), c_ptr, c_ptr, c_ptr], C.c_int),
     "marl_qmix_hyper2_fwd": ([C.c_int, C.c_int, C.c_int, _P(QmixHyper2), c_ptr, c_ptr, c_ptr, c_ptr], C.c_int),
     "marl_qmix_hyper2_bwd": ([C.c_int, C.c_int, C.c_int, _P(QmixHyper2), c_ptr, c_ptr, c_ptr, c_ptr, _P(QmixHyper2Grads), c_ptr], C.c_int),

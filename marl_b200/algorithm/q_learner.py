@@ -28,7 +28,7 @@ import torch as th
 
 from .. import _lib as L
 from ..flat import FlatBuffer, prefixed
-from ..parallel import shard_bounds, allreduce_flat
+from ..parallel import shard_bounds, allreduce_flat, PeerGradients
 from ..common.replaybuffer import DeviceEpisodeBatch
 from ..network.mixer import VDNMixer, QMixMixer, qmix_struct, qmix2_struct, qmix_tail_struct, QMIX2_FLAT_ORDER
 from ..network.q_network import agent_param_struct, AGENT_FLAT_ORDER
@@ -94,6 +94,7 @@ class QLearner:
         self._graphs = {}
         self._use_graph = bool(getattr(args, "cuda_graph", True))
         self._dist = None
+        self._peer = None
         self._side = None
         self._copy_stream, self._prefetched, self._slot_free, self._prefetch_seq = None, {}, {}, 0
         self.last = {}
@@ -154,6 +155,15 @@ class QLearner:
         import torch.distributed as dist
         self._dist = (dist, group)
         self._graphs = {}
+        self._peer = None
+        # same node, <= 8 ranks, <= 2^18 parameters: the gradient sum happens inside the optimiser launch over NVLink
+        # peer memory (marl_clip_step_peer) instead of an NCCL call between two graphs
+        if (self._dev.type == "cuda" and dist.get_backend(group) == "nccl" and dist.get_world_size(group) > 1
+                and os.environ.get("MARL_B200_PEER_ALLREDUCE", "1") != "0"):
+            peer = PeerGradients(self._flat.numel, dist, group, self._dev)
+            if peer.ok:
+                self._flat.adopt_grad_storage(peer.grad_full)
+                self._peer = peer
 
     # ---- reference surface: episode-length cut ------------------------------------------------------
     def get_max_episode_len(self, batch):
@@ -523,6 +533,13 @@ class QLearner:
 
     def _launch_optimizer(self):
         a, fl, opt, sp = self.args, self._flat, self.optimizer, L.stream_ptr()
+        if self._peer is not None:
+            adam = opt.kind != "RMS"
+            L.call("marl_clip_step_peer", int(adam), fl.data.data_ptr(), fl.grad.data_ptr(),
+                   (opt.exp_avg if adam else opt.square_avg).data_ptr(), opt.exp_avg_sq.data_ptr() if adam else None,
+                   fl.numel, float(a.grad_norm_clip), float(self.lr), 0.9 if adam else 0.99, 0.999 if adam else 0.0, 1e-8,
+                   opt.step_counter.data_ptr() if adam else None, self._loss_out.data_ptr(), C.byref(self._peer.struct), sp)
+            return 1
         if opt.kind == "RMS":
             L.call("marl_clip_rmsprop_step", fl.data.data_ptr(), fl.grad.data_ptr(), opt.square_avg.data_ptr(), fl.numel,
                    fl.tail.data_ptr(), float(a.grad_norm_clip), float(self.lr), 0.99, 1e-8, self._partials.data_ptr(),
@@ -535,7 +552,7 @@ class QLearner:
         return 1 if fl.numel <= (1 << 18) else 2      # one cluster launch up to 2^18 parameters (csrc/optim.cu)
 
     def _device_step(self, bt, ws, B, Lq):
-        if self._dist is not None:
+        if self._dist is not None and self._peer is None:
             n = self._launch_forward_backward(bt, ws, B, Lq)
             dist, group = self._dist
             allreduce_flat(self._flat.grad_full, dist, group)
@@ -554,7 +571,7 @@ class QLearner:
             self._graphs[key] = "warm"
             return
         if entry == "warm":
-            if self._dist is None:
+            if self._dist is None or self._peer is not None:
                 g = th.cuda.CUDAGraph()
                 with th.cuda.graph(g):
                     self._device_step(bt, ws, B, Lq)
@@ -605,6 +622,8 @@ class QLearner:
         # hidden states as the reference leaves them ([B*N, H], q_learner.py:96-110)
         self.eval_net.hidden_states = ws["h_last"][2 if self.args.double_q else 0]
         self.target_net.hidden_states = ws["h_last"][1]
+        if self._peer is not None and float(self._loss_host[0]) != float(self._loss_host[0]) and int(self._peer.state[1]):
+            raise RuntimeError("marl_clip_step_peer: a data-parallel peer did not reach the gradient exchange in time")
         self.last = dict(B=B, L=Lq, ws=ws, batch=bt, grad_norm=float(self._loss_host[1]))
         return float(self._loss_host[0])
 

@@ -60,6 +60,14 @@ class FlatBuffer:
         src = self.data if source is None else source
         return src.data_ptr() + 4 * self.offsets[name]
 
+    def adopt_grad_storage(self, grad_full):
+        """Move the gradient buffer (numel + tail floats) into caller-provided device memory."""
+        assert grad_full.numel() == self.grad_full.numel() and grad_full.dtype == torch.float32
+        grad_full.zero_()
+        self.grad_full = grad_full
+        self.grad, self.tail = grad_full[:self.numel], grad_full[self.numel:]
+        self.rebind_grads()
+
     def rebind_grads(self):
         """Re-attach p.grad views (optimizer.zero_grad(set_to_none=True) style resets drop them)."""
         for n, p in zip(self.names, self.params):

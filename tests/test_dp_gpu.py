@@ -29,12 +29,14 @@ def _make_learner():
     return learner
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, peer):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["MARL_B200_PEER_ALLREDUCE"] = "1" if peer else "0"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     learner = _make_learner()
     learner.enable_data_parallel()
+    assert (learner._peer is not None) == peer          # the NVLink peer-memory exchange is the one that runs
     batch = synthetic_batch(0, **SHAPE)
     losses = [learner.train({k: v.copy() for k, v in batch.items()}, i) for i in range(4)]   # eager, capture, 2 replays
     ret[rank] = (losses, learner._flat.data.cpu().numpy())
@@ -42,10 +44,13 @@ def _worker(rank, world, port, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_dp_matches_single_gpu():
+@pytest.mark.parametrize("peer", [True, False])
+def test_two_gpu_dp_matches_single_gpu(peer):
+    """peer=True: gradient sum inside the optimiser launch over NVLink peer memory (marl_clip_step_peer, one CUDA
+    graph per step); peer=False: ncclAllReduce between two graphs.  Both: replicas bit-identical, single-GPU results."""
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), ret, peer), nprocs=2, join=True)
     (l0, p0), (l1, p1) = ret[0], ret[1]
     assert l0 == l1 and np.array_equal(p0, p1)          # replicas identical without a broadcast
     single = _make_learner()
