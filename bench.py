@@ -414,6 +414,9 @@ def run_ours(opt):
         "config": {"workload": "QMIX learner step, synthetic 2s3z-shaped batch (5 agents, 11 actions, T=120, "
                                "batch 32 per GPU, RMSprop, double-Q)",
                    "global_batch": B * world, "parallelism": f"dp{world}",
+                   "gradient_exchange": (None if world == 1 else
+                                         "fused into the optimiser launch over NVLink peer memory (marl_clip_step_peer)"
+                                         if getattr(learner, "_peer", None) is not None else "ncclAllReduce between two graphs"),
                    "l2": f"inputs rotate over {NB} resident batches (150 MB > 126 MB L2)"},
         "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "episode-samples/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
