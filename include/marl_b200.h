@@ -335,7 +335,7 @@ int marl_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_
  *     W gradient buffers directly (summed in rank order on every rank: replicas stay bit-identical), between two
  *     flag barriers ("gradients complete" / "done reading").  n <= 2^18, n % 4 == 0, 16-byte aligned buffers,
  *     grads == pg->grads[pg->rank].  epoch / error: device words of the caller (zero-initialised); *error becomes 1
- *     when a peer does not arrive within ~3 s (the step's results are then invalid).  Graph-capturable. */
+ *     when a peer does not arrive within ~30 s (the step's results are then invalid).  Graph-capturable. */
 #define MARL_PEER_MAX_WORLD 8
 #define MARL_PEER_HANDLE_BYTES 64
 typedef struct marl_peer_group {

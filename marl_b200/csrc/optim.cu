@@ -277,7 +277,7 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& pa, int phase, unsi
         const unsigned* mine = pa.flags[pa.rank] + phase * kPeerMaxWorld + t;
         const long long t0 = clock64();
         while ((int)(ld_acquire_sys(mine) - e) < 0) {
-            if (clock64() - t0 > (6LL << 30)) { *pa.error = 1; break; }      // ~3 s: a peer died; fail loudly on the host
+            if (clock64() - t0 > (56LL << 30)) { *pa.error = 1; break; }     // ~30 s: a peer died; fail loudly on the host
         }
         __threadfence_system();
     }

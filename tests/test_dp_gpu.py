@@ -23,18 +23,19 @@ def _free_port():
     return port
 
 
-def _make_learner():
+def _make_learner(optimizer="RMS"):
     args = PU.make_args("qmix", SHAPE["N"], SHAPE["A"], SHAPE["O"], SHAPE["S"], SHAPE["T"])
+    args.optimizer = optimizer
     learner, _ = PU.build_pair(args, seed=0)
     return learner
 
 
-def _worker(rank, world, port, ret, peer):
+def _worker(rank, world, port, ret, peer, optimizer):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     os.environ["MARL_B200_PEER_ALLREDUCE"] = "1" if peer else "0"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    learner = _make_learner()
+    learner = _make_learner(optimizer)
     learner.enable_data_parallel()
     assert (learner._peer is not None) == peer          # the NVLink peer-memory exchange is the one that runs
     batch = synthetic_batch(0, **SHAPE)
@@ -44,16 +45,16 @@ def _worker(rank, world, port, ret, peer):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("peer", [True, False])
-def test_two_gpu_dp_matches_single_gpu(peer):
+@pytest.mark.parametrize("peer,optimizer", [(True, "RMS"), (True, "Adam"), (False, "RMS")])
+def test_two_gpu_dp_matches_single_gpu(peer, optimizer):
     """peer=True: gradient sum inside the optimiser launch over NVLink peer memory (marl_clip_step_peer, one CUDA
     graph per step); peer=False: ncclAllReduce between two graphs.  Both: replicas bit-identical, single-GPU results."""
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), ret, peer), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), ret, peer, optimizer), nprocs=2, join=True)
     (l0, p0), (l1, p1) = ret[0], ret[1]
     assert l0 == l1 and np.array_equal(p0, p1)          # replicas identical without a broadcast
-    single = _make_learner()
+    single = _make_learner(optimizer)
     batch = synthetic_batch(0, **SHAPE)
     ls = [single.train({k: v.copy() for k, v in batch.items()}, i) for i in range(4)]
     assert np.allclose(l0, ls, rtol=1e-5)
