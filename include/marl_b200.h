@@ -107,7 +107,8 @@ typedef struct marl_unroll_stream {
     int h0_from;             /* -1, or index of an earlier stream in the same call */
     const float* h0;         /* [B*N,H] or NULL */
     marl_agent_params params;
-    float* q;                /* out [B,L,N,A] */
+    float* q;                /* out [B,L,N,A], or NULL: skip the fc2 head (a fused mixer evaluates it from `hidden`,
+                                see marl_select_fused) */
     float* hidden;           /* out [B,L,N,H], h after each step */
     float* h_last;           /* out [B*N,H] or NULL */
     float* x;                /* workspace/out [B,L,N,H]: relu(fc1) (needed by the backward) */
