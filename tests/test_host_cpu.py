@@ -77,6 +77,32 @@ def test_flat_layout_concatenates_qmix_heads():
     assert sum(p.numel() for p in learner.params) == 62892
 
 
+def test_gradient_buffer_can_move_to_caller_memory():
+    """Data parallel puts [grad | loss_sum | mask_sum] into cudaIpc-shared memory (parallel.PeerGradients): the
+    parameters' .grad views and the tail must follow, and the fused exchange needs numel % 4 == 0 and <= 2^18."""
+    a = default_args(alg="qmix", n_agents=5, n_actions=11, obs_shape=80, state_shape=120, episode_limit=120)
+    learner = QLearner(SharedMAC(a), a)
+    fl = learner._flat
+    assert fl.numel % 4 == 0 and fl.numel <= (1 << 18) and fl.grad_full.numel() == fl.numel + 2
+    new = torch.full((fl.numel + 2,), 7.0)
+    fl.adopt_grad_storage(new)
+    assert float(new.abs().max()) == 0.0                       # zeroed on adoption
+    assert fl.grad.data_ptr() == new.data_ptr() and fl.tail.data_ptr() == new.data_ptr() + 4 * fl.numel
+    for name, p in zip(fl.names, fl.params):
+        assert p.grad.data_ptr() == new.data_ptr() + 4 * fl.offsets[name] and p.grad.shape == p.shape
+
+
+def test_peer_exchange_rejects_bad_arguments_without_touching_the_gpu():
+    lib = L.load()
+    pg = L.PeerGroup()
+    pg.world, pg.rank = 9, 0                                   # more ranks than MARL_PEER_MAX_WORLD
+    assert lib.marl_clip_step_peer(0, 16, 16, 16, None, 4, 10.0, 5e-4, 0.99, 0.0, 1e-8, None, None,
+                                   ctypes.byref(pg), None) < 0               # MARL_EINVAL
+    assert lib.marl_clip_step_peer(0, None, 16, 16, None, 4, 10.0, 5e-4, 0.99, 0.0, 1e-8, None, None,
+                                   ctypes.byref(pg), None) < 0
+    assert lib.marl_peer_export(None, None) < 0 and lib.marl_peer_open(None, None) < 0
+
+
 def test_reference_checkpoint_keys_load():
     a = default_args(alg="vdn", n_agents=5, n_actions=11, obs_shape=80, state_shape=120, episode_limit=120)
     mac = SharedMAC(a)
