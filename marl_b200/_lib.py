@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmarl_b200.so")
+LIB_PATH = os.environ.get("MARL_B200_LIB") or os.path.join(_HERE, "lib", "libmarl_b200.so")   # override: kernel A/B builds
 
 c_float_p = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 c_ptr = C.c_void_p

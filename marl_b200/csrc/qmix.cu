@@ -16,7 +16,11 @@
 namespace marl {
 
 constexpr int E = MARL_QMIX_EMBED;
-constexpr int kQmixWarps = 8;
+#ifndef MARL_QMIX_WARPS
+#define MARL_QMIX_WARPS 8
+#endif
+constexpr int kQmixWarps = MARL_QMIX_WARPS;        // samples (warps) per CTA
+constexpr int kQmixCtasPerSm = 32 / kQmixWarps;    // 32 resident warps per SM at 64 registers
 constexpr int kQmixMaxAgents = 64;
 
 enum { QMIX_FWD = 0, QMIX_BWD = 1, QMIX_TD = 2 };
@@ -51,7 +55,7 @@ __device__ __forceinline__ float qmix_forward_lane(const float* __restrict__ y, 
     return warp_sum(part) + bb2;
 }
 
-__global__ void __launch_bounds__(kQmixWarps * 32, 4) qmix_mix_kernel(QmixMixArgs a) {
+__global__ void __launch_bounds__(kQmixWarps * 32, kQmixCtasPerSm) qmix_mix_kernel(QmixMixArgs a) {
     pdl_enter();
     __shared__ float sdq[kQmixWarps][kQmixMaxAgents];
     __shared__ float sred[kQmixWarps][E + 1];
@@ -223,7 +227,7 @@ static int hyper2_bwd(int M, int N, int S, const marl_qmix_hyper2* p, const floa
 
 static int mix_grid(int M) {
     int blocks = (M + kQmixWarps - 1) / kQmixWarps;
-    return blocks < 1 ? 1 : (blocks > 4 * kNumSMs ? 4 * kNumSMs : blocks);
+    return blocks < 1 ? 1 : (blocks > kQmixCtasPerSm * kNumSMs ? kQmixCtasPerSm * kNumSMs : blocks);
 }
 
 }  // namespace marl
