@@ -22,7 +22,13 @@ namespace marl {
 constexpr int kMaxStreams = 4;
 constexpr int kGruPrio = -1;        // launch priority of the recurrence kernels (see launch_pdl_prio)
 constexpr int kGruThreads = 128;   // 64 hidden units x 2-way split of the reduction, one warp per SM sub-partition
-constexpr int kGiDepth = 4;        // cp.async ring depth (time steps) of the forward's input gates
+#ifndef MARL_GI_DEPTH
+#define MARL_GI_DEPTH 4
+#endif
+#ifndef MARL_BWD_DEPTH
+#define MARL_BWD_DEPTH 6
+#endif
+constexpr int kGiDepth = MARL_GI_DEPTH;   // cp.async ring depth (time steps) of the forward's input gates
 
 // MUFU-based gate non-linearities: ex2.approx / rcp.approx are accurate to ~2 ulp, i.e. <= 2e-7 absolute on
 // the (0,1) / (-1,1) outputs -- the same order as the fp32 rounding of the reference's own libm path.
@@ -241,7 +247,7 @@ struct GruBwdArgs {
 };
 
 constexpr int kBwdSlot = 7 * MARL_H;     // r, z, n, gh_n (4H) | h_prev | dh_ext | dh_ext2   per row and time step
-constexpr int bwd_depth(int R) { return R >= 8 ? 3 : 6; }
+constexpr int bwd_depth(int R) { return R >= 8 ? 3 : MARL_BWD_DEPTH; }
 constexpr size_t gru_bwd_smem(int R) { return (size_t)(2 * R * MARL_G + bwd_depth(R) * R * kBwdSlot) * sizeof(float); }
 
 template <int R>
