@@ -110,39 +110,94 @@ def oracle_state(args, seed=0):
     return MO, MO.LearnerState(cfg)
 
 
-def time_cpu_reference(steps, warmup, threads=None):
-    """The reference algorithm's CPU path (oracle port: same per-timestep torch op sequence as
-    controller/share_params.py + algorithm/q_learner.py) on the host cores."""
+WORKLOAD = ("QMIX learner step, synthetic 2s3z-shaped batch (5 agents, 11 actions, T=120, batch 32 per GPU, RMSprop, "
+            "double-Q)")
+
+
+def host_threads():
+    """All the host cores this process may use, whatever OMP_NUM_THREADS torchrun exported."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_learner(alg, shape, cuda=False, seed=0):
+    """The UNMODIFIED reference (oracle/_ref, staged by oracle/fetch_ref.py) when it travelled with the snapshot,
+    else the oracle port of its CPU path.  Returns (train_fn(batch, step) -> loss, kind)."""
+    import torch
+    from oracle import fetch_ref as FR
+    if FR.available():
+        ns = FR.load()
+        a = FR.make_args(ns, alg, shape["N"], shape["A"], shape["O"], shape["S"], shape["T"], cuda=cuda)
+        torch.manual_seed(seed)
+        mac = ns.SharedMAC(a)
+        learner = (ns.QTRANLearner if alg == "qtran_base" else ns.QLearner)(mac, a)
+        return (lambda batch, step: learner.train({k: v.copy() for k, v in batch.items()}, step)), "reference"
+    if cuda:
+        return None, "port"
+    from marl_b200.common.arguments import default_args
+    args = default_args(alg=alg, n_agents=shape["N"], n_actions=shape["A"], obs_shape=shape["O"], state_shape=shape["S"],
+                        episode_limit=shape["T"], map="synthetic")
+    MO, st = oracle_state(args, seed)
+    return (lambda batch, step: MO.train_step(st, batch, step)[0]), "port"
+
+
+def time_reference(steps, warmup, alg="qmix", shape=None, cuda=False):
+    """episode-samples/s of the reference's own train() on the host cores (or, cuda=True, on this GPU with stock ATen
+    kernels: the same-box GPU baseline of SURVEY.md section 8(c))."""
     import torch
     from marl_b200.synthetic import synthetic_batch
-    if threads:
-        torch.set_num_threads(threads)
-    MO, st = oracle_state(make_args())
-    batch = synthetic_batch(0, **SHAPE)
+    shape = shape or SHAPE
+    torch.set_num_threads(host_threads())
+    train, kind = reference_learner(alg, shape, cuda=cuda)
+    if train is None:
+        return None
+    batch = synthetic_batch(0, **shape)
     for i in range(warmup):
-        MO.train_step(st, batch, i)
+        train(batch, i)
+    if cuda:
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(steps):
-        MO.train_step(st, batch, warmup + i)
+        train(batch, warmup + i)          # returns loss.item(): synchronises every step, like the reference's caller
+    if cuda:
+        torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    return SHAPE["B"] * steps / dt, dt / steps, torch.get_num_threads()
+    return {"value": shape["B"] * steps / dt, "unit": "episode-samples/s", "ms_per_step": dt / steps * 1e3, "kind": kind,
+            "cores": torch.get_num_threads(), "steps": steps, "warmup": warmup}
 
 
 def run_reference(opt):
+    """--impl reference: the reference's own QLearner.train on this box's host cores (rank 0 only), plus the same
+    code with args.cuda=True on GPU 0 as `gpu_baseline`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = min(opt.steps, 30)
-    val, per, cores = time_cpu_reference(steps, min(opt.warmup, 3))
-    line = {"impl": "reference", "metric": "QMIX learner episode-samples/sec (2s3z shape)", "value": val,
-            "unit": "episode-samples/s", "n_gpus": opt.gpus, "steps": steps, "warmup": min(opt.warmup, 3),
-            "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "QMIX learner step, synthetic 2s3z-shaped batch (5 agents, 11 actions, T=120, batch 32)"},
-            "cpu_baseline": {"value": val, "unit": "episode-samples/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} train steps of the B=32 batch; oracle port of the reference's CPU path "
-                                       "(the Python reference cannot travel to the GPU box)"},
-            "e2e": {"value": val, "unit": "episode-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    import torch
+    steps, warm = max(1, min(opt.steps, 30)), max(1, min(opt.warmup, 3))
+    r = time_reference(steps, warm)
+    sample = (f"{steps} train steps (after {warm} warm-up) of one B=32 synthetic 2s3z-shaped batch through "
+              + ("the UNMODIFIED reference QLearner.train (oracle/_ref), args.cuda=False" if r["kind"] == "reference"
+                 else "the oracle port of the reference's CPU path (oracle/_ref was not staged)")
+              + f", torch.set_num_threads({r['cores']})")
+    gpu = None
+    if torch.cuda.is_available() and r["kind"] == "reference":
+        try:
+            g = time_reference(10, 3, cuda=True)
+            gpu = {"value": g["value"], "unit": g["unit"], "ms_per_step": g["ms_per_step"],
+                   "what": "UNMODIFIED reference QLearner.train with args.cuda=True on this GPU (stock ATen / cuBLAS kernels; "
+                           "o / o_next / avail stay on the host as in controller/share_params.py:132-134)", "steps": 10}
+        except Exception as e:      # noqa: BLE001
+            gpu = {"unavailable": repr(e)[:200]}
+    line = {"impl": "reference", "metric": "QMIX learner episode-samples/sec (2s3z shape)", "value": r["value"],
+            "unit": "episode-samples/s", "n_gpus": opt.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": r["value"], "unit": "episode-samples/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": sample},
+            "gpu_baseline": gpu,
+            "e2e": {"value": r["value"], "unit": "episode-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 

@@ -354,6 +354,29 @@ int marl_clip_step_peer(int adam, float* params, float* grads, float* m1, float*
                         float max_norm, float lr, float c1 /*alpha | beta1*/, float c2 /*beta2*/, float eps,
                         int* step_counter /*Adam only, device*/, float* loss_out, const marl_peer_group* pg, void* stream);
 
+/* ---- dense-layer primitives (nn.Linear and its autograd duals) ----
+ * The operators above call these internally; they are exported for the parity tests and tools/gemm_bench.py.
+ * Row-major fp32 operands with explicit pitches (in floats), 3xTF32 on the tensor cores (csrc/tgemm.cu when the
+ * operands are TMA-addressable, csrc/linear.cu otherwise).  Replace torch.nn.functional.linear and its backward
+ * (network/q_network.py:17,20; network/mixer.py:45-55):
+ *   marl_linear_fwd  : y[M,N]   = act(x[M,K] . w[N,K]^T + bias[N])        (bias nullable, relu 0/1)
+ *   marl_linear_dgrad: dx[M,K]  = (dy[M,N] . w[N,K]) * (relu_src[M,K] > 0) (relu_src nullable)
+ *   marl_linear_wgrad: dw[N,K] += dy[M,N]^T . x[M,K] ; db[N] += column sums of dy (db nullable)
+ * marl_set_scratch registers a caller-owned device arena (>= 64 MB recommended) for the split weight-gradient
+ * partials; without it the weight gradients fall back to the atomic kernels of csrc/linear.cu. */
+int marl_set_scratch(void* device_ptr, size_t bytes);
+/* routes the TMA-addressable dense layers through csrc/tgemm.cu (1) or csrc/linear.cu (0, default; env MARL_B200_TGEMM);
+ * returns the previous setting.  Captured CUDA graphs keep the path they were captured with. */
+int marl_tgemm_enable(int on);
+/* debug: (tag, clock64) phase trace of CTA 0 of the following tgemm launches; see tools/gemm_trace.py */
+int marl_tgemm_trace(int on, long long* host_out /* 2048 words or NULL */);
+int marl_linear_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
+                    int M, int N, int K, int relu, void* stream);
+int marl_linear_dgrad(const float* dy, int lddy, const float* w, int ldw, const float* relu_src, int ldrs, float* dx,
+                      int lddx, int M, int N, int K, void* stream);
+int marl_linear_wgrad(const float* dy, int lddy, const float* x, int ldx, float* dw, int ldw, float* db, int M, int N,
+                      int K, void* stream);
+
 /* ---- built-in launch profiler (bench.py roofline leg) ----
  * When enabled, every kernel launch of the library is bracketed by CUDA events on its stream.
  * marl_profile_collect synchronises the device and writes "kernel,count,total_ms\n" lines. */

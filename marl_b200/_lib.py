@@ -165,6 +165,12 @@ _SIGNATURES = {
     "marl_qtran_select": ([_P(Dims)] + [c_ptr] * 10 + [c_ptr], C.c_int),
     "marl_qtran_losses_fwd_bwd": ([_P(Dims)] + [c_ptr] * 12 + [C.c_float] * 3 + [c_ptr] * 5 + [c_ptr], C.c_int),
     "marl_epsgreedy_select": ([C.c_int, C.c_int] + [c_ptr] * 6 + [c_ptr], C.c_int),
+    "marl_set_scratch": ([c_ptr, C.c_size_t], C.c_int),
+    "marl_tgemm_trace": ([C.c_int, c_ptr], C.c_int),
+    "marl_tgemm_enable": ([C.c_int], C.c_int),
+    "marl_linear_fwd": ([c_ptr, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int] + [C.c_int] * 4 + [c_ptr], C.c_int),
+    "marl_linear_dgrad": ([c_ptr, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int] + [C.c_int] * 3 + [c_ptr], C.c_int),
+    "marl_linear_wgrad": ([c_ptr, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int, c_ptr] + [C.c_int] * 3 + [c_ptr], C.c_int),
     "marl_optim_partials": ([], C.c_int),
     "marl_spin_us": ([C.c_int, c_ptr], C.c_int),
     "marl_profile_enable": ([C.c_int], C.c_int),
@@ -224,6 +230,21 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+_scratch = {}
+
+
+def ensure_scratch(nbytes=None):
+    """One process-wide device arena per GPU for the split weight-gradient partials (csrc/tgemm.cu); never freed, so
+    captured CUDA graphs that baked its addresses stay valid for the life of the process."""
+    dev = torch.cuda.current_device()
+    if dev not in _scratch:
+        nbytes = nbytes or int(os.environ.get("MARL_B200_SCRATCH_MB", "512")) << 20
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{dev}")
+        check(load().marl_set_scratch(buf.data_ptr(), nbytes), "marl_set_scratch")
+        _scratch[dev] = buf
+    return _scratch[dev]
+
+
 def profile(on):
     load().marl_profile_enable(1 if on else 0)
 
@@ -251,4 +272,6 @@ def profile_timeline():
 
 
 def call(name, *args):
+    if not _scratch and torch.cuda.is_available():
+        ensure_scratch()
     check(getattr(load(), name)(*args), name)

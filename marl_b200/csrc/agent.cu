@@ -13,6 +13,7 @@
 // dependent ones (the double-Q eval unroll on o_next that starts from the final hidden of the
 // eval unroll on o, algorithm/q_learner.py:96,110) are chained inside the same CTA.
 #include "linear.h"
+#include "tgemm.h"
 #include "forkjoin.h"
 #include "../../include/marl_b200.h"
 #include "profile.h"
@@ -470,27 +471,52 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         if (!s[i].obs || (!s[i].onehot && !s[i].full_input) || !s[i].hidden || !s[i].x || !s[i].gi) return MARL_EINVAL;
         if (s[i].h0_from >= i) return MARL_EINVAL;
     }
-    // phase A: the streams are independent -> one lane each
-    ForkJoin fa(st, n_streams);
-    {
-        LinearPrio prio_(kGruPrio);   // placed ahead of the GEMMs other streams issue at the same moment (the mixer's hyper-networks)
-        for (int i = 0; i < n_streams; ++i) {
-            cudaStream_t st = fa.lane(i);
-            LinearFwd f{};
-            f.in = agent_input(d, s[i].obs, s[i].onehot, s[i].shift_onehot, s[i].full_input);
-            f.w = s[i].params.fc1_w; f.ldw = I; f.bias = s[i].params.fc1_b;
-            f.y = s[i].x; f.ldy = MARL_H; f.M = rows_total; f.N = MARL_H; f.relu = 1; f.batch = 1;
-            int rc = linear_fwd(f, st);
+    // phase A: x = relu(fc1(input)), gi = W_ih x + b_ih for every stream
+    auto fc1_of = [&](int i) {
+        LinearFwd f{};
+        f.in = agent_input(d, s[i].obs, s[i].onehot, s[i].shift_onehot, s[i].full_input);
+        f.w = s[i].params.fc1_w; f.ldw = I; f.bias = s[i].params.fc1_b;
+        f.y = s[i].x; f.ldy = MARL_H; f.M = rows_total; f.N = MARL_H; f.relu = 1; f.batch = 1;
+        return f;
+    };
+    auto ih_of = [&](int i) {
+        LinearFwd g{};
+        g.in = plain_operand(s[i].x, MARL_H, MARL_H);
+        g.w = s[i].params.w_ih; g.ldw = MARL_H; g.bias = s[i].params.b_ih;
+        g.y = s[i].gi; g.ldy = MARL_G; g.M = rows_total; g.N = MARL_G; g.batch = 1;
+        return g;
+    };
+    bool grouped = false;
+    if (tgemm_enabled()) {
+        // TMA path: the streams of one layer are ONE grouped launch of persistent CTAs (csrc/tgemm.cu): 2 launches
+        // instead of 2 x n_streams on forked streams
+        TGBuilder b1, b2;
+        bool ok = true;
+        for (int i = 0; i < n_streams && ok; ++i) ok = b1.add_fwd(fc1_of(i));
+        for (int i = 0; i < n_streams && ok; ++i) ok = b2.add_fwd(ih_of(i));
+        if (ok) {
+            LinearPrio prio_(kGruPrio);
+            int rc = b1.launch(st);
             if (rc) return rc;
-            LinearFwd g{};
-            g.in = plain_operand(s[i].x, MARL_H, MARL_H);
-            g.w = s[i].params.w_ih; g.ldw = MARL_H; g.bias = s[i].params.b_ih;
-            g.y = s[i].gi; g.ldy = MARL_G; g.M = rows_total; g.N = MARL_G; g.batch = 1;
-            rc = linear_fwd(g, st);
-            if (rc) return rc;
+            if ((rc = b2.launch(st))) return rc;
+            grouped = true;
         }
     }
-    fa.join();
+    if (!grouped) {
+        // the streams are independent -> one lane each
+        ForkJoin fa(st, n_streams);
+        {
+            LinearPrio prio_(kGruPrio);   // placed ahead of the GEMMs other streams issue at the same moment (the mixer's hyper-networks)
+            for (int i = 0; i < n_streams; ++i) {
+                cudaStream_t st = fa.lane(i);
+                int rc = linear_fwd(fc1_of(i), st);
+                if (rc) return rc;
+                rc = linear_fwd(ih_of(i), st);
+                if (rc) return rc;
+            }
+        }
+        fa.join();
+    }
     // phase B: build chains (a stream whose h0_from == j continues chain of j; j must be a chain tail)
     GruFwdArgs ga{};
     ga.B = d->B; ga.L = d->L; ga.N = d->N;
@@ -576,53 +602,60 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
         pdl_small_problem() = keep_;
     }
     MARL_LAUNCH_CHECK();
-    // the four weight gradients and the dx chain are independent: fan them out
-    ForkJoin fb(st, 4);
-    if (a->dq) {   // dW2 += dq^T h ; db2 += colsum(dq)
-        cudaStream_t st = fb.lane(3);
-        LinearWgrad w{};
-        w.dy = a->dq; w.lddy = d->A; w.in = plain_operand(a->hidden, MARL_H, MARL_H);
-        w.dw = a->grads.fc2_w; w.ldw = MARL_H; w.db = a->grads.fc2_b; w.M = rows_total; w.N = d->A; w.batch = 1;
-        if ((rc = linear_wgrad(w, st))) return rc;
-    }
-    {   // dW_hh += dgh^T . h_{t-1} (hidden shifted by one step, zeros at t = 0) ; db_hh
-        cudaStream_t st = fb.lane(1);
-        LinearWgrad w{};
-        w.dy = a->dgh; w.lddy = MARL_G;
+    LinearWgrad w_fc2{}, w_hh{}, w_ih{}, w_fc1{}, w_h0{};
+    LinearDgrad g_dx{};
+    // dW2 += dq^T h ; db2 += colsum(dq)
+    w_fc2.dy = a->dq; w_fc2.lddy = d->A; w_fc2.in = plain_operand(a->hidden, MARL_H, MARL_H);
+    w_fc2.dw = a->grads.fc2_w; w_fc2.ldw = MARL_H; w_fc2.db = a->grads.fc2_b; w_fc2.M = rows_total; w_fc2.N = d->A; w_fc2.batch = 1;
+    // dW_hh += dgh^T . h_{t-1} (hidden shifted by one step, zeros at t = 0) ; db_hh
+    w_hh.dy = a->dgh; w_hh.lddy = MARL_G;
+    {
         LinOperand in{};
         in.x = nullptr; in.K1 = 0; in.x2 = a->hidden; in.ldx2 = MARL_H; in.K2 = MARL_H;
         in.x2_shift = d->N; in.x2_period = d->L * d->N; in.onehot_mod = 0;
-        w.in = in;
-        w.dw = a->grads.w_hh; w.ldw = MARL_H; w.db = a->grads.b_hh; w.M = rows_total; w.N = MARL_G; w.batch = 1;
-        if ((rc = linear_wgrad(w, st))) return rc;
-        if (a->h0) {   // the t = 0 rows see h0 instead of zeros: one [N x H] problem per episode
-            LinearWgrad w0{};
-            w0.dy = a->dgh; w0.lddy = MARL_G; w0.dy_bs = (long long)d->L * d->N * MARL_G;
-            w0.in = plain_operand(a->h0, MARL_H, MARL_H, (long long)d->N * MARL_H);
-            w0.dw = a->grads.w_hh; w0.ldw = MARL_H; w0.db = nullptr; w0.M = d->N; w0.N = MARL_G; w0.batch = d->B;
-            if ((rc = linear_wgrad(w0, st))) return rc;
+        w_hh.in = in;
+    }
+    w_hh.dw = a->grads.w_hh; w_hh.ldw = MARL_H; w_hh.db = a->grads.b_hh; w_hh.M = rows_total; w_hh.N = MARL_G; w_hh.batch = 1;
+    // the t = 0 rows see h0 instead of zeros: one [N x H] problem per episode
+    w_h0.dy = a->dgh; w_h0.lddy = MARL_G; w_h0.dy_bs = (long long)d->L * d->N * MARL_G;
+    w_h0.in = plain_operand(a->h0, MARL_H, MARL_H, (long long)d->N * MARL_H);
+    w_h0.dw = a->grads.w_hh; w_h0.ldw = MARL_H; w_h0.db = nullptr; w_h0.M = d->N; w_h0.N = MARL_G; w_h0.batch = d->B;
+    // dW_ih += dgi^T . x ; db_ih
+    w_ih.dy = a->dgi; w_ih.lddy = MARL_G; w_ih.in = plain_operand(a->x, MARL_H, MARL_H);
+    w_ih.dw = a->grads.w_ih; w_ih.ldw = MARL_H; w_ih.db = a->grads.b_ih; w_ih.M = rows_total; w_ih.N = MARL_G; w_ih.batch = 1;
+    // dx = (dgi . W_ih) * (x > 0)
+    g_dx.dy = a->dgi; g_dx.lddy = MARL_G; g_dx.w = a->params.w_ih; g_dx.ldw = MARL_H; g_dx.w_col0 = 0;
+    g_dx.dx = a->dx; g_dx.lddx = MARL_H; g_dx.relu_src = a->x; g_dx.ldrs = MARL_H;
+    g_dx.M = rows_total; g_dx.N = MARL_G; g_dx.K = MARL_H; g_dx.batch = 1;
+    // dW1 += dx^T . [obs | last_action | agent_id] ; db1
+    w_fc1.dy = a->dx; w_fc1.lddy = MARL_H; w_fc1.in = agent_input(d, a->obs, a->onehot, a->shift_onehot, a->full_input);
+    w_fc1.dw = a->grads.fc1_w; w_fc1.ldw = I; w_fc1.db = a->grads.fc1_b; w_fc1.M = rows_total; w_fc1.N = MARL_H; w_fc1.batch = 1;
+
+    if (tgemm_enabled()) {
+        // TMA path (csrc/tgemm.cu): the data gradient and the three weight gradients that only need the BPTT's outputs are
+        // ONE grouped launch, the fc1 weight gradient (needs dx) a second, and one deterministic reduce folds every
+        // split partial into the flat gradient
+        TGBuilder bA, bB;
+        bool ok = bA.add_dgrad(g_dx) && bA.add_wgrad(w_ih) && bA.add_wgrad(w_hh);
+        if (ok && a->dq) ok = bA.add_wgrad(w_fc2);
+        ok = ok && bB.add_wgrad(w_fc1);
+        if (ok) {
+            if ((rc = bA.launch(st))) return rc;
+            if ((rc = bB.launch(st))) return rc;
+            bA.move_reduce_to(bB);
+            if ((rc = bB.launch_reduce(st))) return rc;
+            if (a->h0 && (rc = linear_wgrad(w_h0, st))) return rc;
+            return MARL_OK;
         }
     }
-    {   // dW_ih += dgi^T . x ; db_ih
-        cudaStream_t st = fb.lane(2);
-        LinearWgrad w{};
-        w.dy = a->dgi; w.lddy = MARL_G; w.in = plain_operand(a->x, MARL_H, MARL_H);
-        w.dw = a->grads.w_ih; w.ldw = MARL_H; w.db = a->grads.b_ih; w.M = rows_total; w.N = MARL_G; w.batch = 1;
-        if ((rc = linear_wgrad(w, st))) return rc;
-    }
-    {   // dx = (dgi . W_ih) * (x > 0)
-        LinearDgrad g{};
-        g.dy = a->dgi; g.lddy = MARL_G; g.w = a->params.w_ih; g.ldw = MARL_H; g.w_col0 = 0;
-        g.dx = a->dx; g.lddx = MARL_H; g.relu_src = a->x; g.ldrs = MARL_H;
-        g.M = rows_total; g.N = MARL_G; g.K = MARL_H; g.batch = 1;
-        if ((rc = linear_dgrad(g, st))) return rc;
-    }
-    {   // dW1 += dx^T . [obs | last_action | agent_id] ; db1
-        LinearWgrad w{};
-        w.dy = a->dx; w.lddy = MARL_H; w.in = agent_input(d, a->obs, a->onehot, a->shift_onehot, a->full_input);
-        w.dw = a->grads.fc1_w; w.ldw = I; w.db = a->grads.fc1_b; w.M = rows_total; w.N = MARL_H; w.batch = 1;
-        if ((rc = linear_wgrad(w, st))) return rc;
-    }
+    // the four weight gradients and the dx chain are independent: fan them out
+    ForkJoin fb(st, 4);
+    if (a->dq && (rc = linear_wgrad(w_fc2, fb.lane(3)))) return rc;
+    if ((rc = linear_wgrad(w_hh, fb.lane(1)))) return rc;
+    if (a->h0 && (rc = linear_wgrad(w_h0, fb.lane(1)))) return rc;
+    if ((rc = linear_wgrad(w_ih, fb.lane(2)))) return rc;
+    if ((rc = linear_dgrad(g_dx, st))) return rc;
+    if ((rc = linear_wgrad(w_fc1, st))) return rc;
     fb.join();
     return MARL_OK;
 }

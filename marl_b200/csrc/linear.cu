@@ -13,6 +13,7 @@
 // They replace the cuBLAS addmm calls behind nn.Linear in the reference (network/q_network.py:17,20;
 // network/mixer.py:45-55,117-145,200-206,365-375,399-409) and their autograd duals.
 #include "linear.h"
+#include "tgemm.h"
 #include "profile.h"
 
 namespace marl {
@@ -520,6 +521,7 @@ static bool vec_ok_mat(const float* p, int ld, long long bs, int col0 = 0) {
 
 int linear_fwd(const LinearFwd& a, cudaStream_t st) {
     if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return MARL_OK;
+    { TGBuilder tg; if (tg.add_fwd(a)) return tg.launch(st); }       // TMA-addressable operands: tgemm.cu
     dim3 grid(cdiv(a.M, UM), cdiv(a.N, UN), a.batch);
     const bool va = vec_ok_lin(a.in), vb = vec_ok_mat(a.w, a.ldw, a.w_bs);
     { if (prof_enabled()) prof_note(a.M, a.N, lin_width(a.in)); ProfScope ps_("linear_fwd_kernel", st); MARL_DISPATCH2(linear_fwd_kernel, va, vb, grid, st, a); }
@@ -529,6 +531,7 @@ int linear_fwd(const LinearFwd& a, cudaStream_t st) {
 
 int linear_dgrad(const LinearDgrad& a, cudaStream_t st) {
     if (a.M <= 0 || a.K <= 0 || a.batch <= 0) return MARL_OK;
+    { TGBuilder tg; if (tg.add_dgrad(a)) return tg.launch(st); }
     dim3 grid(cdiv(a.M, UM), cdiv(a.K, UN), a.batch);
     const bool va = vec_ok_mat(a.dy, a.lddy, a.dy_bs), vb = vec_ok_mat(a.w, a.ldw, a.w_bs, a.w_col0);
     { if (prof_enabled()) prof_note(a.M, a.K, a.N); ProfScope ps_("linear_dgrad_kernel", st); MARL_DISPATCH2(linear_dgrad_kernel, va, vb, grid, st, a); }
@@ -538,6 +541,10 @@ int linear_dgrad(const LinearDgrad& a, cudaStream_t st) {
 
 int linear_wgrad(const LinearWgrad& a, cudaStream_t st) {
     if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return MARL_OK;
+    {
+        TGBuilder tg;
+        if (tg.add_wgrad(a)) { const int rc = tg.launch(st); return rc ? rc : tg.launch_reduce(st); }
+    }
     const int K = lin_width(a.in);
     const int tiles = cdiv(a.N, UM) * cdiv(K, UN) * a.batch;
     int splits = cdiv(2 * kNumSMs, tiles);
