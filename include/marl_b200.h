@@ -354,6 +354,10 @@ int marl_clip_step_peer(int adam, float* params, float* grads, float* m1, float*
                         float max_norm, float lr, float c1 /*alpha | beta1*/, float c2 /*beta2*/, float eps,
                         int* step_counter /*Adam only, device*/, float* loss_out, const marl_peer_group* pg, void* stream);
 
+/* 1 when the fused VDN (qmix = 0) / QMIX (qmix = 1) mixing kernel can stage the action selection (heads = 0) or the
+ * selection plus the agents' fc2 heads (heads = 1) of an [N, A] problem in shared memory. */
+int marl_select_fits(int qmix, int N, int A, int heads);
+
 /* ---- dense-layer primitives (nn.Linear and its autograd duals) ----
  * The operators above call these internally; they are exported for the parity tests and tools/gemm_bench.py.
  * Row-major fp32 operands with explicit pitches (in floats), 3xTF32 on the tensor cores (csrc/tgemm.cu when the

@@ -165,6 +165,7 @@ _SIGNATURES = {
     "marl_qtran_select": ([_P(Dims)] + [c_ptr] * 10 + [c_ptr], C.c_int),
     "marl_qtran_losses_fwd_bwd": ([_P(Dims)] + [c_ptr] * 12 + [C.c_float] * 3 + [c_ptr] * 5 + [c_ptr], C.c_int),
     "marl_epsgreedy_select": ([C.c_int, C.c_int] + [c_ptr] * 6 + [c_ptr], C.c_int),
+    "marl_select_fits": ([C.c_int] * 4, C.c_int),
     "marl_set_scratch": ([c_ptr, C.c_size_t], C.c_int),
     "marl_tgemm_trace": ([C.c_int, c_ptr], C.c_int),
     "marl_tgemm_enable": ([C.c_int], C.c_int),

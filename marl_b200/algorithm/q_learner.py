@@ -155,6 +155,9 @@ class QLearner:
         import torch.distributed as dist
         self._dist = (dist, group)
         self._graphs = {}
+        if self._peer is not None:      # called again: release the previous IPC mappings first
+            self._flat.adopt_grad_storage(th.zeros_like(self._flat.grad_full))
+            self._peer.close()
         self._peer = None
         # same node, <= 8 ranks, <= 2^18 parameters: the gradient sum happens inside the optimiser launch over NVLink
         # peer memory (marl_clip_step_peer) instead of an NCCL call between two graphs
@@ -252,7 +255,10 @@ class QLearner:
             self._copy_stream = th.cuda.Stream()
         slot = 1 + (self._prefetch_seq & 1)
         self._prefetch_seq += 1
-        cur = th.cuda.current_stream()
+        # two staging slots = at most two outstanding prefetches: whatever still claims this slot (a batch that was
+        # prefetched and never trained) is dropped, so a stale entry can never be handed to a later train() call
+        for key in [k for k, e in self._prefetched.items() if e["slot"] == slot]:
+            del self._prefetched[key]
         free_ev = self._slot_free.get(slot)
         with th.cuda.stream(self._copy_stream):
             if free_ev is not None:
@@ -261,11 +267,14 @@ class QLearner:
             up["ready"] = th.cuda.Event()
             up["ready"].record(self._copy_stream)
         up["slot"] = slot
+        up["batch"] = batch          # keeps the dict alive: its id() cannot be recycled while the entry exists
         self._prefetched[id(batch)] = up
 
     def _stage_host_batch(self, batch):
         """numpy (float64, [B, T_src, ...]) -> H2D (or a prefetched copy) -> marl_ingest_f64 -> fp32 working set."""
         up = self._prefetched.pop(id(batch), None)
+        if up is not None and up.get("batch") is not batch:
+            up = None
         cur = th.cuda.current_stream()
         if up is not None:
             cur.wait_event(up["ready"])
@@ -336,6 +345,7 @@ class QLearner:
     def _stage_replay_batch(self, batch):
         """``ReplayBuffer.sample()`` of the device-resident buffer (common/replaybuffer.py) -> working set: the
         sampled ring rows are gathered and cut to the batch's max episode length in ONE launch."""
+        batch.check_fresh()
         ring, Lq = batch.ring, batch.max_episode_len
         B_glob = int(batch.idx.shape[0])
         lo, hi = self._shard(B_glob)
@@ -416,9 +426,9 @@ class QLearner:
         NA = a.n_agents * a.n_actions
         fc2_w, fc2_wt = self._flat.ptr("agent.fc2.weight"), self._tflat.ptr("agent.fc2.weight")
         fuse = a.alg in ("vdn", "qmix") and bool(getattr(a, "fused_mixer_kernel", True))   # False: one kernel per stage
-        fused_select = fuse and 64 * NA <= 160 * 1024
-        fused_heads = (fused_select and (8 * (3 * NA + 3 + 3 * a.n_agents * 68) + 2 * a.n_actions * 69) * 4 <= 160 * 1024
-                       and fc2_w % 16 == 0 and fc2_wt % 16 == 0)
+        fits = lambda heads: bool(L.load().marl_select_fits(int(a.alg == "qmix"), a.n_agents, a.n_actions, heads))
+        fused_select = fuse and fits(0)
+        fused_heads = fused_select and fits(1) and fc2_w % 16 == 0 and fc2_wt % 16 == 0
         dhext_fused = fuse and fc2_w % 8 == 0
 
         def fill(i, obs, shift, params, h0_from, gates):

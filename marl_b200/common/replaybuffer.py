@@ -16,6 +16,12 @@ ring lives in HBM as fp32 (``u`` int64), i.e. exactly what ``QLearner.train`` co
 
 The first-terminated index of every stored episode is kept on the host, so the episode-length cut of
 ``get_max_episode_len`` (q_learner.py:49-66) needs no device synchronisation.
+
+One difference from the reference, which COPIES the sampled rows inside ``sample``: the batch returned here refers to
+the ring, so it must be trained on (or materialised) before a ``store_episode`` overwrites one of its rows.  The
+reference's loop (runner.py:92-97: store, then sample, then train) satisfies that; a collector thread that stores
+between ``sample`` and ``train`` does not, and is DETECTED: every ring row carries a version counter, and
+``DeviceEpisodeBatch.check_fresh`` (called by the learner) raises if a sampled row was rewritten meanwhile.
 """
 from __future__ import annotations
 
@@ -33,16 +39,24 @@ class DeviceEpisodeBatch(dict):
     Behaves like the reference's dict of ``[batch, episode_limit, ...]`` arrays (keys are gathered on
     first access as CUDA tensors); ``QLearner.train`` recognises it and skips the materialisation."""
 
-    def __init__(self, ring, idx_host, idx_dev, max_episode_len):
+    def __init__(self, ring, idx_host, idx_dev, max_episode_len, owner=None, versions=None):
         super().__init__()
         self.ring, self.idx_host, self.idx = ring, idx_host, idx_dev
         self.max_episode_len = int(max_episode_len)
+        self.owner, self.versions = owner, versions
+
+    def check_fresh(self):
+        """Raises if an episode of this batch was overwritten in the ring after ``sample`` drew it."""
+        if self.owner is not None and not np.array_equal(self.owner.version[self.idx_host], self.versions):
+            raise RuntimeError("ReplayBuffer: a sampled episode was overwritten by store_episode() before the batch was "
+                               "consumed; train on (or index) a sampled batch before storing new episodes")
 
     def __missing__(self, key):
         if key == "max_episode_len":
             return self.max_episode_len
         if key not in self.ring:
             raise KeyError(key)
+        self.check_fresh()
         val = self.ring[key].index_select(0, self.idx)
         self[key] = val
         return val
@@ -95,6 +109,7 @@ class ReplayBuffer:
                         'terminated': f(S, T, 1)}
         # index of the first terminated == 1 per stored episode (-1: none), for the episode-length cut
         self.first_terminated = np.full(self.size, -1, dtype=np.int64)
+        self.version = np.zeros(self.size, dtype=np.int64)      # bumped whenever a ring row is rewritten
         self.lock = threading.Lock()
 
     # ---- store ------------------------------------------------------------------------------------
@@ -119,6 +134,7 @@ class ReplayBuffer:
             term = term.reshape(batch_size, -1)[:, :self.episode_limit] == 1
             first = np.where(term.any(axis=1), term.argmax(axis=1), -1)
             self.first_terminated[idx_np] = first
+            self.version[idx_np] += 1
 
     # ---- sample -----------------------------------------------------------------------------------
     def sample(self, batch_size):
@@ -128,10 +144,13 @@ class ReplayBuffer:
     def sample_at(self, idx):
         """The batch made of the given ring rows (what ``sample`` does after drawing the indices)."""
         idx = np.asarray(idx, dtype=np.int64)
-        ft = self.first_terminated[idx]
+        with self.lock:
+            ft = self.first_terminated[idx]
+            versions = self.version[idx].copy()
         has = ft >= 0
         max_len = int(ft[has].max()) + 1 if has.any() else int(self.episode_limit)   # q_learner.py:49-61
-        return DeviceEpisodeBatch(self.buffers, idx, th.from_numpy(idx).to(self.device, non_blocking=True), max_len)
+        return DeviceEpisodeBatch(self.buffers, idx, th.from_numpy(idx).to(self.device, non_blocking=True), max_len,
+                                  owner=self, versions=versions)
 
     # ---- ring indices (common/replaybuffer.py:63-80) -----------------------------------------------
     def _get_storage_idx(self, inc=None):

@@ -440,9 +440,11 @@ __global__ void __launch_bounds__(UTH) linear_dgrad_kernel(LinearDgrad a) {
     umma_teardown(c, nsteps);
 }
 
-// dw[N, 0:K] += dy^T . in ; db[N] += colsum(dy).  Split over the M rows (blockIdx.z), atomics on the output.
+// dw[N, 0:K] += dy^T . in ; db[N] += colsum(dy).  Split over the M rows (blockIdx.z).  With a scratch arena (`part`) every
+// split stores its tile to part[blockIdx.z][N][ldp] and wgrad_reduce_kernel adds the splits in a fixed order (bitwise
+// reproducible gradients); without one the splits meet in atomics on the output.
 template <bool VEC_A, bool VEC_B>
-__global__ void __launch_bounds__(UTH) linear_wgrad_kernel(LinearWgrad a, int splits, int chunk) {
+__global__ void __launch_bounds__(UTH) linear_wgrad_kernel(LinearWgrad a, int splits, int chunk, float* part, float* part_b, int ldp) {
     extern __shared__ unsigned char umma_smem[];
     const int zb = blockIdx.z / splits, sp = blockIdx.z % splits;
     const int i0 = blockIdx.x * UM, j0 = blockIdx.y * UN;
@@ -470,15 +472,31 @@ __global__ void __launch_bounds__(UTH) linear_wgrad_kernel(LinearWgrad a, int sp
                 v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
                 v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8);
                 const int n = i0 + ma.i[l] + e;
-                if (ma.r[l] == 0 && n < a.N) atomicAdd(a.db + (long long)zb * a.db_bs + n, bmul * v);
+                if (ma.r[l] == 0 && n < a.N) {
+                    if (part_b) part_b[(long long)blockIdx.z * a.N + n] = bmul * v;
+                    else atomicAdd(a.db + (long long)zb * a.db_bs + n, bmul * v);
+                }
             }
     }
     float* dw = a.dw + (long long)zb * a.dw_bs;
+    if (part && mbeg >= mend) {      // (cannot happen with the host's split plan; keeps the reduce well-defined)
+        for (int idx = threadIdx.x; idx < UM * UN; idx += UTH) {
+            const int n = i0 + idx / UN, k = j0 + idx % UN;
+            if (n < a.N && k < K) part[((long long)blockIdx.z * a.N + n) * ldp + k] = 0.f;
+        }
+    }
     const bool vec_dw = ((a.ldw & 3) == 0) && ((reinterpret_cast<uintptr_t>(dw) & 15) == 0);
     if (mbeg < mend)
         umma_epilogue(c, nsteps, [&](int i, int j, float (&v)[4]) {
             const int n = i0 + i, k = j0 + j;
             if (n >= a.N || k >= K) return;
+            if (part) {      // ldp is a multiple of 4 and the arena is 256-byte aligned: one 128-bit store
+                float* pd = part + ((long long)blockIdx.z * a.N + n) * ldp + k;
+                if (k + 3 < ldp) { *reinterpret_cast<float4*>(pd) = make_float4(v[0], v[1], v[2], v[3]); return; }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (k + e < K) pd[e] = v[e];
+                return;
+            }
             float* dst = dw + (long long)n * a.ldw + k;
             if (vec_dw && k + 3 < K) {      // one 128-bit reduction instead of four atomics
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
@@ -489,6 +507,28 @@ __global__ void __launch_bounds__(UTH) linear_wgrad_kernel(LinearWgrad a, int sp
                 if (k + e < K) atomicAdd(dst + e, v[e]);
         });
     umma_teardown(c, nsteps);
+}
+
+// second stage of the split weight gradient: fixed summation order
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(LinearWgrad a, int splits, int K, const float* part, const float* part_b, int ldp) {
+    pdl_enter();
+    const int zb = blockIdx.y;
+    const long long total = (long long)a.N * K + (part_b ? a.N : 0);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const bool is_b = idx >= (long long)a.N * K;
+        const int n = is_b ? (int)(idx - (long long)a.N * K) : (int)(idx / K), k = is_b ? 0 : (int)(idx % K);
+        const float* src = is_b ? part_b + ((long long)zb * splits) * a.N + n : part + (((long long)zb * splits) * a.N + n) * ldp + k;
+        const long long stride = is_b ? a.N : (long long)a.N * ldp;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int sp = 0;
+        for (; sp + 3 < splits; sp += 4) {
+            s0 += src[sp * stride]; s1 += src[(sp + 1) * stride]; s2 += src[(sp + 2) * stride]; s3 += src[(sp + 3) * stride];
+        }
+        for (; sp < splits; ++sp) s0 += src[sp * stride];
+        const float s = (s0 + s1) + (s2 + s3);
+        if (is_b) a.db[(long long)zb * a.db_bs + n] += s;
+        else a.dw[(long long)zb * a.dw_bs + (long long)n * a.ldw + k] += s;
+    }
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -553,8 +593,24 @@ int linear_wgrad(const LinearWgrad& a, cudaStream_t st) {
     splits = cdiv(a.M, chunk);
     dim3 grid(cdiv(a.N, UM), cdiv(K, UN), a.batch * splits);
     const bool va = vec_ok_mat(a.dy, a.lddy, a.dy_bs), vb = vec_ok_lin(a.in);
-    { if (prof_enabled()) prof_note(a.N, K, a.M); ProfScope ps_("linear_wgrad_kernel", st); MARL_DISPATCH2(linear_wgrad_kernel, va, vb, grid, st, a, splits, chunk); }
+    // deterministic path: per-split tiles in the scratch arena (marl_set_scratch) + a fixed-order reduce
+    const int ldp = (K + 3) & ~3;
+    const size_t pw = (size_t)a.batch * splits * a.N * ldp * sizeof(float), pb = a.db ? (size_t)a.batch * splits * a.N * sizeof(float) : 0;
+    float* part = splits * a.batch > 0 ? tgemm_scratch(pw + 256 + pb) : nullptr;
+    float* part_b = (part && a.db) ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(part) + ((pw + 255) & ~(size_t)255)) : nullptr;
+    { if (prof_enabled()) prof_note(a.N, K, a.M); ProfScope ps_("linear_wgrad_kernel", st); MARL_DISPATCH2(linear_wgrad_kernel, va, vb, grid, st, a, splits, chunk, part, part_b, ldp); }
     MARL_LAUNCH_CHECK();
+    if (part) {
+        const long long total = (long long)a.N * K + a.N;
+        int bx = (int)((total + 255) / 256);
+        if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;
+        // batched problems that accumulate into ONE dw (dw_bs == 0: e.g. the per-episode h0 term of dW_hh) are extra splits
+        const bool fold = a.batch > 1 && a.dw_bs == 0 && (!a.db || a.db_bs == 0);
+        ProfScope ps_("wgrad_reduce_kernel", st);
+        launch_pdl_prio(linear_prio(), wgrad_reduce_kernel, dim3(bx, fold ? 1 : a.batch), dim3(256), 0, st, a, fold ? splits * a.batch : splits, K,
+                        (const float*)part, (const float*)part_b, ldp);
+        MARL_LAUNCH_CHECK();
+    }
     return MARL_OK;
 }
 

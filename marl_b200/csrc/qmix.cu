@@ -372,3 +372,11 @@ extern "C" int marl_qmix_hyper_wgrad(int M, int N, int S, const float* s, const 
     pdl_scope((long long)M * N);
     return hyper_wgrad(M, N, S, s, dhy, g, (cudaStream_t)stream);
 }
+
+/* Can the fused mixing kernels (csrc/qmix.cu, csrc/select_td.cu) stage the selection (heads = 0) / the selection plus the
+ * agents' heads (heads = 1) of an [N, A] problem in shared memory?  1 / 0; the host gates its launch plan on this instead
+ * of repeating the kernels' build-time constants. */
+extern "C" int marl_select_fits(int qmix, int N, int A, int heads) {
+    if (N <= 0 || A <= 0) return 0;
+    return marl::select_smem(qmix ? marl::kQmixWarps : 8, N, A, heads != 0) <= marl::kSelectSmemMax ? 1 : 0;
+}

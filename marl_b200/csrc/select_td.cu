@@ -188,7 +188,9 @@ __global__ void __launch_bounds__(256) ingest_kernel(IngestArgs a) {
     const long long per_b = (long long)a.L * key.inner, total = (long long)a.B * per_b;
     const long long src_b = (long long)a.T_src * key.inner;
     const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
-    if (a.idx && key.kind == 3 && (per_b & 3) == 0 && (src_b & 3) == 0) {
+    // 128-bit paths need 16-byte aligned bases as well as quad-sized rows (a caller's tensor view may start anywhere)
+    const bool al16 = ((reinterpret_cast<uintptr_t>(key.src) | reinterpret_cast<uintptr_t>(key.dst)) & 15) == 0;
+    if (a.idx && key.kind == 3 && al16 && (per_b & 3) == 0 && (src_b & 3) == 0) {
         // gather of sampled episodes (device replay buffer): 128-bit copies, a quad never straddles two episodes
         const long long qb = per_b >> 2, nq = (long long)a.B * qb;
         const float4* s = (const float4*)key.src; float4* d = (float4*)key.dst;
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(256) ingest_kernel(IngestArgs a) {
         }
         return;
     }
-    if (!a.idx && a.T_src == a.L && (total & 3) == 0 && (key.kind == 0 || key.kind == 3)) {
+    if (!a.idx && al16 && a.T_src == a.L && (total & 3) == 0 && (key.kind == 0 || key.kind == 3)) {
         // no truncation: straight vectorised cast / copy
         const long long nq = total >> 2;
         if (key.kind == 0) {

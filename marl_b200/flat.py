@@ -78,3 +78,40 @@ class FlatBuffer:
 def prefixed(prefix, entries):
     """Prefix the names of FlatBuffer entries, keeping their packing markers."""
     return [(prefix + e[0],) + tuple(e[1:]) for e in entries]
+
+
+class FlatPackedMixin:
+    """For nn.Modules whose kernels read several parameters as ONE contiguous matrix (QMIX's four hyper heads, the QPLEX
+    layer groups, the agent): keeps that layout true for copies of the module.
+
+    ``copy.deepcopy``, pickling and ``torch.save(module)`` clone every Parameter on its own, so the copy's tensors are no
+    longer views of one buffer -- a kernel reading ``[N*E + 3E, S]`` from ``hyper_w1.weight`` would then run past the end
+    of that tensor.  Copies are therefore re-packed on creation, and ``ensure_packed()`` (called by ``forward``) re-packs
+    whenever a parameter no longer sits at its slot of ``self._flat`` (e.g. someone re-assigned ``p.data``)."""
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == "_flat" else copy.deepcopy(v, memo)
+        new._pack(next(new.parameters()).device)
+        return new
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._flat = None
+        self._pack(next(self.parameters()).device)
+
+    def ensure_packed(self):
+        flat = self._flat
+        ok = flat is not None
+        if ok:
+            for entry in self.flat_named_parameters():
+                n, p = entry[0], entry[1]
+                name = n if n in flat.offsets else next((k for k in flat.offsets if k.endswith("." + n)), None)
+                if name is None or p.data_ptr() != flat.data.data_ptr() + 4 * flat.offsets[name] or p.device != flat.data.device:
+                    ok = False
+                    break
+        if not ok:
+            self._pack(next(self.parameters()).device)

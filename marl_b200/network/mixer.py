@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib as L
-from ..flat import FlatBuffer
+from ..flat import FlatBuffer, FlatPackedMixin
 
 E = 32
 
@@ -151,7 +151,7 @@ class _QmixFn(torch.autograd.Function):
         return (dq, None, None, None, None, *views)
 
 
-class QMixMixer(nn.Module):
+class QMixMixer(FlatPackedMixin, nn.Module):
     """Monotonic mixing network with state-conditioned hyper-networks (mixer.py:21-80)."""
 
     def __init__(self, args):
@@ -196,6 +196,7 @@ class QMixMixer(nn.Module):
     def forward(self, q_values, states):
         # states (episode_num, max_episode_len, state_shape); q_values (episode_num, max_episode_len, n_agents)
         episode_num = q_values.size(0)
+        self.ensure_packed()      # the kernels read the four heads as ONE matrix: a copied module is re-packed first
         N, S = self.args.n_agents, self.args.state_shape
         q = L.require_cuda(q_values, "q_values").reshape(-1, N).to(torch.float32).contiguous()
         s = L.require_cuda(states, "states").reshape(-1, S).to(torch.float32).contiguous()

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib as L
-from ..flat import FlatBuffer
+from ..flat import FlatBuffer, FlatPackedMixin
 
 H = 64
 
@@ -88,7 +88,7 @@ class _UnrollFn(torch.autograd.Function):
         return (None, None, dh0, None, None, None, *gflat)
 
 
-class RNNQNet(nn.Module):
+class RNNQNet(FlatPackedMixin, nn.Module):
     # Because all the agents share the same network, input_shape = obs_shape + n_actions + n_agents
     def __init__(self, input_shape, args):
         super().__init__()

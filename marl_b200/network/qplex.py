@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib as L
-from ..flat import FlatBuffer
+from ..flat import FlatBuffer, FlatPackedMixin
 
 
 def _mlp3(n_in, hid, n_out):
@@ -148,7 +148,7 @@ class _QplexFn(torch.autograd.Function):
         return (None, None, None, None, None, None, *views)      # adv is detached: no gradient to agent_qs
 
 
-class DMAQer(nn.Module):
+class DMAQer(FlatPackedMixin, nn.Module):
     """Q_tot = sum_i (w_i Q_i + v_i) + sum_i (lambda_i - 1) A_i   (transformation + dueling mixing)."""
 
     def __init__(self, args):
@@ -194,6 +194,7 @@ class DMAQer(nn.Module):
     # ---- reference surface ----------------------------------------------------------------------------
     def forward(self, agent_qs, states, actions=None, max_q_i=None, is_v=False):
         bs = agent_qs.size(0)
+        self.ensure_packed()      # layer groups are read as one matrix each: re-pack a copied module first
         N = self.n_agents
         q = L.require_cuda(agent_qs, "agent_qs").reshape(-1, N).to(torch.float32).contiguous()
         s = L.require_cuda(states, "states").reshape(-1, self.state_dim).to(torch.float32).contiguous()

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib as L
-from ..flat import FlatBuffer
+from ..flat import FlatBuffer, FlatPackedMixin
 
 H = 64
 
@@ -65,7 +65,7 @@ class _JointNetFn(torch.autograd.Function):
         return (None, dhidden.view(hidden.shape), None, None, *grads)
 
 
-class _JointNet(nn.Module):
+class _JointNet(FlatPackedMixin, nn.Module):
     def _finish(self):
         self._flat = None
         self._pack(torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu"))

@@ -42,7 +42,10 @@ class PeerGradients:
         self.numel, self._opened, self._base, self.ok = numel, [], None, False
         ok = self.world <= 8 and numel % 4 == 0 and numel <= (1 << 18)
         grad_bytes = (4 * (numel + 2) + 255) // 256 * 256
-        handles = None
+        # Every rank takes part in BOTH collectives below whatever happened locally (a rank that skipped the all_gather
+        # while its peers sat in it would dead-lock NCCL): a failed rank contributes an all-zero handle, and the
+        # decision is taken only after the MIN all-reduce.
+        mine = torch.zeros(64, dtype=torch.uint8)
         if ok:
             try:
                 base = C.c_void_p()
@@ -50,11 +53,13 @@ class PeerGradients:
                 self._base = base.value
                 hbuf = C.create_string_buffer(64)
                 L.call("marl_peer_export", self._base, hbuf)
-                mine = torch.frombuffer(bytearray(hbuf.raw), dtype=torch.uint8).to(device)
-                handles = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(self.world)]
-                dist.all_gather(handles, mine, group=group)
+                mine = torch.frombuffer(bytearray(hbuf.raw), dtype=torch.uint8).clone()
             except Exception:
                 ok = False
+        handles = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(self.world)]
+        dist.all_gather(handles, mine.to(device), group=group)
+        if ok and any(int(h.sum().item()) == 0 for h in handles):
+            ok = False
         bases = [None] * self.world
         if ok:
             try:
@@ -82,6 +87,12 @@ class PeerGradients:
             pg.grads[r], pg.flags[r] = bases[r], bases[r] + grad_bytes
         pg.epoch, pg.error = self.state.data_ptr(), self.state.data_ptr() + 4
         self.struct = pg
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: the driver reclaims the mappings
+            pass
 
     def close(self):
         from . import _lib as L
