@@ -228,27 +228,101 @@ def bench_env(torch, dist, world, n_envs, iters, hbm_peak):
                          "traffic": NCU_TRAFFIC["matrix_game_step_kernel"] if n_envs == (1 << 24) else None, "note": "per GPU"}}
 
 
+def to_device_batch(torch, hb, T):
+    db = {k: torch.as_tensor(v, device="cuda") for k, v in hb.items()}
+    db = {k: (v.to(torch.int64) if k == "u" else v.to(torch.float32)).contiguous() for k, v in db.items()}
+    db["max_episode_len"] = T
+    return db
+
+
+class Timer:
+    """CUDA-event timing of K train steps on the current stream, max over ranks; also the per-step median."""
+
+    def __init__(self, torch, dist, world):
+        self.torch, self.dist, self.world = torch, dist, world
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, K, step_fn):
+        torch = self.torch
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        self.barrier()
+        evs[0].record()
+        for i in range(K):
+            step_fn(i)
+            evs[i + 1].record()
+        self.barrier()
+        per = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
+        self.last_per_step = per
+        t = torch.tensor([evs[0].elapsed_time(evs[K]) / K, float(np.median(per))], device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+
+def dp_check(torch, dist, world, rank, make_learner):
+    """Data-parallel correctness INSIDE the multi-GPU run: (a) replicas stay bit-identical, (b) loss and parameters after 3
+    steps agree with a single-GPU learner trained on the concatenated global batch (fp32 summation order differs: 1e-5)."""
+    from marl_b200.synthetic import synthetic_batch
+    Bg = 8 * world
+    shape = dict(SHAPE, B=Bg, T=40)
+    hb = synthetic_batch(4242, **shape)
+    dp = make_learner(shape, seed=11)
+    dp.enable_data_parallel()
+    single = make_learner(shape, seed=11)
+    db = to_device_batch(torch, hb, shape["T"])
+    losses_dp, losses_1 = [], []
+    for i in range(3):
+        losses_dp.append(dp.train(dict(db), i))          # every rank passes the GLOBAL batch; the learner takes its shard
+        losses_1.append(single.train(dict(db), i))
+    p_dp, p_1 = dp._flat.data.clone(), single._flat.data
+    gathered = [torch.empty_like(p_dp) for _ in range(world)]
+    dist.all_gather(gathered, p_dp)
+    identical = all(bool(torch.equal(gathered[0], g)) for g in gathered[1:])
+    scale = float(p_1.abs().max())
+    perr = float((p_dp - p_1).abs().max()) / scale
+    lerr = max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(losses_dp, losses_1))
+    # RMSprop divides by ~|g| on the first steps: parameters are compared at the noise floor documented in tests/parity_util.py
+    ok = identical and lerr <= 1e-5 and perr <= 1e-5 + 0.25 * dp.lr * 3 / scale
+    return {"replicas_bit_identical": identical, "loss_rel_err_vs_1gpu": lerr, "param_rel_err_vs_1gpu": perr, "steps": 3,
+            "global_batch": Bg, "exchange": "peer" if getattr(dp, "_peer", None) is not None else "nccl", "ok": bool(ok)}
+
+
 def run_ours(opt):
     import torch
     import torch.distributed as dist
     from marl_b200 import _lib as L
     from marl_b200.algorithm.q_learner import QLearner
+    from marl_b200.algorithm.qtran_learner import QTRANLearner
+    from marl_b200.common.arguments import default_args
+    from marl_b200.common.replaybuffer import ReplayBuffer
     from marl_b200.controller.share_params import SharedMAC
-    from marl_b200.synthetic import synthetic_batch, KEYS
+    from marl_b200.env.single_state_matrix_game import BatchedMatrixGame
+    from marl_b200.synthetic import synthetic_batch, KEYS, CONFIGS
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    pin_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hbm_peak, peak_src = peaks()
     K, W = opt.steps, max(opt.warmup, 3)
     B = SHAPE["B"]
+    tm = Timer(torch, dist, world)
+
+    def make_learner(shape, alg="qmix", seed=0, name="synthetic_2s3z"):
+        a = default_args(alg=alg, n_agents=shape["N"], n_actions=shape["A"], obs_shape=shape["O"], state_shape=shape["S"],
+                         episode_limit=shape["T"], map=name)
+        torch.manual_seed(seed)
+        return (QTRANLearner if alg == "qtran_base" else QLearner)(SharedMAC(a), a)
 
     args = make_args()
-    torch.manual_seed(0)
-    learner = QLearner(SharedMAC(args), args)
+    learner = make_learner(SHAPE)
     if world > 1:
         learner.enable_data_parallel()
 
@@ -257,84 +331,129 @@ def run_ours(opt):
     dev_batches, host_batches = [], []
     for i in range(NB):
         hb = synthetic_batch(1000 * rank + i, **SHAPE)
-        db = {k: torch.as_tensor(v, device="cuda") for k, v in hb.items()}
-        db = {k: (v.to(torch.int64) if k == "u" else v.to(torch.float32)).contiguous() for k, v in db.items()}
-        db["max_episode_len"] = SHAPE["T"]
-        dev_batches.append(db)
+        dev_batches.append(to_device_batch(torch, hb, SHAPE["T"]))
         if i < 2:                                     # pinned float64 host copies in the ReplayBuffer layout
             pinned = {k: torch.from_numpy(v).pin_memory() for k, v in hb.items()}
             host_batches.append({k: t.numpy() for k, t in pinned.items()})
             host_batches[-1]["_keep"] = pinned
-    shard = learner._shard
     if world > 1:
         learner._shard = lambda B_glob: (0, B_glob)  # every rank already holds exactly its shard
 
     def host_view(i):
         return {k: host_batches[i % 2][k] for k in KEYS}
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    state = {"step": 0}
 
-    step = 0
+    def train(b):
+        loss = learner.train(b, state["step"])
+        state["step"] += 1
+        return loss
+
     # resident batches are read in place, each through its own captured graph: run every batch through the eager
     # call and the capture call before anything is timed (W warm-up replays follow)
     for _ in range(2):
         for b in dev_batches:
-            learner.train(b, step); step += 1
+            train(b)
     for i in range(W):
-        learner.train(dev_batches[i % NB], step); step += 1
+        train(dev_batches[i % NB])
     for i in range(max(W, 3)):
-        learner.train(host_view(i), step); step += 1
+        train(host_view(i))
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # ---- value: device-resident batches -------------------------------------------------------------
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for i in range(K):
-        learner.train(dev_batches[i % NB], step); step += 1
-    ev1.record()
-    barrier()
-    ms_dev = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
-    # ---- e2e: pinned host float64 batches through the reference-facing call ---------------------------
-    barrier()
-    ev0.record()
-    for i in range(K):
-        learner.train(host_view(i), step); step += 1
-    ev1.record()
-    barrier()
-    ms_e2e_sync = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    # ---- value: device-resident batches ---------------------------------------------------------------------------------
+    ms_dev, ms_dev_median = tm.run(K, lambda i: train(dev_batches[i % NB]))
+
+    # ---- e2e (headline): the reference's own loop, runner.py:92-97 -- one freshly generated HOST episode is stored
+    # (pinned float64 -> H2D -> fp32 ring row), a batch of 32 is sampled, train() returns the loss to the host ----------------
+    rb_args = make_args()
+    rb_args.buffer_size = 512
+    buf = ReplayBuffer(rb_args)
+    for i in range(0, 512, B):                       # untimed: fill the ring
+        buf.store_episode({k: dev_batches[(i // B) % NB][k] for k in KEYS})
+    new_eps = []
+    for i in range(8):
+        hb = synthetic_batch(5000 + 1000 * rank + i, **dict(SHAPE, B=1))
+        pinned = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).pin_memory() for k, v in hb.items()}
+        new_eps.append(({k: t.numpy() for k, t in pinned.items()}, pinned))
+    ep_bytes = sum(v.nbytes for v in new_eps[0][0].values())
+    np.random.seed(1234 + rank)
+
+    def replay_step(i):
+        buf.store_episode(new_eps[i % 8][0])
+        train(buf.sample(B))
+
+    for i in range(max(W, 3)):
+        replay_step(i)
+    ms_replay, ms_replay_median = tm.run(K, replay_step)
+    replay_max = float(max(tm.last_per_step))
+
+    # ---- e2e, host-dict variant: a caller that keeps whole float64 batches in host memory (the reference's ReplayBuffer
+    # layout) and hands one to train() every step: 35.6 MB over PCIe per step ---------------------------------------------
+    ms_e2e_sync, _ = tm.run(K, lambda i: train(host_view(i)))
     h2d = learner.h2d_bytes_last
-    # same, with the next batch's H2D copy started (learner.prefetch) before the current train() call: the copy
-    # of every step is still inside the timed region, it just overlaps the previous step's compute
     hv = [host_view(0), host_view(1)]
     learner.prefetch(hv[0])                           # untimed: first use allocates the two prefetch staging slots
     for i in range(4):
         learner.prefetch(hv[(i + 1) & 1])
-        learner.train(hv[i & 1], step); step += 1
-    learner.train(hv[0], step); step += 1
-    barrier()
-    ev0.record()
+        train(hv[i & 1])
+    train(hv[0])
     learner.prefetch(hv[0])
-    for i in range(K):
+
+    def prefetched_step(i):
         if i + 1 < K:
             learner.prefetch(hv[(i + 1) & 1])
-        learner.train(hv[i & 1], step); step += 1
-    ev1.record()
-    barrier()
-    ms_e2e = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+        train(hv[i & 1])
+
+    ms_e2e_host, _ = tm.run(K, prefetched_step)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        dist.all_reduce(ms_dev, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ms_e2e_sync, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e, ms_e2e_sync = float(ms_dev) / K, float(ms_e2e) / K, float(ms_e2e_sync) / K
     launches = learner.launches_per_step + 1          # + the ingest launch (host-batch path; device batches in the
                                                       # working-set layout are read in place: no ingest launch)
+
+    # ---- multi-GPU only: correctness of the exchange, strong scaling, config 5 sharded ------------------------------------
+    dp, strong = None, None
+    if world > 1:
+        dp = dp_check(torch, dist, world, rank, lambda shape, seed: make_learner(shape, seed=seed))
+        # strong scaling: the GLOBAL batch stays at 32 episodes (B/world per GPU); latency-bound by design
+        if B % world == 0:
+            ls = make_learner(SHAPE)
+            ls.enable_data_parallel()
+            gb = [to_device_batch(torch, synthetic_batch(77 + i, **SHAPE), SHAPE["T"]) for i in range(2)]
+            for i in range(6):
+                ls.train(dict(gb[i % 2]), i)
+            ms_s, ms_s_med = tm.run(K, lambda i: ls.train(dict(gb[i % 2]), 6 + i))
+            strong = {"global_batch": B, "episodes_per_gpu": B // world, "ms_per_step": ms_s, "ms_per_step_median": ms_s_med,
+                      "value": B / (ms_s * 1e-3), "unit": "episode-samples/s",
+                      "limiter": "the 2L = 240 dependent GRU steps do not shrink with the shard, the exchange (flag barrier "
+                                 "inside the optimiser launch) is added: latency-bound, as SURVEY.md 8(e) expects"}
+            del ls, gb
+
+    # ---- BASELINE config 5: 4096 matrix-game envs (sharded over the ranks) feeding the data-parallel QMIX learner ----------
+    n5 = 4096 // world
+    a5 = default_args(alg="qmix", n_agents=2, n_actions=3, obs_shape=1, state_shape=1, episode_limit=1, map="matrix")
+    torch.manual_seed(0)
+    l5 = QLearner(SharedMAC(a5), a5)
+    if world > 1:
+        l5.enable_data_parallel()
+        l5._shard = lambda B_glob: (0, B_glob)
+    env5 = BatchedMatrixGame(PAYOFF1, n5)
+    acts5 = torch.randint(0, 3, (n5, 2), device="cuda")
+
+    def cfg5_step(i):
+        ep = dict(env5.step(acts5))
+        ep["max_episode_len"] = 1
+        l5.train(ep, i)
+
+    for i in range(6):
+        cfg5_step(i)
+    ms5, ms5_med = tm.run(max(K, 20), lambda i: cfg5_step(6 + i))
+    cfg5 = {"workload": "4096 matrix-game envs sharded over the ranks (one env launch per rank) -> QMIX train step on the "
+                        "emitted device batch, gradients exchanged like config 2",
+            "envs_per_gpu": n5, "ms_per_iteration": ms5, "ms_per_iteration_median": ms5_med,
+            "env_steps_per_s": 4096 / (ms5 * 1e-3), "episode_samples_per_s": 4096 / (ms5 * 1e-3), "scaling": "strong",
+            "limiter": "launch latency: 4096 one-step episodes are ~0.25 ms of fixed-size kernels on ONE GPU already"}
+    del l5, env5
 
     # ---- per-kernel device time (eager pass, CUDA events around every launch of the library) ---------
     learner._use_graph = False
@@ -342,7 +461,7 @@ def run_ours(opt):
     P = 10
     for i in range(P):
         L.call("marl_spin_us", 4000, L.stream_ptr())      # let the host run ahead: events then bracket device time only
-        learner.train(dev_batches[i % NB], step); step += 1
+        train(dev_batches[i % NB])
     prof = L.profile_collect() if rank == 0 else {}
     L.profile(False)
     learner._use_graph = True
@@ -368,29 +487,6 @@ def run_ours(opt):
     torch.cuda.synchronize()
     fp32_peak = flops.value / (a.elapsed_time(b) * 1e-3) / 1e12
 
-    # ---- BASELINE config 5: 4096 matrix-game envs stepped on the GPU feeding the QMIX learner directly ----
-    cfg5 = None
-    if world == 1:
-        from marl_b200.common.arguments import default_args
-        from marl_b200.env.single_state_matrix_game import BatchedMatrixGame
-        a5 = default_args(alg="qmix", n_agents=2, n_actions=3, obs_shape=1, state_shape=1, episode_limit=1, map="matrix")
-        l5 = QLearner(SharedMAC(a5), a5)
-        env5 = BatchedMatrixGame(PAYOFF1, 4096)
-        acts5 = torch.randint(0, 3, (4096, 2), device="cuda")
-        for i in range(5):
-            ep = dict(env5.step(acts5)); ep["max_episode_len"] = 1
-            l5.train(ep, i)
-        torch.cuda.synchronize()
-        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a_.record()
-        for i in range(50):
-            ep = dict(env5.step(acts5)); ep["max_episode_len"] = 1
-            l5.train(ep, 5 + i)
-        b_.record(); torch.cuda.synchronize()
-        ms5 = a_.elapsed_time(b_) / 50
-        cfg5 = {"workload": "4096 matrix-game envs (one kernel launch) -> QMIX train step on the emitted device batch",
-                "ms_per_iteration": ms5, "env_steps_per_s": 4096 / (ms5 * 1e-3), "episode_samples_per_s": 4096 / (ms5 * 1e-3)}
-
     peaks_json = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     bf16_peak = peaks_json.get("bf16_tflops_sustained", 1400.0)      # kernels timed inside a long step: the sustained figure
     # ---- larger batches of the same shape (device-resident): where the step leaves the latency-bound regime ----
@@ -398,17 +494,14 @@ def run_ours(opt):
     if world == 1 and not opt.no_sweep:
         sweep = []
         for Bs in (256, 1024):
-            hb = synthetic_batch(7, **dict(SHAPE, B=Bs))
-            db = {k: torch.as_tensor(v, device="cuda") for k, v in hb.items()}
-            db = {k: (v.to(torch.int64) if k == "u" else v.to(torch.float32)).contiguous() for k, v in db.items()}
-            db["max_episode_len"] = SHAPE["T"]
+            db = to_device_batch(torch, synthetic_batch(7, **dict(SHAPE, B=Bs)), SHAPE["T"])
             for i in range(4):
-                learner.train(db, step); step += 1
+                train(db)
             torch.cuda.synchronize()
             a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a_.record()
             for i in range(10):
-                learner.train(db, step); step += 1
+                train(db)
             b_.record(); torch.cuda.synchronize()
             msb = a_.elapsed_time(b_) / 10
             tf = FLOP_PER_STEP * Bs / SHAPE["B"] / (msb * 1e-3) / 1e12
@@ -418,6 +511,40 @@ def run_ours(opt):
             del db
         learner._ws = {k: v for k, v in learner._ws.items() if k[0] == "stage" or k == (B, SHAPE["T"])}
         torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs (device batch, graph replay) with the reference's CPU path beside them ----------------
+    configs = None
+    if world == 1 and not opt.no_sweep:
+        configs = {}
+        for name, flop in (("2s3z:vdn", 6.03e9), ("3s5z", 157.9e9), ("27m_vs_30m", 107.7e9)):
+            cname, _, alg_o = name.partition(":")
+            c = dict(CONFIGS[cname])
+            alg = alg_o or c["alg"]
+            shape = {k: c[k] for k in ("B", "T", "N", "A", "O", "S")}
+            lc = make_learner(shape, alg=alg, name=cname)
+            db = to_device_batch(torch, synthetic_batch(0, **shape), shape["T"])
+            for i in range(4):
+                lc.train(db, i)
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for i in range(10):
+                lc.train(db, 4 + i)
+            b_.record(); torch.cuda.synchronize()
+            msc = a_.elapsed_time(b_) / 10
+            tf = flop / (msc * 1e-3) / 1e12
+            entry = {"alg": alg, "shape": shape, "ms_per_step": msc, "episode_samples_per_s": shape["B"] / (msc * 1e-3),
+                     "algorithmic_gflop_per_step": flop / 1e9, "fp32_tflops": tf, "frac_of_fp32_peak": tf / fp32_peak,
+                     "launches_per_step": lc.launches_per_step}
+            del lc, db
+            torch.cuda.empty_cache()
+            try:
+                r = time_reference(2, 1, alg=alg, shape=shape)
+                entry["cpu_baseline"] = {"value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"], "cores": r["cores"],
+                                         "kind": r["kind"], "sample": "2 train steps after 1 warm-up, same batch"}
+            except Exception as e:      # noqa: BLE001
+                entry["cpu_baseline"] = {"unavailable": repr(e)[:200]}
+            configs[cname + ("_" + alg if alg_o else "")] = entry
 
     roofline = None
     if kernels:
@@ -439,8 +566,9 @@ def run_ours(opt):
                     "traffic": NCU_TRAFFIC.get(dom), "traffic_source": "profiles/r1c_ncu_full_gru.txt (dram_read + dram_write, one --set full capture)",
                     "us_per_launch": dom_us, "algorithmic_flop_per_launch": flop, "algorithmic_bytes_per_launch": gru_bytes,
                     "hbm_frac": (gru_bytes / (dom_us * 1e-6) / 1e9 / hbm_peak) if gru_bytes else None,
-                    "peak_source": "marl_fma_probe on this GPU (MEASURED_PEAKS.json has no fp32 figure); hbm: " + peak_src}
-    gemm_us = sum(v["us_per_step"] for k, v in kernels.items() if k.startswith("linear_"))
+                    "peak_source": "fp32: marl_fma_probe on this GPU, the builder's own probe (MEASURED_PEAKS.json has no fp32 "
+                                   "figure; nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4); hbm: " + peak_src}
+    gemm_us = sum(v["us_per_step"] for k, v in kernels.items() if k.startswith(("linear_", "tgemm_", "wgrad_reduce")))
     gemm_flop = FLOP_PER_STEP - GRU_FWD_FLOP - GRU_FWD_FLOP / 3        # everything but the two recurrent kernels
     roofline_gemm = None
     if gemm_us:
@@ -449,36 +577,52 @@ def run_ours(opt):
                          "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
                          "traffic": NCU_TRAFFIC.get("linear_fwd_kernel"), "us_per_step": gemm_us,
                          "note": "algorithmic fp32 FLOPs of all dense layers / summed launch time (launches on parallel streams "
-                                 "overlap, so the sum overstates the wall time); peak = measured sustained bf16; the TF32 pipe peaks "
-                                 "at half of it and every product is issued 3 times (3xTF32), so 1/6 of `peak` is the ceiling of "
-                                 "this scheme; at cfg-2 sizes each launch is a single wave of 150 CTAs x 3-6 k-tiles and is "
-                                 "bound by fixed per-launch latency and shared-memory bandwidth (profiles/README.md)"}
+                                 "overlap, so the sum overstates the wall time); peak = measured sustained bf16.  Measured "
+                                 "(tools/micro/mma_rate.cu): one tcgen05.mma kind::tf32 takes ~187 cycles whatever its N, i.e. "
+                                 "808 TFLOP/s at N = 256 and 202 at the N = 64 of these layers, and 3xTF32 issues every product "
+                                 "three times: 67 TFLOP/s is the ceiling of this scheme at these shapes"}
     step_tflops = FLOP_PER_STEP / (ms_dev * 1e-3) / 1e12
 
-    cpu = None
+    cpu, gpu_base = None, None
     if world == 1:
-        val, per, cores = time_cpu_reference(20, 3)
-        cpu = {"value": val, "unit": "episode-samples/s", "cores": cores, "kind": "port",
-               "sample": "20 train steps (after 3 warm-up) of the same B=32 2s3z-shaped batch, oracle port of the "
-                         "reference CPU path, all host threads", "ms_per_step": per * 1e3}
+        r = time_reference(20, 3)
+        cpu = {"value": r["value"], "unit": "episode-samples/s", "cores": r["cores"], "kind": r["kind"],
+               "sample": "20 train steps (after 3 warm-up) of the same B=32 2s3z-shaped batch, "
+                         + ("UNMODIFIED reference QLearner.train (oracle/_ref)" if r["kind"] == "reference" else
+                            "oracle port of the reference CPU path (oracle/_ref not staged)") + ", all host threads",
+               "ms_per_step": r["ms_per_step"]}
+        try:
+            g = time_reference(10, 3, cuda=True)
+            if g is not None:
+                gpu_base = {"value": g["value"], "unit": g["unit"], "ms_per_step": g["ms_per_step"], "steps": 10,
+                            "what": "UNMODIFIED reference QLearner.train with args.cuda=True on this B200 (stock ATen / cuBLAS)"}
+        except Exception as e:      # noqa: BLE001
+            gpu_base = {"unavailable": repr(e)[:200]}
 
     line = {
         "metric": "QMIX learner episode-samples/sec (2s3z shape)", "value": B * world / (ms_dev * 1e-3),
         "unit": "episode-samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev,
+        "ms_per_step_median": ms_dev_median,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "QMIX learner step, synthetic 2s3z-shaped batch (5 agents, 11 actions, T=120, "
-                               "batch 32 per GPU, RMSprop, double-Q)",
+        "config": {"workload": WORKLOAD,
                    "global_batch": B * world, "parallelism": f"dp{world}",
                    "gradient_exchange": (None if world == 1 else
                                          "fused into the optimiser launch over NVLink peer memory (marl_clip_step_peer)"
                                          if getattr(learner, "_peer", None) is not None else "ncclAllReduce between two graphs"),
                    "l2": f"inputs rotate over {NB} resident batches (150 MB > 126 MB L2)"},
-        "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "episode-samples/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
-                "how": "QLearner.train(host float64 dict) with learner.prefetch(next batch) issued before it: H2D of step "
-                       "k+1 overlaps the compute of step k; every copy and every loss read-back is inside the timed region",
-                "without_prefetch": {"value": B * world / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync}},
-        "gpu_launches": int((launches - 1) * K + launches * K),   # value leg (in place) + e2e leg (with ingest)
+        "e2e": {"value": B * world / (ms_replay * 1e-3), "unit": "episode-samples/s", "ms_per_step": ms_replay,
+                "ms_per_step_median": ms_replay_median, "ms_per_step_max": replay_max,
+                "h2d_bytes_per_step": int(ep_bytes), "d2h_bytes_per_step": 8,
+                "how": "the reference's training loop (runner.py:92-97, n_episodes = 1, train_steps = 1) through the drop-in "
+                       "classes: buffer.store_episode(one new float64 HOST episode, pinned) -> buffer.sample(32) -> "
+                       "learner.train(batch) -> loss as a Python float; the episode's H2D copy, its cast into the fp32 ring, "
+                       "the gather of the sampled rows and the loss read-back are all inside the timed region",
+                "host_dict_variant": {"value": B * world / (ms_e2e_host * 1e-3), "ms_per_step": ms_e2e_host,
+                                      "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+                                      "how": "QLearner.train(whole float64 host batch) every step, next batch prefetched: "
+                                             "PCIe-bound (35.6 MB per step)",
+                                      "without_prefetch": {"value": B * world / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync}}},
+        "gpu_launches": int((launches - 1) * K + (launches + 1) * K + 2 * launches * K),   # value (in place) + replay (ingest + gather) + 2 host-dict legs
         "launches_per_step": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -488,14 +632,39 @@ def run_ours(opt):
                       "peak_source": peak_src},
         "kernels": kernels,
         "batch_sweep": sweep,
+        "configs": configs,
+        "dp_check": dp,
+        "strong_scaling": strong,
         "env": {"metric": "matrix-game env-steps/sec", "value": env_big["value"], "unit": "env-steps/s",
                 "bytes_per_env_step": ENV_BYTES, "cfg5_4096_envs": env_small, "bandwidth_regime_2^24_envs": env_big},
         "cfg5_env_plus_learner": cfg5,
         "cpu_baseline": cpu,
+        "gpu_baseline": gpu_base,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def pin_to_gpu_numa(local):
+    """Binds this rank's host threads to the cores of its GPU's NUMA node (NVML affinity) so that the pinned staging
+    buffers and the copy-issuing thread sit next to the PCIe root of the GPU; a no-op when NVML cannot tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if cpus and world > 1:
+            # spread the ranks that share a node over disjoint slices of its cores
+            cpus = sorted(cpus)
+            per = max(1, len(cpus) // world)
+            mine = cpus[(local * per) % len(cpus):][:per] or cpus
+            os.sched_setaffinity(0, set(mine))
+    except Exception:       # noqa: BLE001
+        pass
 
 
 def main():

@@ -110,31 +110,88 @@ class ReplayBuffer:
         # index of the first terminated == 1 per stored episode (-1: none), for the episode-length cut
         self.first_terminated = np.full(self.size, -1, dtype=np.int64)
         self.version = np.zeros(self.size, dtype=np.int64)      # bumped whenever a ring row is rewritten
+        self._stage = {}                                          # pinned / device staging of the host fast path
+        self._idx_stage = {}
         self.lock = threading.Lock()
 
     # ---- store ------------------------------------------------------------------------------------
+    def _store_host_f64(self, episode_batch, batch_size, start):
+        """Fast path of ``store_episode`` for what the rollout produces (rollout.py:135-149): float64 numpy arrays going
+        to CONTIGUOUS ring rows.  The 11 keys are packed into one pinned buffer, cross PCIe in ONE copy and are cast to
+        the ring's fp32 / int64 layout by ONE ``marl_ingest_f64`` launch writing the ring rows in place."""
+        import ctypes as C
+        from .. import _lib as L
+        st = self._stage.get(batch_size)
+        if st is None:
+            sizes = [batch_size * int(np.prod(self.buffers[k].shape[1:])) for k in KEYS]
+            offs = np.concatenate(([0], np.cumsum(sizes)))
+            total = int(offs[-1])
+            # two slots: the pinned buffer of call k may still be read by the DMA engine while call k+1 packs its episode
+            st = {"host": [th.empty(total, dtype=th.float64).pin_memory() for _ in range(2)],
+                  "dev": [th.empty(total, dtype=th.float64, device=self.device) for _ in range(2)],
+                  "done": [None, None], "seq": 0, "e64": [], "views": [],
+                  "row_bytes": [self.buffers[k][0].numel() * self.buffers[k].element_size() for k in KEYS],
+                  "base": [self.buffers[k].data_ptr() for k in KEYS],
+                  "dims": L.Dims(batch_size, self.episode_limit, self.n_agents, self.n_actions, self.obs_shape, self.state_shape)}
+            for slot in range(2):
+                e64 = L.EpisodeF64()
+                hnp = st["host"][slot].numpy()
+                views = []
+                for i, k in enumerate(KEYS):
+                    setattr(e64, k, st["dev"][slot].data_ptr() + 8 * int(offs[i]))
+                    views.append(hnp[int(offs[i]):int(offs[i + 1])].reshape((batch_size,) + tuple(self.buffers[k].shape[1:])))
+                e64.u_is_int64 = 0
+                st["e64"].append(e64)
+                st["views"].append(views)
+            self._stage[batch_size] = st
+        slot = st["seq"] & 1
+        st["seq"] += 1
+        if st["done"][slot] is not None:
+            st["done"][slot].synchronize()
+        for view, k in zip(st["views"][slot], KEYS):
+            np.copyto(view, episode_batch[k], casting="unsafe")
+        st["dev"][slot].copy_(st["host"][slot], non_blocking=True)
+        e32 = L.EpisodeF32()
+        for i, k in enumerate(KEYS):
+            setattr(e32, k, st["base"][i] + start * st["row_bytes"][i])
+        L.call("marl_ingest_f64", C.byref(st["e64"][slot]), self.episode_limit, C.byref(st["dims"]), C.byref(e32), L.stream_ptr())
+        ev = th.cuda.Event()
+        ev.record()
+        st["done"][slot] = ev
+
     def store_episode(self, episode_batch):
         batch_size = episode_batch['o'].shape[0]
         with self.lock:
             idxs = self._get_storage_idx(inc=batch_size)
             idx_np = np.atleast_1d(np.asarray(idxs, dtype=np.int64))
-            idx_dev = th.from_numpy(idx_np).to(self.device)
-            for key in KEYS:
-                src = episode_batch[key]
-                want = th.int64 if key == 'u' else th.float32
-                if th.is_tensor(src):
-                    t = src.to(device=self.device)
-                    t = t.to(want) if t.dtype != want else t        # float -> int64 truncates toward zero like th.tensor(..., long)
-                else:
-                    a = np.ascontiguousarray(src)
-                    t = th.from_numpy(a).to(self.device, non_blocking=True).to(want)
-                self.buffers[key].index_copy_(0, idx_dev, t.reshape((batch_size,) + tuple(self.buffers[key].shape[1:])))
+            contiguous = batch_size == 1 or bool(np.all(np.diff(idx_np) == 1))
+            host_f64 = all(isinstance(episode_batch[k], np.ndarray) and episode_batch[k].dtype == np.float64 for k in KEYS
+                           if k != 'u') and isinstance(episode_batch['u'], np.ndarray) and episode_batch['u'].dtype.kind == 'f' \
+                and episode_batch['o'].shape[1] == self.episode_limit and self.device.type == "cuda"
+            if contiguous and host_f64:
+                self._store_host_f64(episode_batch, batch_size, int(idx_np[0]))
+            else:
+                self._store_generic(episode_batch, batch_size, idx_np)
             term = episode_batch['terminated']
             term = term.detach().cpu().numpy() if th.is_tensor(term) else np.asarray(term)
             term = term.reshape(batch_size, -1)[:, :self.episode_limit] == 1
             first = np.where(term.any(axis=1), term.argmax(axis=1), -1)
             self.first_terminated[idx_np] = first
             self.version[idx_np] += 1
+
+    def _store_generic(self, episode_batch, batch_size, idx_np):
+        """Any other input (CUDA tensors from the batched environment, int64 ``u``, wrapped ring positions): per-key copies."""
+        idx_dev = th.from_numpy(idx_np).to(self.device)
+        for key in KEYS:
+            src = episode_batch[key]
+            want = th.int64 if key == 'u' else th.float32
+            if th.is_tensor(src):
+                t = src.to(device=self.device)
+                t = t.to(want) if t.dtype != want else t        # float -> int64 truncates toward zero like th.tensor(..., long)
+            else:
+                a = np.ascontiguousarray(src)
+                t = th.from_numpy(a).to(self.device, non_blocking=True).to(want)
+            self.buffers[key].index_copy_(0, idx_dev, t.reshape((batch_size,) + tuple(self.buffers[key].shape[1:])))
 
     # ---- sample -----------------------------------------------------------------------------------
     def sample(self, batch_size):
@@ -149,8 +206,22 @@ class ReplayBuffer:
             versions = self.version[idx].copy()
         has = ft >= 0
         max_len = int(ft[has].max()) + 1 if has.any() else int(self.episode_limit)   # q_learner.py:49-61
-        return DeviceEpisodeBatch(self.buffers, idx, th.from_numpy(idx).to(self.device, non_blocking=True), max_len,
-                                  owner=self, versions=versions)
+        return DeviceEpisodeBatch(self.buffers, idx, self._indices_to_device(idx), max_len, owner=self, versions=versions)
+
+    def _indices_to_device(self, idx):
+        """Sampled ring rows -> device int64, through a small ring of pinned staging buffers (an asynchronous copy instead
+        of the blocking pageable one)."""
+        if self.device.type != "cuda":
+            return th.from_numpy(idx).to(self.device)
+        n = idx.shape[0]
+        ring = self._idx_stage.get(n)
+        if ring is None:
+            ring = {"host": [th.empty(n, dtype=th.int64).pin_memory() for _ in range(4)], "seq": 0}
+            self._idx_stage[n] = ring
+        h = ring["host"][ring["seq"] & 3]
+        ring["seq"] += 1
+        h.numpy()[:] = idx
+        return h.to(self.device, non_blocking=True)
 
     # ---- ring indices (common/replaybuffer.py:63-80) -----------------------------------------------
     def _get_storage_idx(self, inc=None):

@@ -158,8 +158,132 @@ def env_case():
     print("matrix_game_env ok")
 
 
+def choose_action_case():
+    """SharedMAC.choose_action (share_params.py:37-72) driven like rollout.py:60-76 for 6 steps on the literal 3s5z
+    observations / availability masks the reference keeps in test_file/choose_action_test.py:7-208: greedy steps
+    (epsilon 0) and exploring steps (epsilon 0.5) under a fixed numpy seed.  Stores inputs, actions and the hidden state
+    the controller carries after every step."""
+    src = open(os.path.join(REF, "test_file", "choose_action_test.py")).read()
+    i, j = src.index("obs = ["), src.index("avail_actions = ")
+    obs0 = np.stack(eval(src[i + 6:j].strip(), {"np": np}))                       # [8, 128] float32 literals
+    avail0 = np.array(eval(src[j + len("avail_actions = "):src.index("\n\n", j)]))   # [8, 14]
+    N, O = obs0.shape
+    A = avail0.shape[1]
+    th.manual_seed(0)
+    args = ref_args("qmix", N, A, O, 216, 150)
+    mac = SharedMAC(args)
+    out = {"meta/dims": np.array([N, A, O]), "meta/seed": np.array(7)}
+    dump_sd("init/agent", mac.agent.state_dict(), out)
+    n_steps = 6
+    eps = np.array([0.0, 0.0, 0.5, 0.5, 0.0, 0.5])
+    rng = np.random.RandomState(99)
+    obs = np.stack([obs0 * (1.0 + 0.05 * t) + 0.01 * rng.randn(N, O).astype(np.float32) for t in range(n_steps)]).astype(np.float32)
+    avail = np.stack([np.roll(avail0, t, axis=0) for t in range(n_steps)]).astype(np.float64)
+    avail[:, :, 0] = np.where(avail.sum(-1) == 0, 1.0, avail[:, :, 0])            # at least one action everywhere
+    avail[3, 2] = 0; avail[3, 2, 6] = 1                                              # a single available action
+    np.random.seed(7)
+    mac.init_hidden(1)
+    last = np.zeros((N, A))
+    actions = np.zeros((n_steps, N), dtype=np.int64)
+    hidden = np.zeros((n_steps, N, 64), dtype=np.float32)
+    with th.no_grad():
+        for t in range(n_steps):
+            for a in range(N):
+                act = int(mac.choose_action(obs[t, a], last[a], a, avail[t, a], eps[t]))
+                actions[t, a] = act
+                last[a] = np.eye(A)[act]
+            hidden[t] = mac.hidden_states[0].numpy()
+    out.update({"obs": obs, "avail": avail, "eps": eps, "actions": actions, "hidden": hidden})
+    np.savez_compressed(os.path.join(OUT, "choose_action_3s5z.npz"), **out)
+    print("choose_action_3s5z: actions", actions.tolist())
+
+
+def checkpoint_case():
+    """The trained 2s3z checkpoints the reference ships (model/{vdn,qplex,qtran_base}/2s3z) as realistic-valued weights:
+    copied as data fixtures, plus the losses of two reference train() steps on the seed-0 2s3z-shaped batch."""
+    dst = os.path.join(OUT, "ckpt")
+    os.makedirs(dst, exist_ok=True)
+    picks = {"vdn": ("2", ["rnn"]), "qplex": ("3", ["rnn", "mixer"]), "qtran_base": ("3", ["rnn", "mixer", "v"])}
+    batch = synthetic_batch(0, 32, 120, 5, 11, 80, 120)
+    out = {}
+    for alg, (num, parts) in picks.items():
+        for part in parts:
+            # (the shipped pickles carry CUDA storages: re-saved as CPU state_dicts, values untouched)
+            sd = th.load(os.path.join(REF, "model", alg, "2s3z", f"{num}_{part}_net_params.pkl"), map_location="cpu", weights_only=True)
+            th.save({k: v.clone() for k, v in sd.items()}, os.path.join(dst, f"{alg}_{part}.pkl"))
+        th.manual_seed(0)
+        args = ref_args(alg, 5, 11, 80, 120, 120)
+        mac = SharedMAC(args)
+        learner = QTRANLearner(mac, args) if alg == "qtran_base" else QLearner(mac, args)
+        mac.agent.load_state_dict(th.load(os.path.join(dst, f"{alg}_rnn.pkl"), weights_only=True))
+        if "mixer" in parts:
+            learner.mixer.load_state_dict(th.load(os.path.join(dst, f"{alg}_mixer.pkl"), weights_only=True))
+        if "v" in parts:
+            learner.v.load_state_dict(th.load(os.path.join(dst, f"{alg}_v.pkl"), weights_only=True))
+        learner.target_net.load_state(mac)
+        learner.target_mixer.load_state_dict(learner.mixer.state_dict())
+        losses = [learner.train({k: np.array(v) for k, v in batch.items()}, step) for step in range(2)]
+        out[f"{alg}/loss"] = np.array(losses, dtype=np.float64)
+        print("checkpoint", alg, losses)
+    np.savez_compressed(os.path.join(OUT, "checkpoint_losses.npz"), **out)
+
+
+def seeds_case():
+    """QMIX at the full 2s3z shape: per-step losses of 10 reference train() steps (seed 0) and of 3 steps for data seeds
+    1..4 (1 and 10 steps, seeds 0-4).  Only the losses are stored (the inputs are regenerated from the seed)."""
+    out = {}
+    for seed in range(5):
+        n_steps = 10 if seed == 0 else 3
+        th.manual_seed(seed)
+        args = ref_args("qmix", 5, 11, 80, 120, 120)
+        mac = SharedMAC(args)
+        learner = QLearner(mac, args)
+        for k, v in mac.agent.state_dict().items():
+            out[f"s{seed}/agent/{k}"] = v.numpy().copy()
+        for k, v in learner.mixer.state_dict().items():
+            out[f"s{seed}/mixer/{k}"] = v.numpy().copy()
+        batches = [synthetic_batch(100 * seed + i, 32, 120, 5, 11, 80, 120) for i in range(2)]
+        losses = [learner.train({k: np.array(v) for k, v in batches[i % 2].items()}, i) for i in range(n_steps)]
+        out[f"s{seed}/loss"] = np.array(losses, dtype=np.float64)
+        print("seed", seed, losses)
+    np.savez_compressed(os.path.join(OUT, "qmix_2s3z_seeds.npz"), **out)
+
+
+def rollout_case():
+    """The UNMODIFIED reference RolloutWorker (rollout.py:30-173) playing 7 greedy (evaluate=True) episodes of the
+    multi-step test game of tests/envs.py: ragged lengths, step-dependent availability, padding to episode_limit.
+    Pins the episode layout, the padding rules (rollout.py:122-133) and the greedy actions for the batched worker."""
+    from rollout import RolloutWorker
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from tests.envs import CountdownGameHost
+    env = CountdownGameHost()
+    info = env.get_env_info()
+    th.manual_seed(5)
+    args = ref_args("qmix", info["n_agents"], info["n_actions"], info["obs_shape"], info["state_shape"], info["episode_limit"])
+    args.epsilon, args.anneal_epsilon, args.min_epsilon, args.epsilon_anneal_scale = 0.5, 0.01, 0.02, "step"
+    mac = SharedMAC(args)
+    worker = RolloutWorker(env, mac, args)
+    n = 7
+    np.random.seed(3)
+    episodes, rewards, wins, steps = worker.generate_episodes(n_episodes=n, evaluate=True)
+    out = {"meta/dims": np.array([info["n_agents"], info["n_actions"], info["obs_shape"], info["state_shape"], info["episode_limit"]]),
+           "meta/n": np.array(n), "rewards": np.array(rewards, dtype=np.float64), "steps": np.array(steps)}
+    dump_sd("init/agent", mac.agent.state_dict(), out)
+    for k, v in episodes.items():
+        out[f"episodes/{k}"] = np.asarray(v, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "rollout_multistep.npz"), **out)
+    lens = (1 - out["episodes/padded"][:, :, 0]).sum(1)
+    print("rollout_multistep: steps", steps, "lengths", lens.tolist(), "rewards", rewards)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    extra = {"rollout": rollout_case, "choose_action": choose_action_case, "checkpoints": checkpoint_case, "seeds": seeds_case}
+    picked = [k for k in sys.argv[1:] if k in extra]
+    if picked:                              # round-2 fixtures (the round-1 fixtures stay as committed)
+        for k in picked:
+            extra[k]()
+        return
     tiny = dict(N=3, A=4, O=5, S=6, T=6)
     tb = synthetic_batch(0, 4, tiny["T"], tiny["N"], tiny["A"], tiny["O"], tiny["S"])
     small_qplex = dict(num_kernel=2, adv_hypernet_embed=8, hypernet_embed=8)

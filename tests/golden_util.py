@@ -10,9 +10,13 @@ from oracle import marl_oracle as MO
 GOLDEN_DIR = os.path.join(os.path.dirname(__file__), "golden")
 
 
+# fixtures with their own layout (tests of their own): not full learner cases
+OTHER_FIXTURES = ("matrix_game_env", "choose_action_3s5z", "checkpoint_losses", "qmix_2s3z_seeds", "rollout_multistep")
+
+
 def learner_cases():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith("matrix_game_env"))
+                  if not os.path.basename(p).startswith(OTHER_FIXTURES))
 
 
 def load(name):

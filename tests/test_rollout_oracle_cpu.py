@@ -58,3 +58,20 @@ def test_rollout_oracle_matches_reference(scale, capsys):
     assert np.array_equal(np.asarray(episodes["u"]).reshape(40, 2).astype(np.int64), u)
     assert np.array_equal(np.asarray(rewards, dtype=np.float64), r)
     assert worker.epsilon == eps and steps == 40
+
+
+def test_multistep_rollout_oracle_matches_reference_worker_golden():
+    """oracle.rollout_oracle.rollout_multistep against the UNMODIFIED reference RolloutWorker on the ragged multi-step
+    test game (tests/golden/rollout_multistep.npz, made by oracle/make_golden.py rollout): every key of the padded
+    episode batch, the episode rewards and the step count, bit for bit."""
+    from tests import golden_util as GU
+    from tests.envs import CountdownGameHost
+    z = GU.load("rollout_multistep")
+    n = int(z["meta/n"])
+    np.random.seed(3)
+    eps, rewards, steps = RO.rollout_multistep(GU.group(z, "init/agent"), CountdownGameHost(), n, 0.5, 0.01, 0.02, "step", evaluate=True)
+    for k in ("o", "s", "u", "r", "avail_u", "o_next", "s_next", "avail_u_next", "u_onehot", "padded", "terminated"):
+        assert np.array_equal(eps[k], z[f"episodes/{k}"]), k
+    assert np.array_equal(np.array(rewards), z["rewards"]) and steps == int(z["steps"])
+    lens = (1 - eps["padded"][:, :, 0]).sum(1)
+    assert lens.min() < lens.max() == 6            # the fixture really is ragged and reaches the limit
