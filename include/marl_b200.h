@@ -249,7 +249,10 @@ int marl_qmix_mix_bwd(int M, int N, const marl_qmix_params* p, const float* q, c
  *   w3k [K, ae]           key.k.4          w3n [2K, N, ae]  agents.k.4 | action.k.4
  *   wfv [2, N, he]        hyper_w_final.2 | V.2            (biases b* in the same order)
  * Workspaces (kept for the backward): h1 [M, 2he + 3K*ae], h2 [M, 3K*ae], o3 [M, K + 2K*N], wv [M, 2N]. */
-typedef struct marl_qplex_dims { int N, A, S, he, ae, K, weighted_head, is_minus_one; } marl_qplex_dims;
+/* layers = adv_hypernet_layers (network/mixer.py:115-145; 0 means 3).  2: no w2 / b2, the output layers (w3k / w3n) read the
+ * extractor block of h1; 1: single-Linear extractors, w3k = [K key rows | K*N agents rows] x S, w3n = [K*N, S + N*A], no w1a /
+ * b1a / w2 / b2 and w1s / b1s hold only hyper_w_final.0 | V.0 (h1 [M, 2he]). */
+typedef struct marl_qplex_dims { int N, A, S, he, ae, K, weighted_head, is_minus_one, layers; } marl_qplex_dims;
 typedef struct marl_qplex_params {
     const float *w1s, *b1s, *w1a, *b1a, *w2, *b2, *w3k, *b3k, *w3n, *b3n, *wfv, *bfv;
 } marl_qplex_params;

@@ -89,7 +89,7 @@ class QmixHyper2Grads(C.Structure):
 
 
 class QplexDims(C.Structure):
-    _fields_ = [(k, C.c_int) for k in ("N", "A", "S", "he", "ae", "K", "weighted_head", "is_minus_one")]
+    _fields_ = [(k, C.c_int) for k in ("N", "A", "S", "he", "ae", "K", "weighted_head", "is_minus_one", "layers")]
 
 
 QPLEX_FIELDS = ("w1s", "b1s", "w1a", "b1a", "w2", "b2", "w3k", "b3k", "w3n", "b3n", "wfv", "bfv")

@@ -101,6 +101,7 @@ class QLearner:
         self.launches_per_step = 0
         self.ingest_launches = 1
         self._inplace_keep, self._max_inplace_graphs = {}, 32
+        self._capture_after = int(getattr(args, "graph_capture_after", 2))      # eager sightings of a (B, L) before its graph is captured
 
     # ---- construction helpers ---------------------------------------------------------------------
     def _make_mixer(self, args):
@@ -116,16 +117,26 @@ class QLearner:
     def _pack(self):
         """All optimised tensors into one flat buffer (+grad +2 tail scalars); targets mirror it."""
         dev = self._dev
-        named = prefixed("agent.", self.eval_net.agent.flat_named_parameters())
+        separated = isinstance(self.eval_net.agent, (list, tuple))          # SeparatedMAC: one network per agent
+        agents_of = lambda mac: list(mac.agent) if separated else [mac.agent]
+        tag = (lambda i: f"agent.{i}.") if separated else (lambda i: "agent.")
+        named = []
+        for i, ag in enumerate(agents_of(self.eval_net)):
+            named += prefixed(tag(i), ag.flat_named_parameters())
         named += prefixed("mixer.", self.mixer.flat_named_parameters())
         for prefix, module in self._extra_groups():
             named += prefixed(prefix, module.flat_named_parameters())
         self._flat = FlatBuffer(named, device=dev, with_grad=True, extra_tail=2)
-        tnamed = prefixed("agent.", self.target_net.agent.flat_named_parameters())
+        tnamed = []
+        for i, ag in enumerate(agents_of(self.target_net)):
+            tnamed += prefixed(tag(i), ag.flat_named_parameters())
         tnamed += prefixed("mixer.", self.target_mixer.flat_named_parameters())
         self._tflat = FlatBuffer(tnamed, device=dev, with_grad=False)
-        self.eval_net.agent.adopt(self._flat)
-        self.target_net.agent.adopt(self._tflat)
+        for ag in agents_of(self.eval_net):
+            ag.adopt(self._flat)
+        for ag in agents_of(self.target_net):
+            ag.adopt(self._tflat)
+        self._separated = separated
         if hasattr(self.mixer, "adopt"):
             self.mixer.adopt(self._flat)
             self.target_mixer.adopt(self._tflat)
@@ -486,9 +497,10 @@ class QLearner:
             M = B * Lq
             qd = qplex_dims(a)
             K = a.num_kernel
-            p = qplex_struct(lambda n: self._flat.ptr("mixer." + n), K)
-            ptg = qplex_struct(lambda n: self._tflat.ptr("mixer." + n), K)
-            g = qplex_struct(lambda n: self._flat.ptr("mixer." + n, self._flat.grad), K, L.QplexGrads)
+            nl = int(getattr(a, "adv_hypernet_layers", 1))
+            p = qplex_struct(lambda n: self._flat.ptr("mixer." + n), K, layers=nl)
+            ptg = qplex_struct(lambda n: self._tflat.ptr("mixer." + n), K, layers=nl)
+            g = qplex_struct(lambda n: self._flat.ptr("mixer." + n, self._flat.grad), K, L.QplexGrads, layers=nl)
             wse, wst, dws = ws_struct(ws["qp"]), ws_struct(ws["qp_t"]), ws_struct(ws["dqp"])
             # q_tot = v_tot + a_tot (q_learner.py:120-135); target likewise with the eval net's argmax (:138-158)
             L.call("marl_qplex_fwd", M, C.byref(qd), C.byref(p), ws["q_chosen"].data_ptr(), bt["s"].data_ptr(),
@@ -575,10 +587,13 @@ class QLearner:
             return
         key = (B, Lq) + tuple(bt[k].data_ptr() for k in BATCH_KEYS)
         entry = self._graphs.get(key)
-        if entry is None:
-            # first call with this shape runs eagerly (lazy CUDA/NCCL init must not happen in capture)
+        if entry is None or isinstance(entry, int):
+            # the first calls with a shape run eagerly (lazy CUDA/NCCL init must not happen in capture).  A graph is only
+            # captured at the third sighting: replay batches come with many different max_episode_len values, most of
+            # them rare, and a capture (~tens of ms) is only worth it for the lengths that keep coming back
             self.launches_per_step = self._device_step(bt, ws, B, Lq)
-            self._graphs[key] = "warm"
+            seen = (entry or 0) + 1
+            self._graphs[key] = "warm" if seen >= self._capture_after else seen
             return
         if entry == "warm":
             if self._dist is None or self._peer is not None:
@@ -614,6 +629,8 @@ class QLearner:
         drives the target sync exactly like the reference's ``train_step``."""
         if self._dev.type != "cuda":
             raise L.MarlLibraryError("QLearner.train needs a CUDA device: marl_b200 has no CPU path")
+        if self._separated or getattr(self.args, "train_through_modules", False):
+            return self._train_modules(batch, train_step)
         if isinstance(batch, DeviceEpisodeBatch):
             bt, B, Lq, _ = self._stage_replay_batch(batch)
             ws = self._workspace(B, Lq)
@@ -635,6 +652,82 @@ class QLearner:
         if self._peer is not None and float(self._loss_host[0]) != float(self._loss_host[0]) and int(self._peer.state[1]):
             raise RuntimeError("marl_clip_step_peer: a data-parallel peer did not reach the gradient exchange in time")
         self.last = dict(B=B, L=Lq, ws=ws, batch=bt, grad_norm=float(self._loss_host[1]))
+        return float(self._loss_host[0])
+
+    # ---- the same step through the drop-in MODULE surface (autograd over the library's kernels) -------------------------
+    def _train_modules(self, batch, train_step):
+        """q_learner.py:68-179 written against the controller / mixer modules: every unroll and every mixer call is a
+        libmarl_b200 kernel sequence behind a torch.autograd.Function, the gather / mask / TD arithmetic between them is
+        torch on the GPU, clip + RMSprop/Adam is the flat optimiser kernel.  This is what SeparatedMAC trains with (its
+        per-agent weights do not fit the shared-weight fused kernels), and an independent second implementation of the
+        fused step for the tests."""
+        a, dev = self.args, self._dev
+        if isinstance(batch, DeviceEpisodeBatch):
+            Lq = batch.max_episode_len
+        else:
+            Lq = host_max_episode_len(_to_numpy(batch["terminated"]), a.episode_limit)
+        b = {}
+        for k in BATCH_KEYS:
+            t = batch[k]
+            t = th.as_tensor(_to_numpy(t)) if not th.is_tensor(t) else t
+            b[k] = t[:, :Lq].to(device=dev, dtype=th.int64 if k == "u" else th.float32)
+        B = b["o"].shape[0]
+        s, u, r, s_next, avail_u, avail_u_next, terminated = (b[k] for k in ("s", "u", "r", "s_next", "avail_u", "avail_u_next",
+                                                                               "terminated"))
+        u = u.reshape(B, Lq, a.n_agents, 1)
+        r, terminated = r.reshape(B, Lq, 1), terminated.reshape(B, Lq, 1)
+        mask = 1 - b["padded"].reshape(B, Lq, 1)
+        self.eval_net.init_hidden(B)
+        q_evals, _ = self.eval_net.get_current_q_values(b, Lq)
+        q_chosen = th.gather(q_evals, dim=3, index=u).squeeze(3)
+        with th.no_grad():
+            self.target_net.init_hidden(B)
+            q_targets, _ = self.target_net.get_next_q_values(b, Lq)
+            q_targets = q_targets.clone()
+            q_targets[avail_u_next == 0.0] = -9999999
+            if a.double_q:
+                q_next = self.eval_net.get_next_q_values(b, Lq)[0].clone()        # hidden carried (q_learner.py:110)
+                q_next[avail_u_next == 0] = -9999999
+                a_star = th.argmax(q_next, dim=3, keepdim=True)
+                q_tc = th.gather(q_targets, 3, a_star).squeeze(3)
+            else:
+                a_star = None
+                q_tc = q_targets.max(dim=3)[0]
+        if a.alg == "qplex":
+            v_tot = self.mixer(q_chosen, s, is_v=True)
+            qd = q_evals.detach().clone()
+            qd[avail_u == 0] = -9999999
+            a_tot = self.mixer(q_chosen, s, actions=b["u_onehot"], max_q_i=qd.max(dim=3)[0], is_v=False)
+            q_tot = v_tot + a_tot
+            with th.no_grad():
+                if a.double_q:
+                    oh = th.zeros_like(q_targets).scatter_(3, a_star, 1)
+                    tv = self.target_mixer(q_tc, s_next, is_v=True)
+                    ta = self.target_mixer(q_tc, s_next, actions=oh, max_q_i=q_targets.max(dim=3)[0], is_v=False)
+                    q_tot_t = tv + ta
+                else:
+                    q_tot_t = self.target_mixer(q_tc, s_next, is_v=True)
+        else:
+            q_tot = self.mixer(q_chosen, s)
+            with th.no_grad():
+                q_tot_t = self.target_mixer(q_tc, s_next)
+        targets = r + self.gamma * q_tot_t * (1 - terminated)
+        masked = mask * (q_tot - targets.detach())
+        loss = (masked ** 2).sum() / mask.sum()
+        self._flat.grad_full.zero_()
+        self._flat.rebind_grads()
+        loss.backward()
+        # the optimiser kernel expects the gradient of the UN-normalised sum and (loss_sum, mask_sum): hand it the
+        # normalised gradient with mask_sum = 1
+        self._flat.tail.copy_(th.stack([loss.detach(), th.ones((), device=dev)]))
+        self._launch_optimizer()
+        if train_step > 0 and train_step % a.target_update_cycle == 0:
+            self._update_targets()
+        self._loss_host.copy_(self._loss_out, non_blocking=True)
+        th.cuda.current_stream().synchronize()
+        self.max_episode_len = Lq
+        self.last = dict(B=B, L=Lq, q_evals=q_evals.detach(), q_tot=q_tot.detach(), a_star=a_star,
+                         grad_norm=float(self._loss_host[1]))
         return float(self._loss_host[0])
 
     def _update_targets(self):

@@ -441,8 +441,10 @@ static void plan_rows(GruFwdArgs& ga, int rows, int n_ctas) {
     }
 }
 
+// (O may be 0 or negative for a FULL input, where only O + A + N = the network's input width is meaningful; the entry points
+// check O > 0 for the composed [obs | last_action | agent_id] input)
 static int check_dims(const marl_dims* d) {
-    if (!d || d->B <= 0 || d->L <= 0 || d->N <= 0 || d->A <= 0 || d->O <= 0 || d->S < 0) return MARL_EINVAL;
+    if (!d || d->B <= 0 || d->L <= 0 || d->N <= 0 || d->A <= 0 || d->O + d->A + d->N <= 0 || d->S < 0) return MARL_EINVAL;
     return MARL_OK;
 }
 
@@ -469,6 +471,7 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
     const int I = d->O + d->A + d->N;
     for (int i = 0; i < n_streams; ++i) {
         if (!s[i].obs || (!s[i].onehot && !s[i].full_input) || !s[i].hidden || !s[i].x || !s[i].gi) return MARL_EINVAL;
+        if (!s[i].full_input && d->O <= 0) return MARL_EINVAL;
         if (s[i].h0_from >= i) return MARL_EINVAL;
     }
     // phase A: x = relu(fc1(input)), gi = W_ih x + b_ih for every stream
@@ -575,6 +578,7 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
 extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* a, void* stream) {
     if (check_dims(d) || !a || !a->hidden || !a->x || !a->gates || !a->dgi || !a->dgh || !a->dx) return MARL_EINVAL;
     if (a->dq && !a->dhext) return MARL_EINVAL;
+    if (!a->full_input && d->O <= 0) return MARL_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     pdl_scope((long long)d->B * d->L * d->N);
     const int rows_total = d->B * d->L * d->N;

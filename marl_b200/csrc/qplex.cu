@@ -92,14 +92,27 @@ __global__ void __launch_bounds__(256) scatter_dq_kernel(int rows, int A, const 
     for (int c = 0; c < A; ++c) dq[(long long)i * A + c] = (c == ua) ? g : 0.0f;
 }
 
-struct QplexLayout { int he, ae, K, N, A, S, Ws, W1, W2, W3; };
+// `layers` = adv_hypernet_layers (network/mixer.py:115-145): Linear layers per lambda extractor.
+//   3 (default): L1 -> ReLU -> L2 -> ReLU -> L3 ; 2: L1 -> ReLU -> L3 (the first hidden layer feeds the output layer: h2 is h1's
+//   extractor block) ; 1: one Linear straight from the state / [state | actions] (no extractor columns in h1 at all).
+struct QplexLayout { int he, ae, K, N, A, S, Ws, W1, W2, W3, layers; };
 static QplexLayout layout(const marl_qplex_dims* d) {
-    QplexLayout l{d->he, d->ae, d->K, d->N, d->A, d->S, 0, 0, 0, 0};
-    l.Ws = 2 * d->he + 2 * d->K * d->ae;
-    l.W1 = l.Ws + d->K * d->ae;
-    l.W2 = 3 * d->K * d->ae;
+    QplexLayout l{d->he, d->ae, d->K, d->N, d->A, d->S, 0, 0, 0, 0, d->layers ? d->layers : 3};
+    const int ext = l.layers == 1 ? 0 : d->K * d->ae;          // hidden columns per extractor family
+    l.Ws = 2 * d->he + 2 * ext;
+    l.W1 = l.Ws + ext;
+    l.W2 = 3 * ext;
     l.W3 = d->K + 2 * d->K * d->N;
     return l;
+}
+// where the output layers of the extractors read their input: h2 (3 layers) or the extractor block of h1 (2 layers)
+static const float* ext_hidden(const QplexLayout& l, const marl_qplex_ws* ws, int& pitch) {
+    if (l.layers == 3) { pitch = l.W2; return ws->h2; }
+    pitch = l.W1; return ws->h1 + 2 * l.he;
+}
+static float* ext_hidden_mut(const QplexLayout& l, const marl_qplex_ws* ws, int& pitch) {
+    if (l.layers == 3) { pitch = l.W2; return ws->h2; }
+    pitch = l.W1; return ws->h1 + 2 * l.he;
 }
 
 static int qplex_forward_gemms(int M, const QplexLayout& l, const marl_qplex_params* p, const float* s, const float* actions,
@@ -120,6 +133,21 @@ static int qplex_forward_gemms(int M, const QplexLayout& l, const marl_qplex_par
         if ((rc = linear_fwd(f, st))) return rc;
     }
     if (!with_adv) return MARL_OK;
+    if (l.layers == 1) {
+        // single-Linear extractors: o3 = [key_k(s) | agents_k(s) | action_k([s | a])] in two GEMMs (w3k holds the K key rows
+        // followed by the K*N agents rows, w3n the K*N action rows)
+        LinearFwd f{};
+        f.in = plain_operand(s, l.S, l.S);
+        f.w = p->w3k; f.ldw = l.S; f.bias = p->b3k; f.y = ws->o3; f.ldy = l.W3; f.M = M; f.N = l.K + l.K * l.N; f.batch = 1;
+        if ((rc = linear_fwd(f, st))) return rc;
+        LinearFwd g{};
+        LinOperand in = plain_operand(s, l.S, l.S);
+        in.x2 = actions; in.ldx2 = l.N * l.A; in.K2 = l.N * l.A;
+        g.in = in;
+        g.w = p->w3n; g.ldw = l.S + l.N * l.A; g.bias = p->b3n; g.y = ws->o3 + l.K + l.K * l.N; g.ldy = l.W3;
+        g.M = M; g.N = l.K * l.N; g.batch = 1;
+        return linear_fwd(g, st);
+    }
     {   // L1a on the virtual concatenation [s | actions]
         LinearFwd f{};
         LinOperand in = plain_operand(s, l.S, l.S);
@@ -129,23 +157,25 @@ static int qplex_forward_gemms(int M, const QplexLayout& l, const marl_qplex_par
         f.M = M; f.N = l.K * l.ae; f.relu = 1; f.batch = 1;
         if ((rc = linear_fwd(f, st))) return rc;
     }
-    {   // L2, batched over the 3K extractors
+    if (l.layers == 3) {   // L2, batched over the 3K extractors
         LinearFwd f{};
         f.in = plain_operand(ws->h1 + 2 * l.he, l.W1, l.ae, l.ae);
         f.w = p->w2; f.ldw = l.ae; f.w_bs = (long long)l.ae * l.ae; f.bias = p->b2; f.b_bs = l.ae;
         f.y = ws->h2; f.ldy = l.W2; f.y_bs = l.ae; f.M = M; f.N = l.ae; f.relu = 1; f.batch = 3 * l.K;
         if ((rc = linear_fwd(f, st))) return rc;
     }
+    int hp;
+    const float* hx = ext_hidden(l, ws, hp);
     {   // L3k
         LinearFwd f{};
-        f.in = plain_operand(ws->h2, l.W2, l.ae, l.ae);
+        f.in = plain_operand(hx, hp, l.ae, l.ae);
         f.w = p->w3k; f.ldw = l.ae; f.w_bs = l.ae; f.bias = p->b3k; f.b_bs = 1;
         f.y = ws->o3; f.ldy = l.W3; f.y_bs = 1; f.M = M; f.N = 1; f.batch = l.K;
         if ((rc = linear_fwd(f, st))) return rc;
     }
     {   // L3n
         LinearFwd f{};
-        f.in = plain_operand(ws->h2 + l.K * l.ae, l.W2, l.ae, l.ae);
+        f.in = plain_operand(hx + l.K * l.ae, hp, l.ae, l.ae);
         f.w = p->w3n; f.ldw = l.ae; f.w_bs = (long long)l.N * l.ae; f.bias = p->b3n; f.b_bs = l.N;
         f.y = ws->o3 + l.K; f.ldy = l.W3; f.y_bs = l.N; f.M = M; f.N = l.N; f.batch = 2 * l.K;
         if ((rc = linear_fwd(f, st))) return rc;
@@ -154,9 +184,13 @@ static int qplex_forward_gemms(int M, const QplexLayout& l, const marl_qplex_par
 }
 
 static bool qplex_ok(const marl_qplex_dims* d, const marl_qplex_params* p, const marl_qplex_ws* ws) {
-    return d && p && ws && d->N >= 1 && d->N <= 32 && d->K >= 1 && d->he >= 1 && d->ae >= 1 && d->S >= 1 && d->A >= 1 &&
-           p->w1s && p->b1s && p->w1a && p->b1a && p->w2 && p->b2 && p->w3k && p->b3k && p->w3n && p->b3n && p->wfv &&
-           p->bfv && ws->h1 && ws->h2 && ws->o3 && ws->wv;
+    if (!(d && p && ws && d->N >= 1 && d->N <= 32 && d->K >= 1 && d->he >= 1 && d->ae >= 1 && d->S >= 1 && d->A >= 1)) return false;
+    const int layers = d->layers ? d->layers : 3;
+    if (layers < 1 || layers > 3) return false;
+    if (!(p->w1s && p->b1s && p->w3k && p->b3k && p->w3n && p->b3n && p->wfv && p->bfv && ws->h1 && ws->o3 && ws->wv)) return false;
+    if (layers >= 2 && !(p->w1a && p->b1a)) return false;
+    if (layers == 3 && !(p->w2 && p->b2 && ws->h2)) return false;
+    return true;
 }
 
 }  // namespace marl
@@ -189,7 +223,7 @@ extern "C" int marl_qplex_bwd(int M, const marl_qplex_dims* d, const marl_qplex_
                               const float* da_tot, const marl_qplex_ws* dws, float* dq, const marl_qplex_grads* g,
                               void* stream) {
     if (M < 0 || !qplex_ok(d, p, ws) || !q || !s || (!dv_tot && !da_tot) || !dws || !dq || !g) return MARL_EINVAL;
-    if (!dws->h1 || !dws->h2 || !dws->o3 || !dws->wv) return MARL_EINVAL;
+    if (!dws->h1 || !dws->o3 || !dws->wv || ((d->layers ? d->layers : 3) == 3 && !dws->h2)) return MARL_EINVAL;
     if (da_tot && !actions) return MARL_EINVAL;
     const bool with_adv = actions != nullptr && da_tot != nullptr;
     if (with_adv && !max_q) return MARL_EINVAL;
@@ -217,29 +251,44 @@ extern "C" int marl_qplex_bwd(int M, const marl_qplex_dims* d, const marl_qplex_
         dg.M = M; dg.N = l.N; dg.K = l.he; dg.batch = 2;
         if ((rc = linear_dgrad(dg, st))) return rc;
     }
-    if (with_adv) {
+    if (with_adv && l.layers == 1) {
+        // single-Linear extractors: only weight gradients (their inputs, the state and the actions, need none)
+        LinearWgrad w{};
+        w.dy = dws->o3; w.lddy = l.W3; w.in = plain_operand(s, l.S, l.S);
+        w.dw = g->w3k; w.ldw = l.S; w.db = g->b3k; w.M = M; w.N = l.K + l.K * l.N; w.batch = 1;
+        if ((rc = linear_wgrad(w, st))) return rc;
+        LinearWgrad w2{};
+        LinOperand in = plain_operand(s, l.S, l.S);
+        in.x2 = actions; in.ldx2 = l.N * l.A; in.K2 = l.N * l.A;
+        w2.dy = dws->o3 + l.K + l.K * l.N; w2.lddy = l.W3; w2.in = in;
+        w2.dw = g->w3n; w2.ldw = l.S + l.N * l.A; w2.db = g->b3n; w2.M = M; w2.N = l.K * l.N; w2.batch = 1;
+        if ((rc = linear_wgrad(w2, st))) return rc;
+    } else if (with_adv) {
+        int hp, dhp;
+        const float* hx = ext_hidden(l, ws, hp);
+        float* dhx = ext_hidden_mut(l, dws, dhp);
         {   // L3k / L3n backward
             LinearWgrad w{};
-            w.dy = dws->o3; w.lddy = l.W3; w.dy_bs = 1; w.in = plain_operand(ws->h2, l.W2, l.ae, l.ae);
+            w.dy = dws->o3; w.lddy = l.W3; w.dy_bs = 1; w.in = plain_operand(hx, hp, l.ae, l.ae);
             w.dw = g->w3k; w.ldw = l.ae; w.dw_bs = l.ae; w.db = g->b3k; w.db_bs = 1; w.M = M; w.N = 1; w.batch = l.K;
             if ((rc = linear_wgrad(w, st))) return rc;
             LinearDgrad dg{};
             dg.dy = dws->o3; dg.lddy = l.W3; dg.dy_bs = 1; dg.w = p->w3k; dg.ldw = l.ae; dg.w_bs = l.ae;
-            dg.dx = dws->h2; dg.lddx = l.W2; dg.dx_bs = l.ae; dg.relu_src = ws->h2; dg.ldrs = l.W2; dg.rs_bs = l.ae;
+            dg.dx = dhx; dg.lddx = dhp; dg.dx_bs = l.ae; dg.relu_src = hx; dg.ldrs = hp; dg.rs_bs = l.ae;
             dg.M = M; dg.N = 1; dg.K = l.ae; dg.batch = l.K;
             if ((rc = linear_dgrad(dg, st))) return rc;
             LinearWgrad w2{};
-            w2.dy = dws->o3 + l.K; w2.lddy = l.W3; w2.dy_bs = l.N; w2.in = plain_operand(ws->h2 + l.K * l.ae, l.W2, l.ae, l.ae);
+            w2.dy = dws->o3 + l.K; w2.lddy = l.W3; w2.dy_bs = l.N; w2.in = plain_operand(hx + l.K * l.ae, hp, l.ae, l.ae);
             w2.dw = g->w3n; w2.ldw = l.ae; w2.dw_bs = (long long)l.N * l.ae; w2.db = g->b3n; w2.db_bs = l.N;
             w2.M = M; w2.N = l.N; w2.batch = 2 * l.K;
             if ((rc = linear_wgrad(w2, st))) return rc;
             LinearDgrad d2{};
             d2.dy = dws->o3 + l.K; d2.lddy = l.W3; d2.dy_bs = l.N; d2.w = p->w3n; d2.ldw = l.ae; d2.w_bs = (long long)l.N * l.ae;
-            d2.dx = dws->h2 + l.K * l.ae; d2.lddx = l.W2; d2.dx_bs = l.ae; d2.relu_src = ws->h2 + l.K * l.ae; d2.ldrs = l.W2;
+            d2.dx = dhx + l.K * l.ae; d2.lddx = dhp; d2.dx_bs = l.ae; d2.relu_src = hx + l.K * l.ae; d2.ldrs = hp;
             d2.rs_bs = l.ae; d2.M = M; d2.N = l.N; d2.K = l.ae; d2.batch = 2 * l.K;
             if ((rc = linear_dgrad(d2, st))) return rc;
         }
-        {   // L2 backward
+        if (l.layers == 3) {   // L2 backward
             LinearWgrad w{};
             w.dy = dws->h2; w.lddy = l.W2; w.dy_bs = l.ae; w.in = plain_operand(ws->h1 + 2 * l.he, l.W1, l.ae, l.ae);
             w.dw = g->w2; w.ldw = l.ae; w.dw_bs = (long long)l.ae * l.ae; w.db = g->b2; w.db_bs = l.ae;

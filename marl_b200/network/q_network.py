@@ -134,6 +134,14 @@ class RNNQNet(FlatPackedMixin, nn.Module):
         q, hidden, _ = _UnrollFn.apply(obs, None, h_in, 0, 1, dims, *params)
         return q.view(R, A), hidden.view(R, H)
 
+    def unroll_full(self, x, h0):
+        """x [B, T, 1, input_shape] (already the full network input) -> q [B,T,1,A], hidden [B,T,1,H], h_last [B,H]."""
+        B, T, _, I = x.shape
+        A = self.args.n_actions
+        dims = (B, T, 1, A, I - A - 1)                 # only O + A + N = input_shape matters for a full input
+        params = [p for _, p in self.flat_named_parameters()]
+        return _UnrollFn.apply(x, None, h0, 0, 1, dims, *params)
+
     def unroll(self, obs, onehot, h0, shift):
         """[B,T,N,O], [B,T,N,A] -> q [B,T,N,A], hidden [B,T,N,H], h_last [B*N,H]."""
         B, T, N, O = obs.shape

@@ -33,20 +33,43 @@ class DMAQ_SI_Weight(nn.Module):
         self.action_dim = args.n_agents * args.n_actions
         self.state_action_dim = self.state_dim + self.action_dim
         self.num_kernel = args.num_kernel
-        if getattr(args, "adv_hypernet_layers", 1) != 3:
-            raise NotImplementedError("libmarl_b200 implements the default adv_hypernet_layers = 3")
+        self.layers = int(getattr(args, "adv_hypernet_layers", 1))      # the reference's getattr default (mixer.py:115)
+        if self.layers not in (1, 2, 3):
+            raise Exception("Error setting number of adv hypernet layers.")       # mixer.py:145
         ae = args.adv_hypernet_embed
+
+        def ext(n_in, n_out):
+            if self.layers == 1:
+                return nn.Linear(n_in, n_out)
+            if self.layers == 2:
+                return nn.Sequential(nn.Linear(n_in, ae), nn.ReLU(), nn.Linear(ae, n_out))
+            return _mlp3(n_in, ae, n_out)
+
         self.key_extractors, self.agents_extractors, self.action_extractors = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
         for _ in range(self.num_kernel):
-            self.key_extractors.append(_mlp3(self.state_dim, ae, 1))
-            self.agents_extractors.append(_mlp3(self.state_dim, ae, self.n_agents))
-            self.action_extractors.append(_mlp3(self.state_action_dim, ae, self.n_agents))
+            self.key_extractors.append(ext(self.state_dim, 1))
+            self.agents_extractors.append(ext(self.state_dim, self.n_agents))
+            self.action_extractors.append(ext(self.state_action_dim, self.n_agents))
 
 
-def qplex_flat_order(K):
-    """Parameter names in flat order; entries after the first of each group are packed tight."""
+def qplex_flat_order(K, layers=3):
+    """Parameter names in flat order; entries after the first of each group are packed tight.  `layers` =
+    adv_hypernet_layers: the extractors' output layer is ``.4`` (3 layers), ``.2`` (2 layers) or the bare Linear (1 layer,
+    where the key and agents extractors form ONE [K + K*N, S] matrix and there is no extractor hidden layer at all)."""
     ks = range(K)
     si = "si_weight."
+    if layers == 1:
+        return {
+            "w1s": ["hyper_w_final.0.weight", "V.0.weight"],
+            "b1s": ["hyper_w_final.0.bias", "V.0.bias"],
+            "w3k": [f"{si}key_extractors.{k}.weight" for k in ks] + [f"{si}agents_extractors.{k}.weight" for k in ks],
+            "b3k": [f"{si}key_extractors.{k}.bias" for k in ks] + [f"{si}agents_extractors.{k}.bias" for k in ks],
+            "w3n": [f"{si}action_extractors.{k}.weight" for k in ks],
+            "b3n": [f"{si}action_extractors.{k}.bias" for k in ks],
+            "wfv": ["hyper_w_final.2.weight", "V.2.weight"],
+            "bfv": ["hyper_w_final.2.bias", "V.2.bias"],
+        }
+    out = 2 * (layers - 1)
     groups = {
         "w1s": ["hyper_w_final.0.weight", "V.0.weight"] + [f"{si}key_extractors.{k}.0.weight" for k in ks]
                + [f"{si}agents_extractors.{k}.0.weight" for k in ks],
@@ -54,35 +77,45 @@ def qplex_flat_order(K):
                + [f"{si}agents_extractors.{k}.0.bias" for k in ks],
         "w1a": [f"{si}action_extractors.{k}.0.weight" for k in ks],
         "b1a": [f"{si}action_extractors.{k}.0.bias" for k in ks],
-        "w2": [f"{si}{t}_extractors.{k}.2.weight" for t in ("key", "agents", "action") for k in ks],
-        "b2": [f"{si}{t}_extractors.{k}.2.bias" for t in ("key", "agents", "action") for k in ks],
-        "w3k": [f"{si}key_extractors.{k}.4.weight" for k in ks],
-        "b3k": [f"{si}key_extractors.{k}.4.bias" for k in ks],
-        "w3n": [f"{si}{t}_extractors.{k}.4.weight" for t in ("agents", "action") for k in ks],
-        "b3n": [f"{si}{t}_extractors.{k}.4.bias" for t in ("agents", "action") for k in ks],
+    }
+    if layers == 3:
+        groups["w2"] = [f"{si}{t}_extractors.{k}.2.weight" for t in ("key", "agents", "action") for k in ks]
+        groups["b2"] = [f"{si}{t}_extractors.{k}.2.bias" for t in ("key", "agents", "action") for k in ks]
+    groups.update({
+        "w3k": [f"{si}key_extractors.{k}.{out}.weight" for k in ks],
+        "b3k": [f"{si}key_extractors.{k}.{out}.bias" for k in ks],
+        "w3n": [f"{si}{t}_extractors.{k}.{out}.weight" for t in ("agents", "action") for k in ks],
+        "b3n": [f"{si}{t}_extractors.{k}.{out}.bias" for t in ("agents", "action") for k in ks],
         "wfv": ["hyper_w_final.2.weight", "V.2.weight"],
         "bfv": ["hyper_w_final.2.bias", "V.2.bias"],
-    }
+    })
     return groups
 
 
-def qplex_struct(addr_of, K, cls=L.QplexParams):
-    """addr_of(name) -> device address; fills the 12 group pointers with the address of each group's head."""
+def qplex_struct(addr_of, K, cls=L.QplexParams, layers=3):
+    """addr_of(name) -> device address; fills the group pointers with the address of each group's head (groups a
+    layer count does not have stay NULL)."""
     s = cls()
-    for field, names in qplex_flat_order(K).items():
+    for field, names in qplex_flat_order(K, layers).items():
         setattr(s, field, addr_of(names[0]))
     return s
 
 
+def _layers(args):
+    return int(getattr(args, "adv_hypernet_layers", 1))
+
+
 def qplex_dims(args):
     return L.QplexDims(args.n_agents, args.n_actions, int(np.prod(args.state_shape)), args.hypernet_embed,
-                       args.adv_hypernet_embed, args.num_kernel, int(bool(args.weighted_head)), int(bool(args.is_minus_one)))
+                       args.adv_hypernet_embed, args.num_kernel, int(bool(args.weighted_head)), int(bool(args.is_minus_one)),
+                       _layers(args))
 
 
 def qplex_workspace(M, args, device):
     N, K, he, ae = args.n_agents, args.num_kernel, args.hypernet_embed, args.adv_hypernet_embed
-    f = lambda w: torch.empty(M, w, dtype=torch.float32, device=device)
-    return dict(h1=f(2 * he + 3 * K * ae), h2=f(3 * K * ae), o3=f(K + 2 * K * N), wv=f(2 * N))
+    ext = 0 if _layers(args) == 1 else K * ae
+    f = lambda w: torch.empty(M, max(w, 1), dtype=torch.float32, device=device)
+    return dict(h1=f(2 * he + 3 * ext), h2=f(3 * ext if _layers(args) == 3 else 1), o3=f(K + 2 * K * N), wv=f(2 * N))
 
 
 def ws_struct(ws):
@@ -100,7 +133,7 @@ class _QplexFn(torch.autograd.Function):
         out = torch.empty(M, dtype=torch.float32, device=q.device)
         d = qplex_dims(args)
         names = module.flat_names()
-        p = qplex_struct(dict(zip(names, (t.data_ptr() for t in params))).__getitem__, args.num_kernel)
+        p = qplex_struct(dict(zip(names, (t.data_ptr() for t in params))).__getitem__, args.num_kernel, layers=_layers(args))
         wss = ws_struct(ws)
         if is_v:
             L.call("marl_qplex_fwd", M, C.byref(d), C.byref(p), q.data_ptr(), s.data_ptr(), None, None, C.byref(wss),
@@ -130,8 +163,8 @@ class _QplexFn(torch.autograd.Function):
             off += t.numel()
         gbuf = torch.zeros(off + 4, dtype=torch.float32, device=dev)
         views = [gbuf[offs[n]:offs[n] + t.numel()].view(t.shape) for n, t in zip(names, params)]
-        g = qplex_struct(lambda n: gbuf.data_ptr() + 4 * offs[n], args.num_kernel, L.QplexGrads)
-        p = qplex_struct(dict(zip(names, (t.data_ptr() for t in params))).__getitem__, args.num_kernel)
+        g = qplex_struct(lambda n: gbuf.data_ptr() + 4 * offs[n], args.num_kernel, L.QplexGrads, layers=_layers(args))
+        p = qplex_struct(dict(zip(names, (t.data_ptr() for t in params))).__getitem__, args.num_kernel, layers=_layers(args))
         dws = qplex_workspace(M, args, dev)
         for t in dws.values():
             t.zero_()
@@ -170,10 +203,10 @@ class DMAQer(FlatPackedMixin, nn.Module):
 
     # ---- flat storage ------------------------------------------------------------------------------
     def flat_names(self):
-        return [n for names in qplex_flat_order(self.args.num_kernel).values() for n in names]
+        return [n for names in qplex_flat_order(self.args.num_kernel, _layers(self.args)).values() for n in names]
 
     def flat_tight(self):
-        return {n for names in qplex_flat_order(self.args.num_kernel).values() for n in names[1:]}
+        return {n for names in qplex_flat_order(self.args.num_kernel, _layers(self.args)).values() for n in names[1:]}
 
     def flat_named_parameters(self):
         table = dict(self.named_parameters())

@@ -66,6 +66,7 @@ def run_case(name, alg, batch, N, A, O, S, T, n_steps=3, seed=0, **kw):
     for k in ("num_kernel", "adv_hypernet_embed", "hypernet_embed", "qtran_hidden_dim", "hyper_hidden_dim"):
         out[f"meta/{k}"] = np.array(getattr(args, k))
     out["meta/two_hyper_layers"] = np.array(int(args.two_hyper_layers))
+    out["meta/adv_hypernet_layers"] = np.array(int(getattr(args, "adv_hypernet_layers", 3)))
     for k, v in batch.items():
         out[f"batch/{k}"] = np.asarray(v)
     dump_sd("init/agent", mac.agent.state_dict(), out)
@@ -278,7 +279,56 @@ def rollout_case():
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    extra = {"rollout": rollout_case, "choose_action": choose_action_case, "checkpoints": checkpoint_case, "seeds": seeds_case}
+    def qplex_layers_case():
+        tiny = dict(N=3, A=4, O=5, S=6, T=6)
+        tb = synthetic_batch(0, 4, tiny["T"], tiny["N"], tiny["A"], tiny["O"], tiny["S"])
+        for nl in (1, 2):
+            run_case(f"tiny_qplex_layers{nl}", "qplex", tb, **tiny, target_update_cycle=2, num_kernel=2, adv_hypernet_embed=8,
+                     hypernet_embed=8, adv_hypernet_layers=nl)
+
+    def separated_case():
+        """SeparatedMAC (share_params.py:389-610: one RNNQNet per agent, reuse_network=False as runner.py:24-26 builds it)
+        under the UNMODIFIED QLearner for 3 QMIX steps (< target_update_cycle: the reference's own target sync calls
+        ``other_mac.agent.state_dict()`` on a list and cannot run with this controller)."""
+        from controller.share_params import SeparatedMAC
+        tiny = dict(N=3, A=4, O=5, S=6, T=6)
+        tb = synthetic_batch(2, 4, tiny["T"], tiny["N"], tiny["A"], tiny["O"], tiny["S"])
+        for alg in ("qmix", "vdn"):
+            th.manual_seed(0)
+            args = ref_args(alg, tiny["N"], tiny["A"], tiny["O"], tiny["S"], tiny["T"], reuse_network=False)
+            mac = SeparatedMAC(args)
+            learner = QLearner(mac, args)
+            out = {"meta/alg": np.array(alg), "meta/dims": np.array([tiny[k] for k in ("N", "A", "O", "S", "T")])}
+            for k, v in tb.items():
+                out[f"batch/{k}"] = np.asarray(v)
+            for n, ag in enumerate(mac.agent):
+                dump_sd(f"init/agent.{n}", ag.state_dict(), out)
+            dump_sd("init/mixer", learner.mixer.state_dict(), out)
+            probe = copy.deepcopy(learner)
+            b = {k: np.array(v) for k, v in tb.items()}
+            b, Lc = probe.get_max_episode_len(b)
+            for k in b:
+                b[k] = th.tensor(b[k], dtype=th.long if k == "u" else th.float32)
+            with th.no_grad():
+                probe.eval_net.init_hidden(4)
+                q_evals, hid = probe.eval_net.get_current_q_values(b, Lc)
+                q_next, hid_list = probe.eval_net.get_next_q_values(b, Lc)          # carried hidden; returns the per-agent LIST
+                out["step0/q_evals"], out["step0/hidden_evals"] = q_evals.numpy().copy(), hid.numpy().copy()
+                out["step0/q_evals_next"] = q_next.numpy().copy()
+                out["step0/next_hidden_list"] = np.stack([h.numpy() for h in hid_list])
+            # train(): with the installed torch (2.11) the reference's per-agent in-place hidden-state write-back
+            # (share_params.py:538-539) invalidates the autograd graph and loss.backward() raises -- recorded, so that
+            # the fixture documents that only the FORWARD surface of this controller can be pinned to the reference
+            try:
+                losses = [learner.train({k: np.array(v) for k, v in tb.items()}, step) for step in range(3)]
+                out["loss"] = np.array(losses, dtype=np.float64)
+            except RuntimeError as e:
+                losses = None
+                out["train_error"] = np.array(str(e)[:200])
+            np.savez_compressed(os.path.join(OUT, f"separated_{alg}.npz"), **out)
+            print("separated", alg, losses if losses is not None else "train() raised: " + str(out["train_error"])[:80])
+
+    extra = {"separated": separated_case, "qplex_layers": qplex_layers_case, "rollout": rollout_case, "choose_action": choose_action_case, "checkpoints": checkpoint_case, "seeds": seeds_case}
     picked = [k for k in sys.argv[1:] if k in extra]
     if picked:                              # round-2 fixtures (the round-1 fixtures stay as committed)
         for k in picked:

@@ -30,7 +30,9 @@ import torch.nn.functional as F
 NEG_BIG = -9999999.0      # q_learner.py:105,112,126 ; qtran_learner.py:106
 NEG_QTRAN_EVAL = -999999.0  # qtran_learner.py:105
 
-DEFAULTS = dict(  # common/arguments.py:86-147 (get_mixer_args) + :31-34
+DEFAULTS = dict(
+    separated=False,   # SeparatedMAC (share_params.py:389-610): one network per agent
+     # common/arguments.py:86-147 (get_mixer_args) + :31-34
     rnn_hidden_dim=64, qmix_hidden_dim=32, two_hyper_layers=False, hyper_hidden_dim=64,
     qtran_hidden_dim=64, lr=5e-4, target_update_cycle=200, lambda_opt=1, lambda_nopt=1,
     grad_norm_clip=10, adv_hypernet_embed=64, num_kernel=10, adv_hypernet_layers=3,
@@ -58,7 +60,8 @@ def _linear(sd, name, n_in, n_out):
 def init_agent(cfg):
     """network/q_network.py:8-14 ; input width per share_params.py:114-123."""
     sd = {}
-    n_in = cfg.obs_shape + cfg.n_actions + cfg.n_agents
+    n_in = cfg.obs_shape + (cfg.n_actions if getattr(cfg, "last_action", True) else 0) + \
+        (cfg.n_agents if getattr(cfg, "reuse_network", True) else 0)          # share_params.py:114-123 / :497-506
     H = cfg.rnn_hidden_dim
     _linear(sd, "fc1", n_in, H)
     g = torch.nn.GRUCell(H, H)
@@ -95,17 +98,17 @@ def init_mixer(cfg, alg=None):
         _linear(sd, "hyper_w_final.2", he, N)
         _linear(sd, "V.0", S, he)
         _linear(sd, "V.2", he, N)
-        assert cfg.adv_hypernet_layers == 3
+        nl = cfg.adv_hypernet_layers          # mixer.py:115-145: 1, 2 or 3 Linear layers per extractor
+        assert nl in (1, 2, 3)
         for k in range(cfg.num_kernel):
-            _linear(sd, f"si_weight.key_extractors.{k}.0", S, ae)
-            _linear(sd, f"si_weight.key_extractors.{k}.2", ae, ae)
-            _linear(sd, f"si_weight.key_extractors.{k}.4", ae, 1)
-            _linear(sd, f"si_weight.agents_extractors.{k}.0", S, ae)
-            _linear(sd, f"si_weight.agents_extractors.{k}.2", ae, ae)
-            _linear(sd, f"si_weight.agents_extractors.{k}.4", ae, N)
-            _linear(sd, f"si_weight.action_extractors.{k}.0", S + N * A, ae)
-            _linear(sd, f"si_weight.action_extractors.{k}.2", ae, ae)
-            _linear(sd, f"si_weight.action_extractors.{k}.4", ae, N)
+            for name, n_in, n_out in (("key", S, 1), ("agents", S, N), ("action", S + N * A, N)):
+                pre = f"si_weight.{name}_extractors.{k}"
+                if nl == 1:
+                    _linear(sd, pre, n_in, n_out)
+                else:
+                    widths = [n_in] + [ae] * (nl - 1) + [n_out]
+                    for i in range(nl):
+                        _linear(sd, f"{pre}.{2 * i}", widths[i], widths[i + 1])
         return sd
     if alg == "qtran_base":  # mixer.py:364-375
         ae, qh = H + A, cfg.qtran_hidden_dim
@@ -159,11 +162,22 @@ def unroll(p, obs, last_onehot, h, cfg):
     """
     B, T, N, _ = obs.shape
     eye = torch.eye(N, dtype=obs.dtype).unsqueeze(0).expand(B, -1, -1)
+    separated = isinstance(p, (list, tuple))        # SeparatedMAC: agent n's rows go through network n (share_params.py:527-533)
     qs, hs = [], []
     for t in range(T):
-        x = torch.cat([obs[:, t].reshape(B * N, -1), last_onehot[:, t].reshape(B * N, -1),
-                       eye.reshape(B * N, -1)], dim=1)
-        q, h = agent_step(p, x, h.reshape(B * N, -1))
+        parts = [obs[:, t].reshape(B * N, -1)]
+        if getattr(cfg, "last_action", True):
+            parts.append(last_onehot[:, t].reshape(B * N, -1))
+        if getattr(cfg, "reuse_network", True):
+            parts.append(eye.reshape(B * N, -1))
+        x = torch.cat(parts, dim=1)
+        if separated:
+            xv, hv = x.view(B, N, -1), h.reshape(B, N, -1)
+            outs = [agent_step(p[n], xv[:, n], hv[:, n]) for n in range(N)]
+            q = torch.stack([o[0] for o in outs], dim=1).reshape(B * N, -1)
+            h = torch.stack([o[1] for o in outs], dim=1).reshape(B * N, -1)
+        else:
+            q, h = agent_step(p, x, h.reshape(B * N, -1))
         qs.append(q.view(B, N, -1))
         hs.append(h.view(B, N, -1))
     return torch.stack(qs, 1), torch.stack(hs, 1), h
@@ -214,10 +228,16 @@ def qplex_lambda(p, s, actions, cfg):
     s = s.reshape(-1, cfg.state_shape)
     data = torch.cat([s, actions.reshape(-1, N * cfg.n_actions)], dim=1)
     tot = 0
+    nl = cfg.adv_hypernet_layers
+
+    def ext(name, k, x):
+        pre = f"si_weight.{name}_extractors.{k}"
+        return F.linear(x, p[pre + ".weight"], p[pre + ".bias"]) if nl == 1 else _mlp(p, pre, x, nl)
+
     for k in range(cfg.num_kernel):
-        key = torch.abs(_mlp(p, f"si_weight.key_extractors.{k}", s, 3)).repeat(1, N) + 1e-10
-        ag = torch.sigmoid(_mlp(p, f"si_weight.agents_extractors.{k}", s, 3))
-        ac = torch.sigmoid(_mlp(p, f"si_weight.action_extractors.{k}", data, 3))
+        key = torch.abs(ext("key", k, s)).repeat(1, N) + 1e-10
+        ag = torch.sigmoid(ext("agents", k, s))
+        ac = torch.sigmoid(ext("action", k, data))
         tot = tot + key * ag * ac
     return tot
 
@@ -288,14 +308,18 @@ class LearnerState:
     def __init__(self, cfg, params=None, dtype=torch.float32):
         self.cfg, self.dtype = cfg, dtype
         if params is None:
-            params = {"agent": init_agent(cfg), "mixer": init_mixer(cfg)}
+            if getattr(cfg, "separated", False):
+                params = {f"agent.{n}": init_agent(cfg) for n in range(cfg.n_agents)}
+                params["mixer"] = init_mixer(cfg)
+            else:
+                params = {"agent": init_agent(cfg), "mixer": init_mixer(cfg)}
             if cfg.alg == "qtran_base":
                 params["v"] = init_qtran_v(cfg)
                 params["q_sum_mixer"] = init_mixer(cfg, "qmix")  # qtran_learner.py:37 (never used)
         self.params = {g: {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in sd.items()}
                        for g, sd in params.items()}
         self.target = {g: {k: v.detach().clone() for k, v in self.params[g].items()}
-                       for g in ("agent", "mixer")}
+                       for g in self.params if g == "mixer" or g.startswith("agent")}
         self.opt = {}      # (group, key) -> dict of moment tensors
         self.steps = 0
 
@@ -303,9 +327,16 @@ class LearnerState:
         return [(g, k, v) for g, sd in self.params.items() for k, v in sd.items()]
 
     def sync_targets(self):  # q_learner.py:181-184
-        for g in ("agent", "mixer"):
+        for g in self.target:
             for k, v in self.params[g].items():
                 self.target[g][k] = v.detach().clone()
+
+    @staticmethod
+    def agent_of(P):
+        """The agent parameters of a group table: one dict (SharedMAC) or the per-agent list (SeparatedMAC)."""
+        if "agent" in P:
+            return P["agent"]
+        return [P[f"agent.{n}"] for n in range(sum(1 for g in P if g.startswith("agent.")))]
 
 
 def q_learner_forward(st, batch_np):
@@ -316,14 +347,14 @@ def q_learner_forward(st, batch_np):
     B, N = b["o"].shape[0], cfg.n_agents
     mask = 1 - b["padded"]
     h0 = torch.zeros(B * N, cfg.rnn_hidden_dim, dtype=st.dtype)
-    q_evals, hid_evals, h_last = unroll(P["agent"], b["o"], shift_onehot(b["u_onehot"]), h0, cfg)
+    q_evals, hid_evals, h_last = unroll(LearnerState.agent_of(P), b["o"], shift_onehot(b["u_onehot"]), h0, cfg)
     q_chosen = torch.gather(q_evals, 3, b["u"]).squeeze(3)
     with torch.no_grad():
-        q_targets, _, _ = unroll(TP["agent"], b["o_next"], b["u_onehot"], h0, cfg)
+        q_targets, _, _ = unroll(LearnerState.agent_of(TP), b["o_next"], b["u_onehot"], h0, cfg)
         q_targets[b["avail_u_next"] == 0.0] = NEG_BIG
         if cfg.double_q:
             # NB: hidden carried over from the current-obs unroll (no init_hidden, q_learner.py:110)
-            q_en, _, _ = unroll(P["agent"], b["o_next"], b["u_onehot"], h_last.detach(), cfg)
+            q_en, _, _ = unroll(LearnerState.agent_of(P), b["o_next"], b["u_onehot"], h_last.detach(), cfg)
             q_en[b["avail_u_next"] == 0] = NEG_BIG
             a_star = torch.argmax(q_en, dim=3, keepdim=True)
             q_tc = torch.gather(q_targets, 3, a_star).squeeze(3)
@@ -370,9 +401,9 @@ def qtran_forward(st, batch_np):
     B, N = b["o"].shape[0], cfg.n_agents
     mask = 1 - b["padded"].squeeze(-1)
     h0 = torch.zeros(B * N, cfg.rnn_hidden_dim, dtype=st.dtype)
-    q_ev, hid_ev, _ = unroll(P["agent"], b["o"], shift_onehot(b["u_onehot"]), h0, cfg)
+    q_ev, hid_ev, _ = unroll(LearnerState.agent_of(P), b["o"], shift_onehot(b["u_onehot"]), h0, cfg)
     with torch.no_grad():
-        q_tg, hid_tg, _ = unroll(TP["agent"], b["o_next"], b["u_onehot"], h0, cfg)
+        q_tg, hid_tg, _ = unroll(LearnerState.agent_of(TP), b["o_next"], b["u_onehot"], h0, cfg)
         q_tg[b["avail_u_next"] == 0.0] = NEG_BIG
         oh_t = torch.zeros_like(q_tg).scatter(-1, q_tg.argmax(dim=3, keepdim=True), 1)
     q_clone = q_ev.clone()

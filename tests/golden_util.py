@@ -11,7 +11,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(__file__), "golden")
 
 
 # fixtures with their own layout (tests of their own): not full learner cases
-OTHER_FIXTURES = ("matrix_game_env", "choose_action_3s5z", "checkpoint_losses", "qmix_2s3z_seeds", "rollout_multistep")
+OTHER_FIXTURES = ("matrix_game_env", "choose_action_3s5z", "checkpoint_losses", "qmix_2s3z_seeds", "rollout_multistep", "separated_")
 
 
 def learner_cases():
@@ -38,7 +38,8 @@ def cfg_from(z):
                        num_kernel=int(z["meta/num_kernel"]), adv_hypernet_embed=int(z["meta/adv_hypernet_embed"]),
                        hypernet_embed=int(z["meta/hypernet_embed"]), qtran_hidden_dim=int(z["meta/qtran_hidden_dim"]),
                        two_hyper_layers=bool(int(z["meta/two_hyper_layers"])) if "meta/two_hyper_layers" in z else False,
-                       hyper_hidden_dim=int(z["meta/hyper_hidden_dim"]) if "meta/hyper_hidden_dim" in z else 64)
+                       hyper_hidden_dim=int(z["meta/hyper_hidden_dim"]) if "meta/hyper_hidden_dim" in z else 64,
+                       adv_hypernet_layers=int(z["meta/adv_hypernet_layers"]) if "meta/adv_hypernet_layers" in z else 3)
 
 
 def init_params(z):

@@ -30,7 +30,7 @@ def oracle_cfg(args):
         "alg", "optimizer", "n_agents", "n_actions", "obs_shape", "state_shape", "episode_limit", "double_q", "lr",
         "target_update_cycle", "num_kernel", "adv_hypernet_embed", "hypernet_embed", "qtran_hidden_dim", "gamma",
         "grad_norm_clip", "lambda_opt", "lambda_nopt", "weighted_head", "is_minus_one", "rnn_hidden_dim",
-        "qmix_hidden_dim", "two_hyper_layers", "hyper_hidden_dim")})
+        "qmix_hidden_dim", "two_hyper_layers", "hyper_hidden_dim", "adv_hypernet_layers")})
 
 
 def build_pair(args, params=None, seed=0, dtype=torch.float32):
@@ -121,7 +121,7 @@ def params_close(mine, ref, lr, n_steps, report=None, what=""):
     return ok
 
 
-def compare_grads(mine, theirs, tol, report, truth=None):
+def compare_grads(mine, theirs, tol, report, truth=None, whole_tol=None):
     """Gradients: every tensor with >= 64 entries within `tol` (max-norm, relative to that tensor); tensors
     with fewer entries (biases of 1-wide heads: a single cancelling sum over all samples) within 5*tol; and
     the whole gradient, concatenated, within `tol`.
@@ -147,7 +147,7 @@ def compare_grads(mine, theirs, tol, report, truth=None):
             (report if truth is None else kinked).append(f"grad[{k}] rel err {e:.3e} > {lim:g}")
         num = max(num, float(np.max(np.abs(x - y))) if y.size else 0.0)
         den = max(den, float(np.max(np.abs(y))) if y.size else 0.0)
-    if num > tol * max(den, 1e-30):
+    if num > (whole_tol or tol) * max(den, 1e-30):
         report.append(f"whole gradient: max abs diff {num:.3e} vs scale {den:.3e}")
     # At full size (hundreds of thousands of pre-activations per layer) a ReLU input within the fp32 noise of
     # zero can flip in one fp32 implementation and not in another; it perturbs only that layer's first-layer

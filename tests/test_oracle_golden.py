@@ -131,3 +131,34 @@ def test_oracle_full_shape_qmix_seeds(seed):
     ref = z[f"s{seed}/loss"]
     losses = [MO.train_step(st, batches[i % 2], i)[0] for i in range(len(ref))]
     assert np.allclose(losses, ref, rtol=1e-4, atol=0), (losses, ref)
+
+
+@pytest.mark.parametrize("alg", ["qmix", "vdn"])
+def test_oracle_separated_mac_matches_reference(alg):
+    """One network per agent (SeparatedMAC, share_params.py:389-610, reuse_network=False): the per-agent unroll and the
+    hidden state carried between the two eval unrolls against the UNMODIFIED reference.  (Only the forward surface can
+    be pinned: the reference's own train() raises an autograd in-place error with this controller under torch 2.11,
+    which the fixture records.)"""
+    import torch
+    z = GU.load(f"separated_{alg}")
+    assert "train_error" in z and "loss" not in z
+    N, A, O, S, T = (int(x) for x in z["meta/dims"])
+    cfg = MO.make_cfg(alg=alg, n_agents=N, n_actions=A, obs_shape=O, state_shape=S, episode_limit=T, separated=True,
+                      reuse_network=False)
+    params = {f"agent.{n}": GU.group(z, f"init/agent.{n}") for n in range(N)}
+    params["mixer"] = GU.group(z, "init/mixer")
+    st = MO.LearnerState(cfg, params)
+    batch = GU.batch_of(z)
+    loss, info = MO.train_step(st, batch, 0)
+    assert np.isfinite(loss)
+    assert GU.rel_err(info["q_evals"], z["step0/q_evals"]) < TOL
+    assert GU.rel_err(info["hidden_evals"], z["step0/hidden_evals"]) < TOL
+    # the double-Q unroll continues from the carried hidden state (q_learner.py:96,110)
+    b = MO.to_tensors(batch, info["L"], torch.float32)
+    B = b["o"].shape[0]
+    agents = [{k: v.detach() for k, v in GU.group(z, f"init/agent.{n}").items()} for n in range(N)]
+    with torch.no_grad():
+        _, _, hl = MO.unroll(agents, b["o"], MO.shift_onehot(b["u_onehot"]), torch.zeros(B * N, 64), cfg)
+        qn, _, hl2 = MO.unroll(agents, b["o_next"], b["u_onehot"], hl, cfg)
+    assert GU.rel_err(qn, z["step0/q_evals_next"]) < TOL
+    assert GU.rel_err(hl2.view(B, N, -1).permute(1, 0, 2), z["step0/next_hidden_list"]) < TOL
