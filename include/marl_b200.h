@@ -114,7 +114,17 @@ typedef struct marl_unroll_stream {
     float* x;                /* workspace/out [B,L,N,H]: relu(fc1) (needed by the backward) */
     float* gi;               /* workspace [B,L,N,3H] */
     float* gates;            /* out [B,L,N,4H] (r, z, n, W_hn h + b_hn) for the backward, or NULL */
+    const int* ep_len;       /* device [B] (marl_episode_lengths) or NULL.  Non-NULL: this stream's recurrence stops each row at
+                                its episode's length -- the padded steps behind it (q_learner.py:49-66 keeps them up to the
+                                batch maximum) are not computed; `hidden` / `q` keep whatever they held there (finite: the
+                                loss masks them) and h_last is the hidden after the last REAL step.  Never set it on a
+                                stream another stream continues from (h0_from): the reference carries the hidden state through
+                                the padded steps (q_learner.py:96,110), so that one must run to L. */
 } marl_unroll_stream;
+
+/* ep_len[b] = 1 + the last step with padded[b, t] == 0 (at least 1): every step at or beyond it has mask = 0 in the loss
+ * (q_learner.py:79,167), i.e. contributes neither to the loss nor to any gradient.  padded [B, L] fp32. */
+int marl_episode_lengths(const float* padded, int B, int L, int* ep_len, void* stream);
 
 int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_stream* streams, int n_streams, void* stream);
 
@@ -133,6 +143,9 @@ typedef struct marl_unroll_bwd {
     float* dh0;              /* out [B*N,H] dL/dh0, or NULL */
     marl_agent_grads grads;
     int dhext_ready;         /* != 0: dhext already holds dq . fc2_w (marl_qmix_td_fwd_bwd wrote it); skip that product */
+    const int* ep_len;       /* device [B] or NULL.  Non-NULL: the backward chain of a row starts at its episode's last real
+                                step; dgi / dgh of the padded steps behind it are written as zeros (what the full chain
+                                computes there: every upstream gradient is masked to zero) */
 } marl_unroll_bwd;
 
 int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* a, void* stream);

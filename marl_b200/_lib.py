@@ -48,14 +48,14 @@ class UnrollStream(C.Structure):
     _fields_ = [("obs", c_ptr), ("onehot", c_ptr), ("shift_onehot", C.c_int), ("full_input", C.c_int),
                 ("h0_from", C.c_int), ("h0", c_ptr),
                 ("params", AgentParams), ("q", c_ptr), ("hidden", c_ptr), ("h_last", c_ptr), ("x", c_ptr),
-                ("gi", c_ptr), ("gates", c_ptr)]
+                ("gi", c_ptr), ("gates", c_ptr), ("ep_len", c_ptr)]
 
 
 class UnrollBwd(C.Structure):
     _fields_ = [("obs", c_ptr), ("onehot", c_ptr), ("shift_onehot", C.c_int), ("full_input", C.c_int),
                 ("params", AgentParams), ("hidden", c_ptr), ("x", c_ptr), ("gates", c_ptr), ("h0", c_ptr), ("dq", c_ptr),
                 ("dhidden", c_ptr), ("dhext", c_ptr), ("dgi", c_ptr), ("dgh", c_ptr), ("dx", c_ptr), ("dh0", c_ptr),
-                ("grads", AgentGrads), ("dhext_ready", C.c_int)]
+                ("grads", AgentGrads), ("dhext_ready", C.c_int), ("ep_len", c_ptr)]
 
 
 class PeerGroup(C.Structure):
@@ -166,6 +166,7 @@ _SIGNATURES = {
     "marl_qtran_losses_fwd_bwd": ([_P(Dims)] + [c_ptr] * 12 + [C.c_float] * 3 + [c_ptr] * 5 + [c_ptr], C.c_int),
     "marl_epsgreedy_select": ([C.c_int, C.c_int] + [c_ptr] * 6 + [c_ptr], C.c_int),
     "marl_select_fits": ([C.c_int] * 4, C.c_int),
+    "marl_episode_lengths": ([c_ptr, C.c_int, C.c_int, c_ptr, c_ptr], C.c_int),
     "marl_set_scratch": ([c_ptr, C.c_size_t], C.c_int),
     "marl_tgemm_trace": ([C.c_int, c_ptr], C.c_int),
     "marl_tgemm_enable": ([C.c_int], C.c_int),

@@ -205,7 +205,11 @@ class QLearner:
                        o_next=f(B, Lq, N, O), s_next=f(B, Lq, S), avail_u=f(B, Lq, N, A), avail_u_next=f(B, Lq, N, A),
                        u_onehot=f(B, Lq, N, A), padded=f(B, Lq), terminated=f(B, Lq)),
             x=[f(rows, H) for _ in range(3)], gi=[f(rows, 3 * H) for _ in range(3)],
-            hidden=[f(B, Lq, N, H) for _ in range(3)], q=[f(B, Lq, N, A) for _ in range(3)],
+            # (zero-initialised: with args.early_exit the steps behind an episode's end are never written, and the masked
+            # consumers must still read finite numbers there)
+            hidden=[th.zeros(B, Lq, N, H, dtype=th.float32, device=dev) for _ in range(3)],
+            q=[th.zeros(B, Lq, N, A, dtype=th.float32, device=dev) for _ in range(3)],
+            ep_len=th.ones(B, dtype=th.int32, device=dev),
             h_last=[f(B * N, H) for _ in range(3)], gates=f(rows, 4 * H),
             q_chosen=f(B, Lq, N), q_tc=f(B, Lq, N), a_star=th.empty(B, Lq, N, dtype=th.int64, device=dev),
             q_tot=f(B, Lq, 1), q_tot_t=f(B, Lq, 1), dq=f(B, Lq, N, A),
@@ -442,8 +446,17 @@ class QLearner:
         fused_heads = fused_select and fits(1) and fc2_w % 16 == 0 and fc2_wt % 16 == 0
         dhext_fused = fuse and fc2_w % 8 == 0
 
+        # per-episode early exit of the recurrences.  The eval unroll on `o` must run to L when the double-Q
+        # unroll continues from its final hidden state (the reference carries it through the padded steps, q_learner.py:96,110)
+        early = bool(getattr(a, "early_exit", False))
+        if early:
+            L.call("marl_episode_lengths", bt["padded"].data_ptr(), B, Lq, ws["ep_len"].data_ptr(), sp)
+            n_launch += 1
+        ep_len = ws["ep_len"].data_ptr() if early else None
+
         def fill(i, obs, shift, params, h0_from, gates):
             s = arr[i]
+            s.ep_len = ep_len if (i > 0 or not double_q) else None      # stream 0 is continued by stream 2 under double-Q
             s.obs, s.onehot, s.shift_onehot, s.full_input = obs.data_ptr(), bt["u_onehot"].data_ptr(), shift, 0
             s.h0_from, s.h0, s.params = h0_from, None, params
             s.q = None if fused_heads else ws["q"][i].data_ptr()
@@ -530,6 +543,7 @@ class QLearner:
         bw.dhext, bw.dgi, bw.dgh, bw.dx = (ws[k].data_ptr() for k in ("dhext", "dgi", "dgh", "dx"))
         bw.dh0 = None
         bw.dhext_ready = int(dhext_fused)
+        bw.ep_len = ep_len
         bw.grads = agent_param_struct({n: self._flat.ptr("agent." + n, self._flat.grad) for n in AGENT_FLAT_ORDER},
                                       L.AgentGrads)
         if a.alg == "qmix":

@@ -51,6 +51,7 @@ struct GruSegment {
     float* hidden;        // [B,L,N,H]
     float* gates;         // [B,L,N,4H] or null
     float* h_last;        // [B*N,H] or null
+    const int* ep_len;    // [B] or null: rows stop at their episode's length (padded steps are not computed)
 };
 
 struct GruFwdArgs {
@@ -117,8 +118,14 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
             gp_out[q] = S.gates ? S.gates + base[q] * (4 * MARL_H) + j : nullptr;
         }
         const long long hstep = (long long)N * MARL_H, gstep = (long long)N * 4 * MARL_H;
+        // early exit: the rows of this pass advance in lock-step, so the pass runs to the longest of its episodes
+        int Lp = L;
+        if (S.ep_len) {
+            Lp = 1;
+            for (int rr = 0; rr < nrows; ++rr) Lp = max(Lp, min(L, __ldg(S.ep_len + (row0 + rr) / N)));
+        }
         auto issue = [&](int t) {
-            if (t < L) {
+            if (t < Lp) {
 #pragma unroll
                 for (int l = 0; l < NCH; ++l)
                     if (csrc[l] >= 0) cp_async16(&ring[t % kGiDepth][0][0] + cdst[l], S.gi + csrc[l] + (long long)t * N * MARL_G);
@@ -127,7 +134,7 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
         };
 #pragma unroll
         for (int t = 0; t < kGiDepth - 1; ++t) issue(t);
-        for (int t = 0; t < L; ++t) {
+        for (int t = 0; t < Lp; ++t) {
             cp_async_wait<kGiDepth - 2>();           // this thread's copies for step t have landed
             group_sync(bar_id);                      // ... the whole group's; also orders the h double buffer
             // Few rows per CTA = latency-bound chain: the refill's address math and LSU hand-off (~150 cycles when it sat
@@ -245,6 +252,7 @@ struct GruBwdArgs {
     float* dgh;            // [B,L,N,3H]
     float* dh0;            // [B*N,H] or null
     int B, L, N;
+    const int* ep_len;     // [B] or null: a row's chain starts at its episode's last real step
 };
 
 constexpr int kBwdSlot = 7 * MARL_H;     // r, z, n, gh_n (4H) | h_prev | dh_ext | dh_ext2   per row and time step
@@ -315,12 +323,29 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
         ph_[q] = a.dgh + (base[q] + (long long)(L - 1) * N) * MARL_G + j;
     }
     const long long ostep = (long long)N * MARL_G;
+    // early exit: behind the longest episode of this pass every upstream gradient is masked to zero, so the
+    // chain would only produce zeros there -- they are written directly and the chain starts at that episode's last step
+    int Lp = L;
+    if (a.ep_len) {
+        Lp = 1;
+        for (int rr = 0; rr < nrows; ++rr) Lp = max(Lp, min(L, __ldg(a.ep_len + (row0 + rr) / N)));
+        const int tail = L - Lp;
+        for (int idx = tid; idx < tail * nrows * (MARL_G / 4); idx += kGruThreads) {
+            const int c4 = idx % (MARL_G / 4), rr = (idx / (MARL_G / 4)) % nrows, t = Lp + idx / ((MARL_G / 4) * nrows);
+            const int row = row0 + rr;
+            const long long off = (((long long)(row / N) * L + t) * N + (row % N)) * MARL_G + 4 * c4;
+            *reinterpret_cast<float4*>(a.dgi + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(a.dgh + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-    for (int d = 0; d < D - 1; ++d) issue(L - 1 - d);
+        for (int q = 0; q < OWN; ++q) { pi_[q] -= (long long)tail * ostep; ph_[q] -= (long long)tail * ostep; }
+    }
+#pragma unroll
+    for (int d = 0; d < D - 1; ++d) issue(Lp - 1 - d);
     cp_async_wait<D - 2>();
     __syncthreads();
     int cur = 0;
-    for (int t = L - 1; t >= 0; --t) {
+    for (int t = Lp - 1; t >= 0; --t) {
         float dh_dir[OWN];
 #pragma unroll
         for (int q = 0; q < OWN; ++q) {
@@ -443,6 +468,19 @@ static void plan_rows(GruFwdArgs& ga, int rows, int n_ctas) {
 
 // (O may be 0 or negative for a FULL input, where only O + A + N = the network's input width is meaningful; the entry points
 // check O > 0 for the composed [obs | last_action | agent_id] input)
+// ep_len[b] = 1 + last step with padded == 0 (one warp per episode)
+__global__ void __launch_bounds__(256) episode_lengths_kernel(const float* padded, int B, int L, int* ep_len) {
+    pdl_enter();
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    int last = 0;
+    for (int t = lane; t < L; t += 32)
+        if (padded[(long long)b * L + t] == 0.f) last = t + 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    if (lane == 0) ep_len[b] = max(last, 1);
+}
+
 static int check_dims(const marl_dims* d) {
     if (!d || d->B <= 0 || d->L <= 0 || d->N <= 0 || d->A <= 0 || d->O + d->A + d->N <= 0 || d->S < 0) return MARL_EINVAL;
     return MARL_OK;
@@ -463,6 +501,14 @@ static LinOperand agent_input(const marl_dims* d, const float* obs, const float*
 
 using namespace marl;
 
+extern "C" int marl_episode_lengths(const float* padded, int B, int L, int* ep_len, void* stream) {
+    if (!padded || !ep_len || B <= 0 || L <= 0) return MARL_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    { ProfScope ps_("episode_lengths_kernel", st); launch_pdl(episode_lengths_kernel, dim3((B + 7) / 8), dim3(256), 0, st, padded, B, L, ep_len); }
+    MARL_LAUNCH_CHECK();
+    return MARL_OK;
+}
+
 extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_stream* s, int n_streams, void* stream) {
     if (check_dims(d) || !s || n_streams < 1 || n_streams > kMaxStreams) return MARL_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
@@ -473,6 +519,7 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         if (!s[i].obs || (!s[i].onehot && !s[i].full_input) || !s[i].hidden || !s[i].x || !s[i].gi) return MARL_EINVAL;
         if (!s[i].full_input && d->O <= 0) return MARL_EINVAL;
         if (s[i].h0_from >= i) return MARL_EINVAL;
+        if (s[i].h0_from >= 0 && s[s[i].h0_from].ep_len) return MARL_EINVAL;     // a continued stream must run to L (header)
     }
     // phase A: x = relu(fc1(input)), gi = W_ih x + b_ih for every stream
     auto fc1_of = [&](int i) {
@@ -543,7 +590,7 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
     if (n_ordered != n_streams) return MARL_EINVAL;   // two successors of one stream are not supported
     for (int k = 0; k < n_streams; ++k) {
         const marl_unroll_stream& u = s[order[k]];
-        ga.seg[k] = GruSegment{u.gi, u.params.w_hh, u.params.b_hh, u.hidden, u.gates, u.h_last};
+        ga.seg[k] = GruSegment{u.gi, u.params.w_hh, u.params.b_hh, u.hidden, u.gates, u.h_last, u.ep_len};
     }
     const int rows = d->B * d->N;
     {
@@ -592,7 +639,7 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
         if ((rc = linear_dgrad(g, st))) return rc;
     }
     GruBwdArgs ga{a->gates, a->hidden, a->dq ? a->dhext : nullptr, a->dhidden, a->params.w_hh, a->h0, a->dgi, a->dgh, a->dh0,
-                  d->B, d->L, d->N};
+                  d->B, d->L, d->N, a->ep_len};
     const int rows = d->B * d->N;
     {
         ProfScope ps_("gru_unroll_bwd_kernel", st);
