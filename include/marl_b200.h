@@ -385,6 +385,10 @@ int marl_select_fits(int qmix, int N, int A, int heads);
  * marl_set_scratch registers a caller-owned device arena (>= 64 MB recommended) for the split weight-gradient
  * partials; without it the weight gradients fall back to the atomic kernels of csrc/linear.cu. */
 int marl_set_scratch(void* device_ptr, size_t bytes);
+/* 1: the row splits of every weight gradient are written to the scratch arena and added in a fixed order by a second launch
+ * (bitwise reproducible gradients; measured +13 us per weight gradient at the 2s3z sizes); 0 (default; env
+ * MARL_B200_DETERMINISTIC=1 flips it): they meet in fp32 atomics (run-to-run differences of 1 ulp).  Returns the previous setting. */
+int marl_set_deterministic(int on);
 /* routes the TMA-addressable dense layers through csrc/tgemm.cu (1) or csrc/linear.cu (0, default; env MARL_B200_TGEMM);
  * returns the previous setting.  Captured CUDA graphs keep the path they were captured with. */
 int marl_tgemm_enable(int on);

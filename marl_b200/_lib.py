@@ -170,6 +170,7 @@ _SIGNATURES = {
     "marl_set_scratch": ([c_ptr, C.c_size_t], C.c_int),
     "marl_tgemm_trace": ([C.c_int, c_ptr], C.c_int),
     "marl_tgemm_enable": ([C.c_int], C.c_int),
+    "marl_set_deterministic": ([C.c_int], C.c_int),
     "marl_linear_fwd": ([c_ptr, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int] + [C.c_int] * 4 + [c_ptr], C.c_int),
     "marl_linear_dgrad": ([c_ptr, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int] + [C.c_int] * 3 + [c_ptr], C.c_int),
     "marl_linear_wgrad": ([c_ptr, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int, c_ptr] + [C.c_int] * 3 + [c_ptr], C.c_int),

@@ -509,27 +509,50 @@ __global__ void __launch_bounds__(UTH) linear_wgrad_kernel(LinearWgrad a, int sp
     umma_teardown(c, nsteps);
 }
 
-// second stage of the split weight gradient: fixed summation order
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(LinearWgrad a, int splits, int K, const float* part, const float* part_b, int ldp) {
+// second stage of the split weight gradient: fixed summation order.  blockDim = (32, 32): threadIdx.x walks 32 consecutive
+// outputs (one coalesced 128-byte read per split), threadIdx.y deals the splits round-robin over 32 groups -- every thread has
+// at most ceil(splits / 32) independent loads in flight, i.e. one memory round trip -- and one thread per output then adds the
+// 32 group sums in group order: bitwise reproducible.
+__global__ void __launch_bounds__(1024) wgrad_reduce_kernel(LinearWgrad a, int splits, int K, const float* part, const float* part_b, int ldp) {
     pdl_enter();
-    const int zb = blockIdx.y;
+    __shared__ float acc[32][33];
+    const int zb = blockIdx.y, g = threadIdx.y;
     const long long total = (long long)a.N * K + (part_b ? a.N : 0);
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const bool is_b = idx >= (long long)a.N * K;
-        const int n = is_b ? (int)(idx - (long long)a.N * K) : (int)(idx / K), k = is_b ? 0 : (int)(idx % K);
-        const float* src = is_b ? part_b + ((long long)zb * splits) * a.N + n : part + (((long long)zb * splits) * a.N + n) * ldp + k;
-        const long long stride = is_b ? a.N : (long long)a.N * ldp;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int sp = 0;
-        for (; sp + 3 < splits; sp += 4) {
-            s0 += src[sp * stride]; s1 += src[(sp + 1) * stride]; s2 += src[(sp + 2) * stride]; s3 += src[(sp + 3) * stride];
+    for (long long base = (long long)blockIdx.x * 32; base < total; base += (long long)gridDim.x * 32) {
+        const long long idx = base + threadIdx.x;
+        float s = 0.f;
+        bool is_b = false; int n = 0, k = 0;
+        if (idx < total) {
+            is_b = idx >= (long long)a.N * K;
+            n = is_b ? (int)(idx - (long long)a.N * K) : (int)(idx / K);
+            k = is_b ? 0 : (int)(idx % K);
+            const float* src = is_b ? part_b + ((long long)zb * splits) * a.N + n : part + (((long long)zb * splits) * a.N + n) * ldp + k;
+            const long long stride = is_b ? a.N : (long long)a.N * ldp;
+            float s0 = 0.f, s1 = 0.f;
+            int sp = g;
+            for (; sp + 32 < splits; sp += 64) { s0 += src[sp * stride]; s1 += src[(sp + 32) * stride]; }
+            if (sp < splits) s0 += src[sp * stride];
+            s = s0 + s1;
         }
-        for (; sp < splits; ++sp) s0 += src[sp * stride];
-        const float s = (s0 + s1) + (s2 + s3);
-        if (is_b) a.db[(long long)zb * a.db_bs + n] += s;
-        else a.dw[(long long)zb * a.dw_bs + (long long)n * a.ldw + k] += s;
+        acc[g][threadIdx.x] = s;
+        __syncthreads();
+        if (g == 0 && idx < total) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t += acc[j][threadIdx.x];
+            if (is_b) a.db[(long long)zb * a.db_bs + n] += t;
+            else a.dw[(long long)zb * a.dw_bs + (long long)n * a.ldw + k] += t;
+        }
+        __syncthreads();
     }
 }
+
+static int g_deterministic = -1;
+bool deterministic_wgrad() {
+    if (g_deterministic < 0) { const char* e = getenv("MARL_B200_DETERMINISTIC"); g_deterministic = (e && e[0] == '1') ? 1 : 0; }
+    return g_deterministic == 1;
+}
+void set_deterministic_wgrad(int on) { g_deterministic = on ? 1 : 0; }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -593,21 +616,22 @@ int linear_wgrad(const LinearWgrad& a, cudaStream_t st) {
     splits = cdiv(a.M, chunk);
     dim3 grid(cdiv(a.N, UM), cdiv(K, UN), a.batch * splits);
     const bool va = vec_ok_mat(a.dy, a.lddy, a.dy_bs), vb = vec_ok_lin(a.in);
-    // deterministic path: per-split tiles in the scratch arena (marl_set_scratch) + a fixed-order reduce
+    // deterministic path (marl_set_deterministic / MARL_B200_DETERMINISTIC=1; measured +13 us per weight gradient at the cfg-2
+    // sizes, hence opt-in): per-split tiles in the scratch arena (marl_set_scratch) + a fixed-order reduce
     const int ldp = (K + 3) & ~3;
     const size_t pw = (size_t)a.batch * splits * a.N * ldp * sizeof(float), pb = a.db ? (size_t)a.batch * splits * a.N * sizeof(float) : 0;
-    float* part = splits * a.batch > 0 ? tgemm_scratch(pw + 256 + pb) : nullptr;
+    float* part = (splits * a.batch > 0 && deterministic_wgrad()) ? tgemm_scratch(pw + 256 + pb) : nullptr;
     float* part_b = (part && a.db) ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(part) + ((pw + 255) & ~(size_t)255)) : nullptr;
     { if (prof_enabled()) prof_note(a.N, K, a.M); ProfScope ps_("linear_wgrad_kernel", st); MARL_DISPATCH2(linear_wgrad_kernel, va, vb, grid, st, a, splits, chunk, part, part_b, ldp); }
     MARL_LAUNCH_CHECK();
     if (part) {
         const long long total = (long long)a.N * K + a.N;
-        int bx = (int)((total + 255) / 256);
-        if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;
+        int bx = (int)((total + 31) / 32);
+        if (bx > 4 * kNumSMs) bx = 4 * kNumSMs;
         // batched problems that accumulate into ONE dw (dw_bs == 0: e.g. the per-episode h0 term of dW_hh) are extra splits
         const bool fold = a.batch > 1 && a.dw_bs == 0 && (!a.db || a.db_bs == 0);
         ProfScope ps_("wgrad_reduce_kernel", st);
-        launch_pdl_prio(linear_prio(), wgrad_reduce_kernel, dim3(bx, fold ? 1 : a.batch), dim3(256), 0, st, a, fold ? splits * a.batch : splits, K,
+        launch_pdl_prio(linear_prio(), wgrad_reduce_kernel, dim3(bx, fold ? 1 : a.batch), dim3(32, 32), 0, st, a, fold ? splits * a.batch : splits, K,
                         (const float*)part, (const float*)part_b, ldp);
         MARL_LAUNCH_CHECK();
     }

@@ -39,6 +39,10 @@ struct LinearWgrad {
     int batch;
 };
 
+// split weight gradients meet in a fixed-order second stage (bitwise reproducible) instead of atomics
+bool deterministic_wgrad();
+void set_deterministic_wgrad(int on);
+
 int linear_fwd(const LinearFwd& a, cudaStream_t st);
 int linear_dgrad(const LinearDgrad& a, cudaStream_t st);
 int linear_wgrad(const LinearWgrad& a, cudaStream_t st);

@@ -34,7 +34,7 @@ constexpr int TG_B_OFF = 2 * TG_A_BYTES;
 constexpr int TG_THREADS = 320;                         // warp 0: TMA, warp 1: MMA, warps 2-5: converters, warps 6-9: epilogue
 constexpr int TG_CVT0 = 64, TG_EPI0 = 192, TG_ROLE = 128;
 constexpr int TG_MAX_STAGES = 6;
-constexpr int TG_RING_BYTES = 206 * 1024;
+constexpr int TG_RING_BYTES = 188 * 1024;
 constexpr int TG_TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t tg_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
     extern __shared__ unsigned char tg_smem_raw[];
     __shared__ uint64_t bar_full[TG_MAX_STAGES], bar_cvt[TG_MAX_STAGES], bar_empty[TG_MAX_STAGES], bar_accf[2], bar_acce[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float epi_stage[4][32 * 33];          // per epilogue warp: 32 x 32 transpose buffer
+    __shared__ __align__(1024) float epi_stage[4][2 * 1024];       // per epilogue warp: two 32 x 32 blocks (TMA-store double buffer; the
+                                                                     // st.global paths use the pair as one pitch-36 buffer)
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tg_smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     __shared__ TGScalars sp[TG_MAXP];
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
         for (int i = 0; i < g.n; ++i) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&g.p[i].mapA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&g.p[i].mapB) : "memory");
+            if (g.p[i].s.out_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&g.p[i].mapOut) : "memory");
         }
     }
     if (warp == 1) {
@@ -337,6 +339,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
         // ================= epilogue: TMEM -> registers -> global =================
         const int q = warp & 3, row_l = q * 32 + lane;                 // a warp reads the TMEM lane quadrant (warp % 4)
         const bool dbg_nostore = (g.debug & 1) != 0;
+        int tma_seq = 0;
         int seq = 0;
         for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++seq) {
             const TGItem it = tg_decode(sp, np, item);
@@ -349,6 +352,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
             const int m = it.m0 + row_l;
             const float bmul = p.bias_mul != 0.f ? p.bias_mul : 1.0f;
             for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                __syncwarp();          // lanes leave the previous chunk on different paths; tcgen05.ld is .sync.aligned
                 TG_STAMP(3, 4000 + c0);
                 float sum[32];
                 for (int a = 0; a < p.nmain + (p.merge_corr ? 0 : 1); ++a) {
@@ -372,49 +376,149 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
                                      "f"(sum[4 * g4 + 2]), "f"(sum[4 * g4 + 3]));
                     continue;
                 }
-                // The warp's 32 x 32 block goes through a per-warp shared-memory buffer and leaves in ROLLED loops: fully
-                // unrolled epilogues made this kernel ~200 KB of straight-line SASS, and the epilogue then ran at the speed
-                // of instruction fetch (~250 cycles per row, measured with the phase trace; stores on or off made no difference).
+                // The warp's 32 x 32 block is staged in shared memory as [output row][output column] (pitch 36 floats: 128-bit
+                // rows, conflict-free both ways) whatever the orientation of the accumulator, and leaves as 128-bit stores: a lane
+                // owns 4 consecutive output columns, one store instruction writes 4 output rows x 128 B.  (History, measured with
+                // the phase trace: direct lane-per-row stores ~700 cycles per instruction; a generic rolled loop with per-element
+                // guards ~3300 cycles per chunk because of ~1000 integer / predicate instructions; this form ~400.)
                 float* sw = &epi_stage[warp - 6][0];
-                __syncwarp();
+                const bool tr = p.transposed != 0;
+                if (p.out_tma) {
+                    // TMA-store epilogue: bias / ReLU in registers, the warp's 32 x 32 block staged in the 128-byte-swizzled layout
+                    // (lane = row writes its eight 16-byte chunks at chunk ^ (row & 7): conflict-free), one cp.async.bulk.tensor
+                    // store per block; rows / columns past the matrix are clipped by the tensor map.  Two staging blocks per warp:
+                    // the store of chunk i drains while chunk i+1 is read from TMEM.
+                    float* blk = &epi_stage[warp - 6][(tma_seq & 1) * 1024];
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");      // the store that last used this block has read it
+                    __syncwarp();
+                    const float* bp = p.bias ? p.bias + it.n0 + c0 : nullptr;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) sw[lane * 33 + e] = sum[e];
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        float4 v = make_float4(sum[4 * g4], sum[4 * g4 + 1], sum[4 * g4 + 2], sum[4 * g4 + 3]);
+                        if (bp) {
+                            const int n = it.n0 + c0 + 4 * g4;
+                            if (n + 3 < p.Nd) {
+                                v.x = fmaf(bmul, __ldg(bp + 4 * g4), v.x); v.y = fmaf(bmul, __ldg(bp + 4 * g4 + 1), v.y);
+                                v.z = fmaf(bmul, __ldg(bp + 4 * g4 + 2), v.z); v.w = fmaf(bmul, __ldg(bp + 4 * g4 + 3), v.w);
+                            } else {
+                                if (n < p.Nd) v.x = fmaf(bmul, __ldg(bp + 4 * g4), v.x);
+                                if (n + 1 < p.Nd) v.y = fmaf(bmul, __ldg(bp + 4 * g4 + 1), v.y);
+                                if (n + 2 < p.Nd) v.z = fmaf(bmul, __ldg(bp + 4 * g4 + 2), v.z);
+                            }
+                        }
+                        if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        *reinterpret_cast<float4*>(&blk[lane * 32 + 4 * (g4 ^ (lane & 7))]) = v;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && !dbg_nostore) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                     ::"l"(&g.p[it.pi].mapOut), "r"(it.n0 + c0), "r"(it.m0 + q * 32), "r"(tg_u32(blk)) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    ++tma_seq;
+                    continue;
+                }
+                // (warp-uniform condition: every lane of the warp takes the same one of the two paths below)
+                const bool direct = !tr && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && it.n0 + c0 + 32 <= p.Nd &&
+                                    (!p.relu_src || (((p.ldrs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.relu_src) & 15) == 0))) &&
+                                    (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+                if (direct && m >= p.Md) continue;                      // rows past the matrix
+                if (direct) {
+                    // rows on the UMMA rows, full aligned chunk: lane = output row, 8 x 128-bit stores straight from registers
+                    // (no shared-memory round trip; the 8 stores of a lane complete one 128-byte line)
+                    float* dst = p.out + (long long)m * p.ldo + it.n0 + c0;
+                    const float* rs = (p.epi == 1 && p.relu_src) ? p.relu_src + (long long)m * p.ldrs + it.n0 + c0 : nullptr;
+                    const float* bp = (p.epi == 0 && p.bias) ? p.bias + it.n0 + c0 : nullptr;
+                    const bool relu = p.epi == 0 && p.relu, acc = p.accumulate != 0;
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        float4 v = make_float4(sum[4 * g4], sum[4 * g4 + 1], sum[4 * g4 + 2], sum[4 * g4 + 3]);
+                        if (bp) {
+                            float4 b;
+                            asm("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(bp + 4 * g4));
+                            v.x = fmaf(bmul, b.x, v.x); v.y = fmaf(bmul, b.y, v.y); v.z = fmaf(bmul, b.z, v.z); v.w = fmaf(bmul, b.w, v.w);
+                        }
+                        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        if (rs) {
+                            float4 mk;
+                            asm("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(mk.x), "=f"(mk.y), "=f"(mk.z), "=f"(mk.w) : "l"(rs + 4 * g4));
+                            if (!(mk.x > 0.f)) v.x = 0.f; if (!(mk.y > 0.f)) v.y = 0.f; if (!(mk.z > 0.f)) v.z = 0.f; if (!(mk.w > 0.f)) v.w = 0.f;
+                        }
+                        if (acc) {
+                            float4 o;
+                            asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "l"(dst + 4 * g4));
+                            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                        }
+                        if (!dbg_nostore)
+                            asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g4), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+                    }
+                    continue;
+                }
+                __syncwarp();
+                if (tr) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) sw[e * 36 + lane] = sum[e];           // lane = output column (feature)
+                } else {
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4)                                       // lane = output row
+                        *reinterpret_cast<float4*>(&sw[lane * 36 + 4 * g4]) = make_float4(sum[4 * g4], sum[4 * g4 + 1], sum[4 * g4 + 2], sum[4 * g4 + 3]);
+                }
                 __syncwarp();
                 TG_STAMP(3, 3000 + c0);
-                // (the descriptor's pointers come out of shared memory, so the compiler only knows them as GENERIC: a generic
-                // store may alias the staging buffer and would pin every following LDS behind it -- batches of 8 rows are
-                // therefore read first and leave through explicit st.global / ld.global.nc)
-                const bool tr = p.transposed != 0;
-                const int fdim = tr ? m : it.n0 + c0 + lane;                   // feature owned by this lane (column of `out`)
-                const int fmax = tr ? p.Md : p.Nd;
-                const int d0 = tr ? it.n0 + c0 : it.m0 + q * 32;               // first data row (row of `out`) of the block
-                const int nd = min(32, (tr ? p.Nd : p.Md) - d0);
-                if (fdim < fmax && nd > 0) {
-                    const float bv = (p.epi == 0 && p.bias) ? bmul * __ldg(p.bias + fdim) : 0.f;
-                    const int sstep = tr ? 1 : 33, sbase = tr ? lane * 33 : lane;
-                    float* dst0 = p.out + (long long)d0 * p.ldo + fdim;
-                    const float* rs0 = (p.epi == 1 && p.relu_src) ? p.relu_src + (long long)d0 * p.ldrs + fdim : nullptr;
+                const int orow0 = tr ? it.n0 + c0 : it.m0 + q * 32, ocol0 = tr ? it.m0 + q * 32 : it.n0 + c0;
+                const int n_rows = tr ? p.Nd : p.Md, n_cols = tr ? p.Md : p.Nd;
+                const int rsub = lane >> 3, col = ocol0 + 4 * (lane & 7);
+                const int rows_here = min(32, n_rows - orow0);
+                if (rows_here <= 0 || ocol0 >= n_cols) continue;
+                const bool vec = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && ocol0 + 32 <= n_cols &&
+                                 (!p.relu_src || (((p.ldrs & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.relu_src) & 15) == 0)));
+                if (vec) {
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.epi == 0 && p.bias) {
+                        b4.x = bmul * __ldg(p.bias + col); b4.y = bmul * __ldg(p.bias + col + 1);
+                        b4.z = bmul * __ldg(p.bias + col + 2); b4.w = bmul * __ldg(p.bias + col + 3);
+                    }
+                    float* dst = p.out + (long long)(orow0 + rsub) * p.ldo + col;
+                    const float* rs = (p.epi == 1 && p.relu_src) ? p.relu_src + (long long)(orow0 + rsub) * p.ldrs + col : nullptr;
+                    const long long dstep = 4LL * p.ldo, rstep = 4LL * p.ldrs;
+                    const bool relu = p.epi == 0 && p.relu, acc = p.accumulate != 0;
+#pragma unroll 4
+                    for (int r4 = 0; r4 < 8; ++r4, dst += dstep) {
+                        if (4 * r4 + rsub >= rows_here) break;
+                        float4 v = *reinterpret_cast<const float4*>(&sw[(4 * r4 + rsub) * 36 + 4 * (lane & 7)]);
+                        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        if (rs) {
+                            float4 m;
+                            asm("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(m.x), "=f"(m.y), "=f"(m.z), "=f"(m.w) : "l"(rs + r4 * rstep));
+                            if (!(m.x > 0.f)) v.x = 0.f; if (!(m.y > 0.f)) v.y = 0.f; if (!(m.z > 0.f)) v.z = 0.f; if (!(m.w > 0.f)) v.w = 0.f;
+                        }
+                        if (acc) {
+                            float4 o;
+                            asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "l"(dst));
+                            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                        }
+                        if (!dbg_nostore)
+                            asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+                    }
+                    continue;
+                }
+                // ragged edge / unaligned output: one element at a time (a lane walks its 4 columns of every 4th row)
 #pragma unroll 1
-                    for (int r8 = 0; r8 < nd; r8 += 8) {
-                        float o[8], aux[8];
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) o[r] = sw[sbase + (r8 + r) * sstep];
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            aux[r] = 1.f;
-                            if (rs0 && r8 + r < nd) aux[r] = tg_ldg_nc(rs0 + (long long)(r8 + r) * p.ldrs);
-                        }
-                        if (p.accumulate) {
-#pragma unroll
-                            for (int r = 0; r < 8; ++r) if (r8 + r < nd) o[r] += tg_ld_global(dst0 + (long long)(r8 + r) * p.ldo);
-                        }
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            float v = o[r];
-                            if (p.epi == 0) { v += bv; if (p.relu) v = fmaxf(v, 0.f); }
-                            else if (!(aux[r] > 0.f)) v = 0.f;
-                            if (r8 + r < nd && !dbg_nostore) tg_st_global(dst0 + (long long)(r8 + r) * p.ldo, v);
-                        }
+                for (int r4 = 0; r4 < 8; ++r4) {
+                    const int r = 4 * r4 + rsub;
+                    if (r >= rows_here) break;
+#pragma unroll 1
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = col + e;
+                        if (c >= n_cols) break;
+                        float v = sw[r * 36 + 4 * (lane & 7) + e];
+                        float* dst = p.out + (long long)(orow0 + r) * p.ldo + c;
+                        if (p.epi == 0) { if (p.bias) v += bmul * __ldg(p.bias + c); if (p.relu) v = fmaxf(v, 0.f); }
+                        else if (p.relu_src && !(tg_ldg_nc(p.relu_src + (long long)(orow0 + r) * p.ldrs + c) > 0.f)) v = 0.f;
+                        if (p.accumulate) v += tg_ld_global(dst);
+                        if (!dbg_nostore) tg_st_global(dst, v);
                     }
                 }
             }
@@ -423,6 +527,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
             TG_STAMP(3, 1000 + seq);
         }
     }
+    if (warp >= 6) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the TMA stores have left shared memory and are complete
     if (trace) trace[(warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 2 : 3) * 512 + 510] = tn;
     pdl_trigger();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -569,7 +674,7 @@ bool TGBuilder::add_fwd(const LinearFwd& a) {
     p.epi = 0; p.out = a.y; p.ldo = a.ldy; p.accumulate = a.accumulate; p.relu = a.relu; p.bias = a.bias; p.bias_mul = a.bias_mul;
     // every tcgen05.mma costs the same ~190 cycles whatever its N (tools/micro/mma_rate.cu), so narrow layers are computed as
     // y^T = W . x^T: the <= 128 output features sit on the UMMA rows and up to 256 data rows on N -- half the instructions
-    p.transposed = (a.N <= TG_BM && a.M >= 2 * TG_BM) ? 1 : 0;
+    p.transposed = (a.N <= TG_BM && a.M >= 256 * 2 * kNumSMs) ? 1 : 0;      // (needs >= 2 waves of 256-row items to pay)
     if (p.transposed) {
         p.BN = cap;
         p.Md = a.N; p.Nd = a.M;
@@ -583,6 +688,17 @@ bool TGBuilder::add_fwd(const LinearFwd& a) {
         if (!make_map(&P.mapB, a.w, K, a.N, a.ldw, p.BN, false)) return false;
         p.m_tiles = cdiv(a.M, TG_BM); p.n_tiles = cdiv(a.N, p.BN);
     }
+    if (!p.transposed && !a.accumulate && al16(a.y) && (a.ldy & 3) == 0) {
+        // 32 x 32 output boxes, 128-byte swizzle; the tensor map clips the ragged edges
+        EncodeTiled enc = encoder();
+        cuuint64_t gdim[2] = {(cuuint64_t)a.N, (cuuint64_t)a.M};
+        cuuint64_t gstr[1] = {(cuuint64_t)a.ldy * 4};
+        cuuint32_t box[2] = {32, 32}, est[2] = {1, 1};
+        if (enc && enc(&P.mapOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.y, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            p.out_tma = 1;
+    }
+    if (!p.out_tma) P.mapOut = P.mapA;
     if (agent) {
         p.fill_on = p.transposed ? 2 : 1; p.fill_col0 = in.K1; p.fill_A = in.K2; p.fill_N = in.onehot_mod; p.fill_ones = 0;
         p.fill_shift = in.x2_shift; p.fill_period = in.x2_period > 0 ? in.x2_period : 1; p.fill_rows = a.M; p.fill_onehot = in.x2;
@@ -600,7 +716,7 @@ bool TGBuilder::add_dgrad(const LinearDgrad& a) {
     p.Kd = a.N;
     p.kb_total = cdiv(a.N, TG_BK); p.kb_per_split = p.kb_total; p.k_splits = 1;
     p.epi = 1; p.out = a.dx; p.ldo = a.lddx; p.accumulate = a.accumulate; p.relu_src = a.relu_src; p.ldrs = a.ldrs;
-    p.transposed = (a.K <= TG_BM && a.M >= 2 * TG_BM) ? 1 : 0;
+    p.transposed = (a.K <= TG_BM && a.M >= 256 * 2 * kNumSMs) ? 1 : 0;
     if (p.transposed) {
         // dx^T = W^T . dy^T: A(m = input feature, k = output unit) = w[k, col0 + m] is MN-major, B = dy is K-major
         p.BN = cap; p.a_mn = 1;
@@ -735,6 +851,12 @@ extern "C" int marl_tgemm_trace(int on, long long* host_out /* 2048 or null */) 
 extern "C" int marl_tgemm_enable(int on) {
     const int prev = marl::tgemm_enabled() ? 1 : 0;
     marl::g_tgemm_on = on ? 1 : 0;
+    return prev;
+}
+
+extern "C" int marl_set_deterministic(int on) {
+    const int prev = marl::deterministic_wgrad() ? 1 : 0;
+    marl::set_deterministic_wgrad(on);
     return prev;
 }
 

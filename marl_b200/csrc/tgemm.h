@@ -21,6 +21,7 @@ struct TGScalars {
     int nmain;                           // main accumulators dealt round-robin (fp32 accumulate truncation, see linear.cu)
     int merge_corr;                      // short reductions: the 2^-11 correction products share the main accumulator
     int epi;                             // 0: y = act(acc + bias) ; 1: dx = acc * (relu_src > 0) ; 2: partial tile to scratch
+    int out_tma;                         // epi 0, rows on the UMMA rows, TMA-addressable output: the epilogue leaves by cp.async.bulk.tensor stores
     int transposed;                      // epi 0/1 computed as D^T (features on the 128 UMMA rows, data rows on N): out[n, m]
     float* out; int ldo; int accumulate; int relu;
     const float* bias; float bias_mul;
@@ -36,6 +37,7 @@ struct TGScalars {
 
 struct alignas(64) TGProblem {
     CUtensorMap mapA, mapB;
+    CUtensorMap mapOut;                  // output [rows, cols] as 32 x 32 SWIZZLE_128B boxes (TMA store epilogue), when out_tma
     TGScalars s;
 };
 

@@ -15,12 +15,15 @@ pytestmark = pytest.mark.gpu
 TOL_GEMM = 3e-6        # 3xTF32: measured <= 1.8e-6 (max-norm relative) on every shape below; fp32 cuBLAS sits at ~1e-6
 
 
-@pytest.fixture(params=[0, 1], ids=["linear.cu", "tgemm.cu"])
+@pytest.fixture(params=[(0, 0), (0, 1), (1, 0)], ids=["linear.cu", "linear.cu-deterministic", "tgemm.cu"])
 def backend(request):
-    prev = L.load().marl_tgemm_enable(request.param)
+    tg, det = request.param
+    prev = L.load().marl_tgemm_enable(tg)
+    prev_det = L.load().marl_set_deterministic(det)
     L.ensure_scratch()
     yield request.param
     L.load().marl_tgemm_enable(prev)
+    L.load().marl_set_deterministic(prev_det)
 
 
 def _rel(a, b):
@@ -56,7 +59,16 @@ def test_linear_primitives_match_float64(backend, shape):
 
 
 def test_weight_gradient_is_bitwise_reproducible(backend):
-    """Both back ends reduce the row splits in a fixed order (no atomics): repeated calls give identical bits."""
+    """With marl_set_deterministic(1) both back ends reduce the row splits in a fixed order (no atomics): repeated calls give
+    identical bits (csrc/tgemm.cu always does)."""
+    prev = L.load().marl_set_deterministic(1)
+    try:
+        _check_reproducible()
+    finally:
+        L.load().marl_set_deterministic(prev)
+
+
+def _check_reproducible():
     M, N, K = 19200, 192, 64
     torch.manual_seed(0)
     dy, x = torch.randn(M, N, device="cuda"), torch.randn(M, K, device="cuda")

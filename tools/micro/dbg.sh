@@ -1,4 +1,5 @@
-for d in 0 1 2 4 3 7; do echo "== debug=$d"; MARL_TGEMM_DEBUG=$d python - <<'PY'
+export MARL_B200_TGEMM=1
+for d in 0 1 4 5 7; do echo "== debug=$d"; MARL_TGEMM_DEBUG=$d python - <<'PY'
 import sys; sys.path.insert(0,'.')
 import torch
 from marl_b200 import _lib as L
