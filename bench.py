@@ -392,7 +392,9 @@ def run_ours(opt):
         buf.store_episode(new_eps[i % 8][0])
         train(buf.sample(B))
 
-    for i in range(max(W, 3)):
+    # sampled batches come with whatever max_episode_len their episodes have; a (B, L) graph is captured at its third sighting
+    # (~ms each), so the frequent lengths are let through before anything is timed, as in a long training run
+    for i in range(max(W, 96)):
         replay_step(i)
     ms_replay, ms_replay_median = tm.run(K, replay_step)
     replay_max = float(max(tm.last_per_step))
