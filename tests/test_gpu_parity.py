@@ -503,7 +503,9 @@ def test_early_exit_unroll_changes_nothing_the_loss_reads(alg, double_q):
     # (not compared bit for bit: the loss / hyper-network bias partial sums of the mixing kernel meet in atomics, whose order
     # differs between any two runs)
     assert all(abs(a - b) <= 1e-6 * abs(a) for a, b in zip(lf, le)), (lf, le)
-    assert PU.rel_err(ge, gf) < 2e-6 and PU.rel_err(pe, pf) < 2e-6
+    # parameters after two RMSprop steps: g / (sqrt(0.01 g^2) + eps) turns the 1e-7 ordering noise of a near-zero gradient
+    # element into a few 1e-6 of the update, hence the wider bound on the parameters than on the gradients
+    assert PU.rel_err(ge, gf) < 2e-6 and PU.rel_err(pe, pf) < 2e-5
     oloss, _ = MO.train_step(st, rb, 0)
     assert abs(le[0] - oloss) <= TOL * abs(oloss)
 
