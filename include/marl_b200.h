@@ -407,6 +407,10 @@ int marl_linear_wgrad(const float* dy, int lddy, const float* x, int ldx, float*
 /* FP32 FMA throughput probe (the compute-roofline denominator bench.py reports against):
  * launches `blocks` x 256 threads x 8 independent FMA chains x `iters`; *flops_out = FLOPs issued. */
 int marl_fma_probe(float* scratch_device, int iters, int blocks, double* flops_out_host, void* stream);
+/* 1 when [p, p + bytes) is page-locked host memory the current device can read in place (the host pointer is the device
+ * pointer), else 0.  No reference counterpart: lets ReplayBuffer.store_episode (common/replaybuffer.py:30-61) hand pinned
+ * episode arrays to marl_ingest_f64 without a staging copy. */
+int marl_host_registered(const void* p, size_t bytes);
 /* Occupies the stream for ~us microseconds (<= 100000) so that later launches queue up behind it. */
 int marl_spin_us(int us, void* stream);
 int marl_profile_enable(int on);

@@ -112,6 +112,7 @@ class ReplayBuffer:
         self.version = np.zeros(self.size, dtype=np.int64)      # bumped whenever a ring row is rewritten
         self._stage = {}                                          # pinned / device staging of the host fast path
         self._idx_stage = {}
+        self._pending_read = None
         self.lock = threading.Lock()
 
     # ---- store ------------------------------------------------------------------------------------
@@ -121,6 +122,8 @@ class ReplayBuffer:
         the ring's fp32 / int64 layout by ONE ``marl_ingest_f64`` launch writing the ring rows in place."""
         import ctypes as C
         from .. import _lib as L
+        if self._store_pinned_in_place(episode_batch, batch_size, start):
+            return
         st = self._stage.get(batch_size)
         if st is None:
             sizes = [batch_size * int(np.prod(self.buffers[k].shape[1:])) for k in KEYS]
@@ -159,6 +162,40 @@ class ReplayBuffer:
         ev.record()
         st["done"][slot] = ev
 
+    def _store_pinned_in_place(self, episode_batch, batch_size, start):
+        """Zero-copy variant of the fast path: when every array of the episode already lives in page-locked host memory
+        (``torch.Tensor.pin_memory().numpy()``, ``cudaHostRegister``), the cast kernel reads the float64 values over PCIe
+        itself and writes the fp32 / int64 ring rows -- no packing pass on the host, no staging copy.  ``store_episode``
+        returns only when the kernel has read the arrays, so the caller may reuse them at once, exactly as after the
+        reference's synchronous numpy copy (common/replaybuffer.py:30-61)."""
+        import ctypes as C
+        from .. import _lib as L
+        lib = L.load()
+        ptrs = []
+        for k in KEYS:
+            a = episode_batch[k]
+            if not a.flags["C_CONTIGUOUS"] or a.dtype != np.float64 or a.ctypes.data % 16:
+                return False
+            if lib.marl_host_registered(a.ctypes.data, a.nbytes) != 1:
+                return False
+            ptrs.append(a.ctypes.data)
+        meta = self._stage.get(("meta", batch_size))
+        if meta is None:
+            meta = {"row_bytes": [self.buffers[k][0].numel() * self.buffers[k].element_size() for k in KEYS],
+                    "base": [self.buffers[k].data_ptr() for k in KEYS],
+                    "dims": L.Dims(batch_size, self.episode_limit, self.n_agents, self.n_actions, self.obs_shape, self.state_shape),
+                    "e64": L.EpisodeF64(), "e32": L.EpisodeF32(), "done": th.cuda.Event()}
+            meta["e64"].u_is_int64 = 0
+            self._stage[("meta", batch_size)] = meta
+        e64, e32 = meta["e64"], meta["e32"]
+        for i, k in enumerate(KEYS):
+            setattr(e64, k, ptrs[i])
+            setattr(e32, k, meta["base"][i] + start * meta["row_bytes"][i])
+        L.call("marl_ingest_f64", C.byref(e64), self.episode_limit, C.byref(meta["dims"]), C.byref(e32), L.stream_ptr())
+        meta["done"].record()
+        self._pending_read = meta["done"]        # store_episode waits on it after its host-side bookkeeping
+        return True
+
     def store_episode(self, episode_batch):
         batch_size = episode_batch['o'].shape[0]
         with self.lock:
@@ -178,6 +215,9 @@ class ReplayBuffer:
             first = np.where(term.any(axis=1), term.argmax(axis=1), -1)
             self.first_terminated[idx_np] = first
             self.version[idx_np] += 1
+            if self._pending_read is not None:       # zero-copy path: the kernel has finished reading the caller's arrays
+                self._pending_read.synchronize()
+                self._pending_read = None
 
     def _store_generic(self, episode_batch, batch_size, idx_np):
         """Any other input (CUDA tensors from the batched environment, int64 ``u``, wrapped ring positions): per-key copies."""

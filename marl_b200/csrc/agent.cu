@@ -14,6 +14,7 @@
 // eval unroll on o, algorithm/q_learner.py:96,110) are chained inside the same CTA.
 #include "linear.h"
 #include "tgemm.h"
+#include "front.h"
 #include "forkjoin.h"
 #include "../../include/marl_b200.h"
 #include "profile.h"
@@ -44,6 +45,15 @@ __device__ __forceinline__ float gate_tanh(float x) {
     return fabsf(x) < 0.2f ? small : big;
 }
 
+// Packed FP32 pairs (sm_100 FFMA2): one instruction = two fused multiply-adds on an aligned register pair.  The recurrent
+// loops run ONE warp per SM sub-partition, which issues an FFMA only every ~2.5 cycles (clock64 traces, profiles/README.md), so
+// they are bound by instructions issued, not by FMA lanes: the (even k, odd k) partial sums the loops already kept apart become
+// the two halves of one packed accumulator -- same products, same association, same rounding, half the instructions.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
 struct GruSegment {
     const float* gi;      // [B,L,N,3H]
     const float* w_hh;    // [3H,H]
@@ -61,7 +71,17 @@ struct GruFwdArgs {
     const float* h0[kMaxStreams];
     int n_chains, B, L, N;
     unsigned short rows_of[kMaxStreams][kNumSMs];   // rows of chain c advanced by CTA i (balanced on the host, see plan_rows)
+    long long* trace;                                // debug (marl_tgemm_trace): clock64 phase stamps of steps 8..15, CTA 0 / CTA 100
 };
+#ifdef MARL_GRU_TRACE      // tools/gru_trace.py with an A/B build (tools/ab_build.py trace -DMARL_GRU_TRACE)
+// (stamps of steps 8..15 stay in registers -- a store per stamp costs ~75 cycles and distorts the step -- and are written after the loop)
+#define GRU_STAMP(tag)                                                                                                  \
+    do {                                                                                                                \
+        if (trace && t >= 8 && t < 16) stamp[(t - 8) * 6 + (tag)] = (unsigned)clock();                                  \
+    } while (0)
+#else
+#define GRU_STAMP(tag) do { } while (0)
+#endif
 
 // One CTA advances R rows (b,n) of one chain through all its segments.  Thread (j, ks): hidden unit j,
 // half ks of the 64-long reduction; its 3 x 32 W_hh weights stay in registers for the whole segment.
@@ -93,6 +113,11 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
             cdst[l] = rr * MARL_G + ch * 4;
         } else { csrc[l] = -1; cdst[l] = 0; }
     }
+#ifdef MARL_GRU_TRACE
+    long long* trace = (a.trace && tid == 0 && chain == 0 && (blockIdx.x == 0 || blockIdx.x == 100)) ? a.trace + (blockIdx.x ? 512 : 0) : nullptr;
+    unsigned stamp[48] = {};
+    if (trace) { trace[508] = R; trace[509] = nrows; }
+#endif
     const float* h0 = a.h0[chain];
     for (int idx = tid; idx < R * MARL_H; idx += kGruThreads) {
         const int rr = idx / MARL_H, jj = idx % MARL_H, row = row0 + rr;
@@ -101,13 +126,13 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
     int cur = 0;
     for (int sg = a.chain_start[chain]; sg < a.chain_start[chain] + a.chain_len[chain]; ++sg) {
         const GruSegment S = a.seg[sg];
-        float w[3][32];
+        f32x2 w[3][16];                                  // (w[k], w[k+1]) pairs of this lane's slice of rows g*H + j
 #pragma unroll
         for (int g = 0; g < 3; ++g)
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(S.w_hh + (long long)(g * MARL_H + j) * MARL_H + 4 * (2 * i + ks)));
-                w[g][4 * i + 0] = v.x; w[g][4 * i + 1] = v.y; w[g][4 * i + 2] = v.z; w[g][4 * i + 3] = v.w;
+                w[g][2 * i] = pack2(v.x, v.y); w[g][2 * i + 1] = pack2(v.z, v.w);
             }
         const float bh_r = __ldg(S.b_hh + j), bh_z = __ldg(S.b_hh + MARL_H + j), bh_n = __ldg(S.b_hh + 2 * MARL_H + j);
         // per-step output pointers of the rows this lane owns: advanced by one time step (N rows) per iteration
@@ -135,39 +160,45 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
 #pragma unroll
         for (int t = 0; t < kGiDepth - 1; ++t) issue(t);
         for (int t = 0; t < Lp; ++t) {
+            GRU_STAMP(0);
             cp_async_wait<kGiDepth - 2>();           // this thread's copies for step t have landed
             group_sync(bar_id);                      // ... the whole group's; also orders the h double buffer
+            GRU_STAMP(1);
             // Few rows per CTA = latency-bound chain: the refill's address math and LSU hand-off (~150 cycles when it sat
             // here, measured with clock64) go behind the FMAs, where they overlap the FMA drain.  Many rows per CTA =
             // throughput-bound: keep the prefetch as early as possible.
             constexpr bool kLateIssue = R <= 2;
             if (!kLateIssue) issue(t + kGiDepth - 1);   // refill the slot consumed in step t-1
-            float acc[3][R], acc2[3][R];          // two partial sums per dot product: short dependent FMA chains
+            float acc[3][R];
+            f32x2 pacc[3][R];                     // (even k, odd k) partial sums of each dot product, packed
 #pragma unroll
             for (int g = 0; g < 3; ++g)
 #pragma unroll
-                for (int rr = 0; rr < R; ++rr) { acc[g][rr] = 0.0f; acc2[g][rr] = 0.0f; }
+                for (int rr = 0; rr < R; ++rr) pacc[g][rr] = 0ull;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr) {
-                    const float4 hv = *reinterpret_cast<const float4*>(&hs[cur][rr][4 * (2 * i + ks)]);
+                    const ulonglong2 hv = *reinterpret_cast<const ulonglong2*>(&hs[cur][rr][4 * (2 * i + ks)]);
 #pragma unroll
                     for (int g = 0; g < 3; ++g) {
-                        acc[g][rr] = fmaf(w[g][4 * i + 0], hv.x, acc[g][rr]);
-                        acc2[g][rr] = fmaf(w[g][4 * i + 1], hv.y, acc2[g][rr]);
-                        acc[g][rr] = fmaf(w[g][4 * i + 2], hv.z, acc[g][rr]);
-                        acc2[g][rr] = fmaf(w[g][4 * i + 3], hv.w, acc2[g][rr]);
+                        pacc[g][rr] = ffma2(w[g][2 * i], hv.x, pacc[g][rr]);
+                        pacc[g][rr] = ffma2(w[g][2 * i + 1], hv.y, pacc[g][rr]);
                     }
                 }
+            GRU_STAMP(2);
             if (kLateIssue) issue(t + kGiDepth - 1);
+            GRU_STAMP(3);
 #pragma unroll
             for (int g = 0; g < 3; ++g)
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr) {
-                    acc[g][rr] += acc2[g][rr];
+                    float ev, od;
+                    unpack2(pacc[g][rr], ev, od);
+                    acc[g][rr] = ev + od;
                     acc[g][rr] += __shfl_xor_sync(0xffffffffu, acc[g][rr], 1);
                 }
+            GRU_STAMP(4);
             const float* gring = &ring[t % kGiDepth][0][0];
 #pragma unroll
             for (int q = 0; q < OWN; ++q) {
@@ -196,7 +227,15 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
                 if (gp_out[q]) gp_out[q] += gstep;
             }
             cur ^= 1;
+            GRU_STAMP(5);
         }
+#ifdef MARL_GRU_TRACE
+        if (trace && sg == a.chain_start[chain]) {
+#pragma unroll
+            for (int k = 0; k < 48; ++k) { trace[2 * k] = (k % 6) + 100 * (8 + k / 6); trace[2 * k + 1] = stamp[k]; }
+            trace[510] = 48;
+        }
+#endif
         cp_async_wait<0>();
         group_sync(bar_id);
         if (S.h_last) {
@@ -276,11 +315,13 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
         dh_carry[q] = 0.0f;
     }
     // column j of W_hh, rows m = 4*(2i+ks)+c, i = 0..23:  dh_prev[j] = dh z + sum_m dgh[m] W_hh[m, j]
-    float wt[96];
+    f32x2 wt[48];                                          // (rows m, m+1) pairs
 #pragma unroll
     for (int i = 0; i < 24; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) wt[4 * i + c] = __ldg(a.w_hh + (long long)(4 * (2 * i + ks) + c) * MARL_H + j);
+        for (int c = 0; c < 2; ++c)
+            wt[2 * i + c] = pack2(__ldg(a.w_hh + (long long)(4 * (2 * i + ks) + 2 * c) * MARL_H + j),
+                                  __ldg(a.w_hh + (long long)(4 * (2 * i + ks) + 2 * c + 1) * MARL_H + j));
     // cp.async work list: per row 112 chunks of 16 B (64 gates, 16 h_prev, 16 dh_ext, 16 dh_ext2); the
     // per-chunk source pointer at t = 0 and its per-step stride are fixed, so they are computed once.
     constexpr int NCH = (R * 112 + kGruThreads - 1) / kGruThreads;
@@ -378,23 +419,24 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
         if (!kLateIssue) { issue(t - (D - 1)); cp_async_wait<D - 2>(); }
         else cp_async_wait<D - 3>();     // only D-2 groups are pending here: step t-1 has landed
         __syncthreads();                 // dgh of step t visible; ring[t-1] visible
-        float part[R], pb[R], pc[R], pd[R];     // four partial sums per row: short dependent FMA chains
+        float part[R];
+        f32x2 pab[R], pcd[R];                   // four partial sums per row in two packed accumulators: short dependent chains
 #pragma unroll
-        for (int rr = 0; rr < R; ++rr) { part[rr] = 0.0f; pb[rr] = 0.0f; pc[rr] = 0.0f; pd[rr] = 0.0f; }
+        for (int rr = 0; rr < R; ++rr) { pab[rr] = 0ull; pcd[rr] = 0ull; }
 #pragma unroll
         for (int i = 0; i < 24; ++i)
 #pragma unroll
             for (int rr = 0; rr < R; ++rr) {
-                const float4 v = *reinterpret_cast<const float4*>(&sg[cur][rr][4 * (2 * i + ks)]);
-                part[rr] = fmaf(wt[4 * i + 0], v.x, part[rr]);
-                pb[rr] = fmaf(wt[4 * i + 1], v.y, pb[rr]);
-                pc[rr] = fmaf(wt[4 * i + 2], v.z, pc[rr]);
-                pd[rr] = fmaf(wt[4 * i + 3], v.w, pd[rr]);
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&sg[cur][rr][4 * (2 * i + ks)]);
+                pab[rr] = ffma2(wt[2 * i], v.x, pab[rr]);
+                pcd[rr] = ffma2(wt[2 * i + 1], v.y, pcd[rr]);
             }
         if (kLateIssue) issue(t - (D - 1));
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
-            part[rr] = (part[rr] + pb[rr]) + (pc[rr] + pd[rr]);
+            float pa, pb, pc, pd;
+            unpack2(pab[rr], pa, pb); unpack2(pcd[rr], pc, pd);
+            part[rr] = (pa + pb) + (pc + pd);
             part[rr] += __shfl_xor_sync(0xffffffffu, part[rr], 1);
         }
 #pragma unroll
@@ -537,7 +579,24 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         return g;
     };
     bool grouped = false;
-    if (tgemm_enabled()) {
+    {
+        // fused path (csrc/front.cu): both layers of every stream in ONE persistent launch, x handed from the first GEMM to the
+        // second through tensor memory
+        FrontArgs fa{};
+        fa.rows = rows_total; fa.I = I;
+        for (int i = 0; i < n_streams; ++i) {
+            fa.s[i].in = agent_input(d, s[i].obs, s[i].onehot, s[i].shift_onehot, s[i].full_input);
+            fa.s[i].x = s[i].x; fa.s[i].gi = s[i].gi;
+            fa.set[i].w1 = s[i].params.fc1_w; fa.set[i].b1 = s[i].params.fc1_b;
+            fa.set[i].w_ih = s[i].params.w_ih; fa.set[i].b_ih = s[i].params.b_ih;
+        }
+        if (front_plan(fa, n_streams)) {
+            const int rc = front_launch(fa, kGruPrio, st);
+            if (rc) return rc;
+            grouped = true;
+        }
+    }
+    if (!grouped && tgemm_enabled()) {
         // TMA path: the streams of one layer are ONE grouped launch of persistent CTAs (csrc/tgemm.cu): 2 launches
         // instead of 2 x n_streams on forked streams
         TGBuilder b1, b2;
@@ -602,6 +661,7 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         const int n_ctas = rows < kNumSMs ? rows : kNumSMs;
         if ((rows + n_ctas - 1) / n_ctas + 2 > 65535) return MARL_EINVAL;
         plan_rows(ga, rows, n_ctas);
+        ga.trace = trace_buffer();
         dim3 grid(n_ctas, (ga.n_chains + kGruGroups - 1) / kGruGroups);
         launch_pdl_prio(kGruPrio, gru_unroll_fwd_kernel, grid, dim3(kGruThreads * kGruGroups), sm, st, ga);
     }

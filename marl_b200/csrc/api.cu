@@ -56,3 +56,20 @@ extern "C" int marl_spin_us(int us, void* stream) {
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }
+
+// 1 when [p, p + bytes) is page-locked host memory that kernels of the current device can read in place (cudaHostAlloc /
+// cudaHostRegister; unified addressing makes the host pointer the device pointer), else 0.  The replay buffer uses it to ingest
+// an episode straight from the caller's pinned arrays -- the float64 -> fp32 cast kernel pulls the bytes over PCIe itself --
+// instead of packing them into a staging buffer first.
+extern "C" int marl_host_registered(const void* p, size_t bytes) {
+    if (!p) return 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (at.type != cudaMemoryTypeHost || at.devicePointer != p) return 0;
+    if (bytes > 1) {
+        cudaPointerAttributes last;
+        if (cudaPointerGetAttributes(&last, static_cast<const char*>(p) + bytes - 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+        if (last.type != cudaMemoryTypeHost) return 0;
+    }
+    return 1;
+}

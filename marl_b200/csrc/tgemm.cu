@@ -93,6 +93,8 @@ struct TGItem { int pi, m0, n0, kb0, kb1, local; };
 
 // Optional phase trace of CTA 0 (MARL_TGEMM_TRACE=1 + marl_tgemm_trace_dump): (tag, clock64) pairs, 512 per role.
 __device__ long long* g_tg_trace = nullptr;
+static long long* g_trace_host = nullptr;          // the same buffer for kernels of other files (passed as an argument)
+long long* trace_buffer() { return g_trace_host; }
 #define TG_STAMP(role, tag)                                                                                   \
     do {                                                                                                      \
         if (trace && tn < 255) { trace[(role) * 512 + 2 * tn] = (tag); trace[(role) * 512 + 2 * tn + 1] = clock64(); ++tn; } \
@@ -844,6 +846,7 @@ extern "C" int marl_tgemm_trace(int on, long long* host_out /* 2048 or null */) 
     if (on && buf) cudaMemset(buf, 0, 2048 * sizeof(long long));
     if (host_out && buf) { cudaDeviceSynchronize(); cudaMemcpy(host_out, buf, 2048 * sizeof(long long), cudaMemcpyDeviceToHost); }
     long long* v = on ? buf : nullptr;
+    marl::g_trace_host = v;
     cudaMemcpyToSymbol(marl::g_tg_trace, &v, sizeof(v));
     return MARL_OK;
 }

@@ -58,6 +58,8 @@ struct TGReduceJob {
 struct TGReduceGroup { TGReduceJob j[TG_MAXP]; int n; };
 
 bool tgemm_enabled();
+// debug phase trace (marl_tgemm_trace): device buffer of 4 roles x 512 words, or nullptr when tracing is off
+long long* trace_buffer();
 // library-owned view of a caller-provided scratch arena (marl_set_scratch); nullptr when it does not fit
 float* tgemm_scratch(size_t bytes);
 

@@ -53,3 +53,32 @@ def test_sampled_view_materialises_like_the_reference_dict():
         want = ep[k][[4, 0, 0, 2]]
         want = want.astype(np.int64) if k == "u" else want.astype(np.float32)
         assert np.array_equal(view[k].cpu().numpy(), want), k
+
+
+def test_pinned_episode_is_ingested_in_place():
+    """store_episode on arrays that already live in page-locked host memory takes the zero-copy path (the cast kernel reads
+    them over PCIe): same ring contents as the packed path and as the reference's numpy ring (common/replaybuffer.py:30-61),
+    and the source may be overwritten as soon as the call returns."""
+    from marl_b200 import _lib as L
+    N, A, O, S, T = 5, 11, 80, 120, 30
+    args = PU.make_args("qmix", N, A, O, S, T, buffer_size=6)
+    pinned_buf, packed_buf = ReplayBuffer(args), ReplayBuffer(args)
+    orc = OracleReplayBuffer(6, T, N, A, O, S)
+    lib = L.load()
+    for seed in range(8):                                     # one episode at a time, the ring wraps
+        ep = synthetic_batch(seed, 1, T, N, A, O, S, full_length_first=False, min_len=2)
+        keep = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).pin_memory() for k, v in ep.items()}
+        src = {k: t.numpy() for k, t in keep.items()}
+        assert all(lib.marl_host_registered(v.ctypes.data, v.nbytes) == 1 for v in src.values())
+        assert lib.marl_host_registered(ep["o"].ctypes.data, ep["o"].nbytes) == 0          # pageable numpy memory
+        pinned_buf.store_episode(src)
+        for v in src.values():
+            v.fill(-7.0)                                       # the caller reuses its arrays at once
+        packed_buf.store_episode({k: v.copy() for k, v in ep.items()})
+        orc.store(ep)
+    assert ("meta", 1) in pinned_buf._stage and ("meta", 1) not in packed_buf._stage
+    for k in KEYS:
+        want = orc.rings[k].astype(np.int64) if k == "u" else orc.rings[k].astype(np.float32)
+        assert np.array_equal(pinned_buf.buffers[k].cpu().numpy(), want), k
+        assert np.array_equal(packed_buf.buffers[k].cpu().numpy(), want), k
+    assert np.array_equal(pinned_buf.first_terminated, packed_buf.first_terminated)

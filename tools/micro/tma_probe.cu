@@ -131,8 +131,10 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
                 const int k = k0 + 4 * h, kb = k / 32, c = (k % 32) / 4;
                 const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(a_raw) + kb * M * 128 + r * 128 + ((c ^ (r & 7)) << 4));
                 hi[4 * h + 0] = __float_as_uint(v.x); hi[4 * h + 1] = __float_as_uint(v.y); hi[4 * h + 2] = __float_as_uint(v.z); hi[4 * h + 3] = __float_as_uint(v.w);
-                lo[4 * h + 0] = __float_as_uint(tf32_lo(v.x)); lo[4 * h + 1] = __float_as_uint(tf32_lo(v.y));
-                lo[4 * h + 2] = __float_as_uint(tf32_lo(v.z)); lo[4 * h + 3] = __float_as_uint(tf32_lo(v.w));
+                // (the lo words come from the lo pass above: with split 4 the raw tile already holds the ROUNDED hi values)
+                const float4 w = *reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(a_lo) + kb * M * 128 + r * 128 + ((c ^ (r & 7)) << 4));
+                lo[4 * h + 0] = __float_as_uint(w.x); lo[4 * h + 1] = __float_as_uint(w.y);
+                lo[4 * h + 2] = __float_as_uint(w.z); lo[4 * h + 3] = __float_as_uint(w.w);
             }
             const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
             asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
