@@ -111,7 +111,7 @@ typedef struct marl_unroll_stream {
                                 see marl_select_fused) */
     float* hidden;           /* out [B,L,N,H], h after each step */
     float* h_last;           /* out [B*N,H] or NULL */
-    float* x;                /* workspace/out [B,L,N,H]: relu(fc1) (needed by the backward) */
+    float* x;                /* workspace/out [B,L,N,H]: relu(fc1) (needed by the backward; the fused input-layer kernel only fills it when `gates` is given) */
     float* gi;               /* workspace [B,L,N,3H] */
     float* gates;            /* out [B,L,N,4H] (r, z, n, W_hn h + b_hn) for the backward, or NULL */
     const int* ep_len;       /* device [B] (marl_episode_lengths) or NULL.  Non-NULL: this stream's recurrence stops each row at

@@ -587,6 +587,7 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         for (int i = 0; i < n_streams; ++i) {
             fa.s[i].in = agent_input(d, s[i].obs, s[i].onehot, s[i].shift_onehot, s[i].full_input);
             fa.s[i].x = s[i].x; fa.s[i].gi = s[i].gi;
+            fa.s[i].store_x = s[i].gates != nullptr;
             fa.set[i].w1 = s[i].params.fc1_w; fa.set[i].b1 = s[i].params.fc1_b;
             fa.set[i].w_ih = s[i].params.w_ih; fa.set[i].b_ih = s[i].params.b_ih;
         }

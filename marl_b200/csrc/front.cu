@@ -26,12 +26,19 @@
 namespace marl {
 
 constexpr int FM = 128, FN1 = MARL_H, FN2 = MARL_G, FK = 16;
-constexpr int kFrontStages = 3;
+constexpr int kFrontStages = 2;
+// k-tiles a producer thread keeps in flight in registers.  With two, a phase trace (tools/front_trace.py) showed ~0.9 us per
+// k-tile = ~1.8 us of loaded memory latency per fetch: the kernel is bound by bytes in flight, not by conversion or MMAs.
+#ifndef MARL_FRONT_DEPTH
+#define MARL_FRONT_DEPTH 3
+#endif
+constexpr int kFrontDepth = MARL_FRONT_DEPTH;
 constexpr int kProd = 256;                                   // producer threads
 constexpr int kFrontThreads = kProd + 32 + 128 + 128;        // + MMA warp + E warps + F warps
 constexpr int kWarpMma = kProd / 32, kWarpE = kWarpMma + 1, kWarpF = kWarpE + 4;
 constexpr int FA_PITCH = FM * 4 + 8, FB_PITCH = FN1 * 4 + 8, FW_PITCH = FN2 * 4 + 8;   // canonical K-major layout, see linear.cu
 constexpr int kStagePitch = 36;                              // floats per staged row: conflict-free 128-bit stores and loads
+constexpr int kStageE = FN1 + 4;                             // same for the [32 rows][64 cols] block of x
 
 // TMEM columns
 constexpr uint32_t kColAcc1 = 0, kColCorr1 = 64, kColXhi = 128, kColXlo = 192, kColAcc2 = 256, kFrontTmemCols = 512;
@@ -47,7 +54,7 @@ struct alignas(128) FrontSmem {
     float wih_hi[(MARL_H / 4) * FW_PITCH];
     float wih_lo[(MARL_H / 4) * FW_PITCH];
     FrontStage st[kFrontStages];
-    float stage_e[4][32 * kStagePitch];
+    float stage_e[4][32 * kStageE];
     float stage_f[4][32 * kStagePitch];
     float b1[FN1];
     float bih[FN2];
@@ -106,6 +113,7 @@ __device__ __forceinline__ void st_global4(float* p, const float4& v) {
 }
 
 // the warp's staged [32 rows][32 cols] block -> global rows of 128 contiguous bytes (four rows per instruction)
+template <int PITCH>
 __device__ __forceinline__ void staged_rows_out(const float* stg, float* out, int ld, int row0, int rows, int col0, const float* bias, bool relu) {
     const int lane = threadIdx.x & 31, c4 = (lane & 7) * 4, rsub = lane >> 3;
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -113,7 +121,7 @@ __device__ __forceinline__ void staged_rows_out(const float* stg, float* out, in
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = 4 * i + rsub;
-        float4 t = *reinterpret_cast<const float4*>(stg + r * kStagePitch + c4);
+        float4 t = *reinterpret_cast<const float4*>(stg + r * PITCH + c4);
         t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
         if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
         if (row0 + r < rows) st_global4(out + (long long)(row0 + r) * ld + col0 + c4, t);
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) agent_front_kernel(const Fro
         OpLin A{};
         OpLin::Row arow[2];
         int f_it = -1, f_kt = nk - 1;                    // fetch cursor (tile iteration, k-tile); advanced before each fetch
-        float4 ra[2][2], rb[2];
+        float4 ra[kFrontDepth][2], rb[kFrontDepth];
         auto fetch = [&](int set) {
             if (++f_kt == nk) {
                 f_kt = 0; ++f_it;
@@ -225,21 +233,27 @@ __global__ void __launch_bounds__(kFrontThreads, 1) agent_front_kernel(const Fro
             *reinterpret_cast<float4*>(lo + off) = l;
         };
         const int total = n_my * nk;
-        fetch(0);
-        fetch(1);
-        for (int g = 0; g < total; ++g) {
-            const int s = g % kFrontStages, use = g / kFrontStages;
-            FrontStage& st = sm.st[s];
-            mbar_wait(&sm.empty[s], (uint32_t)((use & 1) ^ 1));          // the MMAs that read this stage last time are done
-            FT_STAMP(0, g);
-            const int set = g & 1;
-            put(st.a_hi, st.a_lo, (ar >> 2) * FA_PITCH + ai[0] * 4, set ? ra[1][0] : ra[0][0]);
-            put(st.a_hi, st.a_lo, (ar >> 2) * FA_PITCH + ai[1] * 4, set ? ra[1][1] : ra[0][1]);
-            put(st.b_hi, st.b_lo, (ar >> 2) * FB_PITCH + bj * 4, set ? rb[1] : rb[0]);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-            mbar_arrive(&sm.full[s]);
-            FT_STAMP(0, 1000 + g);
-            if (set) fetch(1); else fetch(0);                              // k-tile g + 2
+#pragma unroll
+        for (int d = 0; d < kFrontDepth; ++d) fetch(d);
+        for (int g0 = 0; g0 < total; g0 += kFrontDepth) {
+#pragma unroll
+            for (int d = 0; d < kFrontDepth; ++d) {                         // (unrolled: the register set index must be static)
+                const int g = g0 + d;
+                if (g >= total) break;
+                const int s = g % kFrontStages, use = g / kFrontStages;
+                FrontStage& st = sm.st[s];
+                mbar_wait(&sm.empty[s], (uint32_t)((use & 1) ^ 1));      // the MMAs that read this stage last time are done
+                FT_STAMP(0, g);
+                put(st.a_hi, st.a_lo, (ar >> 2) * FA_PITCH + ai[0] * 4, ra[d][0]);
+                put(st.a_hi, st.a_lo, (ar >> 2) * FA_PITCH + ai[1] * 4, ra[d][1]);
+                put(st.b_hi, st.b_lo, (ar >> 2) * FB_PITCH + bj * 4, rb[d]);
+                FT_STAMP(0, 2000 + g);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+                mbar_arrive(&sm.full[s]);
+                FT_STAMP(0, 1000 + g);
+                fetch(d);                                                    // k-tile g + kFrontDepth
+                FT_STAMP(0, 3000 + g);
+            }
         }
     } else if (warp == kWarpMma) {
         // =========================================================== MMA issue (lane 0)
@@ -293,9 +307,8 @@ __global__ void __launch_bounds__(kFrontThreads, 1) agent_front_kernel(const Fro
                 }
                 __syncwarp();
             }
-            if (it > 0) gemm2(it - 1);                                     // behind GEMM 1 of the next tile: the E warps work meanwhile
+            gemm2(it);
         }
-        if (n_my > 0) gemm2(n_my - 1);
     } else if (warp < kWarpF) {
         // =========================================================== E: acc1 -> x -> (TMEM hi/lo, global)
         const int q = warp & 3;                                            // TMEM lane quarter this warp may touch
@@ -303,55 +316,51 @@ __global__ void __launch_bounds__(kFrontThreads, 1) agent_front_kernel(const Fro
         float* stg = sm.stage_e[q];
         for (int it = 0; it < n_my; ++it) {
             const int t = cta + it * n_ctas;
-            float* xout = sm.s[sm.set.stream[t / tps]].x;
+            const FrontStream& S = sm.s[sm.set.stream[t / tps]];
+            float* xout = S.store_x ? S.x : nullptr;
             const int m0 = (t % tps) * FM;
             mbar_wait(&sm.acc1_full, (uint32_t)(it & 1));
             tc_fence_after();
             FT_STAMP(2, it);
-            float v[FN1];
-#pragma unroll
+            if (it > 0) mbar_wait(&sm.acc2_full, (uint32_t)((it - 1) & 1));   // GEMM 2 of the previous tile has read x(it-1) from TMEM
+            tc_fence_after();
+            FT_STAMP(2, 5500 + it);
+            // 16 columns at a time (registers: 17 warps are allocated as 20, i.e. 96 per thread): acc1 -> +b1 -> ReLU -> hi / lo
+            // back into TMEM; the fp32 values are parked in the warp's staging block and leave for global memory AFTER the
+            // hand-over, off the MMA warp's critical path
+#pragma unroll 1
             for (int c = 0; c < FN1 / 16; ++c) {
                 uint32_t m[16], k[16];
                 tmem_ld16(tq + kColAcc1 + 16 * c, m);
                 tmem_ld16(tq + kColCorr1 + 16 * c, k);
                 tmem_wait_ld();
 #pragma unroll
-                for (int e = 0; e < 16; ++e) v[16 * c + e] = fmaxf(__uint_as_float(m[e]) + __uint_as_float(k[e]) + sm.b1[16 * c + e], 0.f);
+                for (int e4 = 0; e4 < 16; e4 += 4) {
+                    float xv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        xv[e] = fmaxf(__uint_as_float(m[e4 + e]) + __uint_as_float(k[e4 + e]) + sm.b1[16 * c + e4 + e], 0.f);
+                        float hh, ll;
+                        tf32_split(xv[e], hh, ll);
+                        m[e4 + e] = __float_as_uint(hh); k[e4 + e] = __float_as_uint(ll);
+                    }
+                    if (xout) *reinterpret_cast<float4*>(stg + lane * kStageE + 16 * c + e4) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+                }
+                tmem_st16(tq + kColXhi + 16 * c, m);
+                tmem_st16(tq + kColXlo + 16 * c, k);
             }
             tc_fence_before();
             mbar_arrive(&sm.acc1_free);
-            FT_STAMP(2, 5000 + it);
-            if (it > 0) mbar_wait(&sm.acc2_full, (uint32_t)((it - 1) & 1));   // GEMM 2 of the previous tile has read x(it-1) from TMEM
-            tc_fence_after();
-            FT_STAMP(2, 5500 + it);
-#pragma unroll
-            for (int c = 0; c < FN1 / 16; ++c) {
-                uint32_t h[16], l[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    float hh, ll;
-                    tf32_split(v[16 * c + e], hh, ll);
-                    h[e] = __float_as_uint(hh); l[e] = __float_as_uint(ll);
-                }
-                tmem_st16(tq + kColXhi + 16 * c, h);
-                tmem_st16(tq + kColXlo + 16 * c, l);
-            }
             FT_STAMP(2, 6000 + it);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&sm.xa_ready);
             FT_STAMP(2, 1000 + it);
             if (xout) {
-#pragma unroll
-                for (int hlf = 0; hlf < 2; ++hlf) {
-#pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4)
-                        *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * g4) =
-                            make_float4(v[32 * hlf + 4 * g4], v[32 * hlf + 4 * g4 + 1], v[32 * hlf + 4 * g4 + 2], v[32 * hlf + 4 * g4 + 3]);
-                    __syncwarp();
-                    staged_rows_out(stg, xout, FN1, m0 + q * 32, rows, 32 * hlf, nullptr, false);
-                    __syncwarp();
-                }
+                __syncwarp();
+                staged_rows_out<kStageE>(stg, xout, FN1, m0 + q * 32, rows, 0, nullptr, false);
+                staged_rows_out<kStageE>(stg + 32, xout, FN1, m0 + q * 32, rows, 32, nullptr, false);
+                __syncwarp();
             }
             FT_STAMP(2, 2000 + it);
         }
@@ -380,7 +389,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) agent_front_kernel(const Fro
                         make_float4(__uint_as_float(v[4 * g4]), __uint_as_float(v[4 * g4 + 1]), __uint_as_float(v[4 * g4 + 2]), __uint_as_float(v[4 * g4 + 3]));
                 __syncwarp();
                 if (it == 1) FT_STAMP(3, 6000 + c);
-                staged_rows_out(stg, gout, FN2, m0 + q * 32, rows, 32 * c, sm.bih, false);
+                staged_rows_out<kStagePitch>(stg, gout, FN2, m0 + q * 32, rows, 32 * c, sm.bih, false);
                 __syncwarp();
                 if (it == 1) FT_STAMP(3, 7000 + c);
             }

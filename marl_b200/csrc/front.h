@@ -11,6 +11,7 @@ struct FrontStream {
     float* x;               // [rows, 64]  relu(fc1(in))
     float* gi;              // [rows, 192] W_ih x + b_ih
     int vec_in;             // 128-bit loads legal on the first source
+    int store_x;            // x is only needed by the backward pass: streams that record no gates skip its 256 B per row
 };
 
 // streams that share one parameter set (eval on o and on o_next; target on o_next) are served by the same CTAs
