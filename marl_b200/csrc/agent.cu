@@ -592,7 +592,7 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
             fa.set[i].w_ih = s[i].params.w_ih; fa.set[i].b_ih = s[i].params.b_ih;
         }
         if (front_plan(fa, n_streams)) {
-            const int rc = front_launch(fa, kGruPrio, st);
+            const int rc = front_launch(fa, n_streams, kGruPrio, st);
             if (rc) return rc;
             grouped = true;
         }

@@ -4,19 +4,25 @@
 // for every (episode, step, agent) row of every stream (eval on o, target on o_next, double-Q eval on o_next:
 // controller/share_params.py:125-168).
 //
-// One CTA per SM walks 128-row tiles.  Roles (17 warps):
-//   8 producer warps   global -> registers (two k-tiles ahead) -> hi/lo TF32 split -> shared-memory ring (3 stages)
-//   1 MMA warp         GEMM 1: acc1[128 x 64]  = in . W1^T     tcgen05.mma kind::tf32, operands from the ring
-//                      GEMM 2: acc2[128 x 192] = x . W_ih^T    A operand read from TENSOR MEMORY, B = W_ih resident in
-//                                                              shared memory for the CTA's whole life
-//   4 "E" warps        acc1 -> +b1 -> ReLU -> x to global; x split into hi/lo and written back to TMEM as GEMM 2's A
-//   4 "F" warps        acc2 -> +b_ih -> gi to global (staged through shared memory: 128-byte coalesced rows)
-// so x never makes the round trip through HBM/L2 between the two layers, and the four stages overlap across tiles.
+// One CTA per SM walks 128-row tiles.  Roles (18 warps):
+//   1 TMA warp         obs tile -> shared memory, 32 columns x 128 rows per box (cp.async.bulk.tensor, 128-byte swizzle), a ring
+//                      of kRawSlots boxes in flight.  (The register-staged version of this kernel was bound by the LSU: ~1 us to
+//                      ISSUE the loads of a k-tile behind the epilogue's stores, tools/front_trace.py.)
+//   8 converter warps  thread = tile row (two groups alternate k-tiles): raw box (+ the last-action / agent-id columns, composed on the fly) -> hi / lo TF32
+//                      halves -> TENSOR MEMORY (tcgen05.st), the A operand of GEMM 1; the k-tile's slice of W1 -> hi / lo in
+//                      shared memory (B operand)
+//   1 MMA warp         GEMM 1: acc1[128 x 64]  = in . W1^T     tcgen05.mma kind::tf32, A from TMEM
+//                      GEMM 2: acc2[128 x 192] = x . W_ih^T    A from TMEM, B = W_ih resident in shared memory for the CTA's life
+//   4 "E" warps        acc1 -> +b1 -> ReLU -> x split into hi / lo and written back to TMEM as GEMM 2's A; fp32 x -> global
+//   4 "F" warps        acc2 -> +b_ih -> gi -> global
+// Both outputs leave as 32 x 32 boxes through cp.async.bulk.tensor stores from 128-byte-swizzled staging blocks.  x never makes
+// the round trip through HBM/L2 between the two layers, and the stages overlap across tiles.
 //
 // 3xTF32 (see linear.cu).  GEMM 1 streams its reduction, so the two 2^-11 correction products go to their own
 // accumulator; GEMM 2 has both operands resident and issues ALL its correction products first: the accumulator is still
 // ~2^-11 of its final magnitude while they land, so the fp32-accumulate truncation they add is negligible and the eight
 // main products see the same number of updates as with a separate correction accumulator.
+#include <cuda.h>
 #include "front.h"
 #include "umma.cuh"
 #include "tgemm.h"
@@ -26,53 +32,47 @@
 namespace marl {
 
 constexpr int FM = 128, FN1 = MARL_H, FN2 = MARL_G, FK = 16;
-constexpr int kFrontStages = 2;
-// k-tiles a producer thread keeps in flight in registers.  With two, a phase trace (tools/front_trace.py) showed ~0.9 us per
-// k-tile = ~1.8 us of loaded memory latency per fetch: the kernel is bound by bytes in flight, not by conversion or MMAs.
-#ifndef MARL_FRONT_DEPTH
-#define MARL_FRONT_DEPTH 3
+// E / converter / F warps: warp % 4 = TMEM lane quarter.  Two converter groups of four warps: group 0 takes the even k-tiles (A / B
+// buffer 0), group 1 the odd ones (buffer 1)
+constexpr int kWarpE = 0, kWarpC = 4, kWarpF = 12, kWarpMma = 16, kWarpTma = 17;
+constexpr int kFrontThreads = 18 * 32;
+constexpr int FB_PITCH = FN1 * 4 + 8, FW_PITCH = FN2 * 4 + 8;   // canonical K-major layout, see linear.cu
+#ifndef MARL_FRONT_SLOTS
+#define MARL_FRONT_SLOTS 3
 #endif
-constexpr int kFrontDepth = MARL_FRONT_DEPTH;
-constexpr int kProd = 256;                                   // producer threads
-constexpr int kFrontThreads = kProd + 32 + 128 + 128;        // + MMA warp + E warps + F warps
-constexpr int kWarpMma = kProd / 32, kWarpE = kWarpMma + 1, kWarpF = kWarpE + 4;
-constexpr int FA_PITCH = FM * 4 + 8, FB_PITCH = FN1 * 4 + 8, FW_PITCH = FN2 * 4 + 8;   // canonical K-major layout, see linear.cu
-constexpr int kStagePitch = 36;                              // floats per staged row: conflict-free 128-bit stores and loads
-constexpr int kStageE = FN1 + 4;                             // same for the [32 rows][64 cols] block of x
+constexpr int kRawSlots = MARL_FRONT_SLOTS;                     // obs boxes in flight per CTA (16 KB each)
+constexpr int kBoxCols = 2 * FK;                                // one box = two k-tiles: 128-byte rows = whole L2 lines
+constexpr int kRawBytes = FM * kBoxCols * 4;
 
 // TMEM columns
-constexpr uint32_t kColAcc1 = 0, kColCorr1 = 64, kColXhi = 128, kColXlo = 192, kColAcc2 = 256, kFrontTmemCols = 512;
+constexpr uint32_t kColAcc1 = 0, kColCorr1 = 64, kColXhi = 128, kColXlo = 192, kColAcc2 = 256, kColA = 448, kFrontTmemCols = 512;
 
-struct FrontStage {
-    float a_hi[(FK / 4) * FA_PITCH];
-    float a_lo[(FK / 4) * FA_PITCH];
-    float b_hi[(FK / 4) * FB_PITCH];
-    float b_lo[(FK / 4) * FB_PITCH];
+struct FrontB {                                                  // one k-tile of W1, hi / lo
+    float hi[(FK / 4) * FB_PITCH];
+    float lo[(FK / 4) * FB_PITCH];
 };
 
-struct alignas(128) FrontSmem {
+struct alignas(1024) FrontSmem {
+    unsigned char raw[kRawSlots][kRawBytes];                     // TMA boxes [128 rows][128 B], 128-byte swizzle
+    float stage_e[4][32 * 32];                                   // per E warp: one swizzled 32 x 32 box of x (columns 0-31, then 32-63)
+    float stage_f[4][2][32 * 32];                                // per F warp: two gi boxes (one draining, one being filled)
     float wih_hi[(MARL_H / 4) * FW_PITCH];
     float wih_lo[(MARL_H / 4) * FW_PITCH];
-    FrontStage st[kFrontStages];
-    float stage_e[4][32 * kStageE];
-    float stage_f[4][32 * kStagePitch];
+    FrontB b[2];
     float b1[FN1];
     float bih[FN2];
     FrontSet set;
     FrontStream s[kFrontMaxStreams];
-    uint64_t full[kFrontStages], empty[kFrontStages];
+    uint64_t raw_full[kRawSlots], raw_empty[kRawSlots];
+    uint64_t a_full[2], a_empty[2];
     uint64_t acc1_full, acc1_free, xa_ready, acc2_full, acc2_free;
     uint32_t tmem_base;
 };
-constexpr size_t kFrontSmemBytes = sizeof(FrontSmem) + 128;
+constexpr size_t kFrontSmemBytes = sizeof(FrontSmem) + 1024;
 static_assert(kFrontSmemBytes <= 227 * 1024, "front kernel shared memory");
 
 constexpr uint32_t front_idesc(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(FM >> 4) << 24); }
 
-__device__ __forceinline__ void fmma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-                 ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
-}
 __device__ __forceinline__ void fmma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
                  ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
@@ -80,8 +80,22 @@ __device__ __forceinline__ void fmma_ts(uint32_t d, uint32_t a_tmem, uint64_t b,
 __device__ __forceinline__ void fcommit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -107,28 +121,8 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// (a pointer read from shared memory is generic to the compiler; a generic store would fence the LDS traffic around it)
-__device__ __forceinline__ void st_global4(float* p, const float4& v) {
-    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 
-// the warp's staged [32 rows][32 cols] block -> global rows of 128 contiguous bytes (four rows per instruction)
-template <int PITCH>
-__device__ __forceinline__ void staged_rows_out(const float* stg, float* out, int ld, int row0, int rows, int col0, const float* bias, bool relu) {
-    const int lane = threadIdx.x & 31, c4 = (lane & 7) * 4, rsub = lane >> 3;
-    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias) b = *reinterpret_cast<const float4*>(bias + col0 + c4);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = 4 * i + rsub;
-        float4 t = *reinterpret_cast<const float4*>(stg + r * PITCH + c4);
-        t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
-        if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
-        if (row0 + r < rows) st_global4(out + (long long)(row0 + r) * ld + col0 + c4, t);
-    }
-}
-
-// debug phase trace of CTA 0: (tag, globaltimer ns) pairs, 255 per role (0 producer, 1 MMA, 2 E, 3 F)
+// debug phase trace of CTA 0: (tag, globaltimer ns) pairs, 255 per role (0 converter, 1 MMA, 2 E, 3 F)
 #define FT_STAMP(role, tag)                                                                                            \
     do {                                                                                                               \
         if (trace && tn < 255) {                                                                                       \
@@ -137,11 +131,18 @@ __device__ __forceinline__ void staged_rows_out(const float* stg, float* out, in
         }                                                                                                              \
     } while (0)
 
-__global__ void __launch_bounds__(kFrontThreads, 1) agent_front_kernel(const FrontArgs a) {
+struct FrontMaps {
+    CUtensorMap obs[kFrontMaxStreams];      // [rows, K1]   box {32, 128}, 128-byte swizzle
+    CUtensorMap x[kFrontMaxStreams];        // [rows, 64]   box {32, 32}, 128-byte swizzle
+    CUtensorMap gi[kFrontMaxStreams];       // [rows, 192]  box {32, 32}, 128-byte swizzle
+};
+
+__global__ void __launch_bounds__(kFrontThreads, 1) agent_front_kernel(const FrontArgs a, const __grid_constant__ FrontMaps maps) {
     extern __shared__ unsigned char front_smem_raw[];
-    FrontSmem& sm = *reinterpret_cast<FrontSmem*>((reinterpret_cast<uintptr_t>(front_smem_raw) + 127) & ~(uintptr_t)127);
+    FrontSmem& sm = *reinterpret_cast<FrontSmem*>((reinterpret_cast<uintptr_t>(front_smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    long long* trace = (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kWarpMma || warp == kWarpE || warp == kWarpF)) ? a.trace : nullptr;
+    const int role = warp == kWarpC ? 0 : warp == kWarpMma ? 1 : warp == kWarpE ? 2 : warp == kWarpF ? 3 : 0;
+    long long* trace = (blockIdx.x == 0 && lane == 0 && (warp == kWarpC || warp == kWarpMma || warp == kWarpE || warp == kWarpF)) ? a.trace : nullptr;
     int tn = 0;
 
     // ---- which parameter set this CTA serves, copied to shared memory (dynamically indexed reads of the kernel
@@ -152,15 +153,11 @@ __global__ void __launch_bounds__(kFrontThreads, 1) agent_front_kernel(const Fro
         sm.set = a.set[p];
         for (int k = 0; k < kFrontMaxStreams; ++k) sm.s[k] = a.s[k];
 #pragma unroll
-        for (int s = 0; s < kFrontStages; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&sm.full[s])), "r"(kProd));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.empty[s])));
-        }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.acc1_full)));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_u32(&sm.acc1_free)));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_u32(&sm.xa_ready)));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.acc2_full)));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_u32(&sm.acc2_free)));
+        for (int s = 0; s < kRawSlots; ++s) { mbar_init(&sm.raw_full[s], 1); mbar_init(&sm.raw_empty[s], 256); }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) { mbar_init(&sm.a_full[s], 128); mbar_init(&sm.a_empty[s], 1); }
+        mbar_init(&sm.acc1_full, 1); mbar_init(&sm.acc1_free, 128); mbar_init(&sm.xa_ready, 128);
+        mbar_init(&sm.acc2_full, 1); mbar_init(&sm.acc2_free, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kWarpMma) {
@@ -170,20 +167,42 @@ __global__ void __launch_bounds__(kFrontThreads, 1) agent_front_kernel(const Fro
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    FT_STAMP(warp == 0 ? 0 : warp == kWarpMma ? 1 : warp == kWarpE ? 2 : 3, 9000);
+    FT_STAMP(role, 9000);
     pdl_wait();                                          // nothing above touched global memory
-    FT_STAMP(warp == 0 ? 0 : warp == kWarpMma ? 1 : warp == kWarpE ? 2 : 3, 9001);
+    FT_STAMP(role, 9001);
     const uint32_t tmem = sm.tmem_base;
     const int I = a.I, rows = a.rows, tps = a.tiles_per_stream;
     const int nk = (I + FK - 1) / FK;
     const int n_ctas = sm.set.n_ctas, cta = (int)blockIdx.x - sm.set.cta0;
     const int set_tiles = sm.set.n_streams * tps;
     const int n_my = cta < set_tiles ? (set_tiles - cta + n_ctas - 1) / n_ctas : 0;
+    const int nb = (nk + 1) / 2;                         // boxes per tile: box j holds k-tiles 2j (converter group 0) and 2j + 1 (group 1)
+    const int total_boxes = n_my * nb;
 
-    // ---- resident operands: W_ih as hi / lo TF32 halves in the K-major UMMA layout, the two bias vectors
-    {
+    // =========================================================== TMA producer (lane 0 of its warp)
+    int tma_it = 0, tma_j = 0;
+    auto tma_issue = [&](int b_begin, int b_end) {
+        for (int bs = b_begin; bs < b_end; ++bs) {
+            const int r = bs % kRawSlots, use = bs / kRawSlots;
+            mbar_wait(&sm.raw_empty[r], (uint32_t)((use & 1) ^ 1));
+            const int t = cta + tma_it * n_ctas, si = sm.set.stream[t / tps];
+            if (tma_j * kBoxCols < sm.s[si].in.K1) {
+                mbar_expect_tx(&sm.raw_full[r], (uint32_t)kRawBytes);      // (columns / rows past the tensor are zero-filled and counted)
+                tma_load_2d(sm.raw[r], &maps.obs[si], tma_j * kBoxCols, (t % tps) * FM, &sm.raw_full[r]);
+            } else {
+                mbar_arrive(&sm.raw_full[r]);                              // a box made of composed columns only
+            }
+            if (++tma_j == nb) { tma_j = 0; ++tma_it; }
+        }
+    };
+    const int tma_prologue = total_boxes < kRawSlots ? total_boxes : kRawSlots;
+    if (warp == kWarpTma) {
+        if (lane == 0) tma_issue(0, tma_prologue);      // the first boxes are in flight while the other warps stage the weights
+        __syncwarp();
+    } else {
+        // ---- resident operands: W_ih as hi / lo TF32 halves in the K-major UMMA layout, the two bias vectors
         const float* w = sm.set.w_ih;
-        for (int idx = tid; idx < FN2 * (MARL_H / 4); idx += kFrontThreads) {
+        for (int idx = tid; idx < FN2 * (MARL_H / 4); idx += kWarpTma * 32) {
             const int n = idx >> 4, c = idx & 15;
             const float4 v = __ldg(reinterpret_cast<const float4*>(w + (long long)n * MARL_H + 4 * c));
             float4 h, l;
@@ -194,75 +213,143 @@ __global__ void __launch_bounds__(kFrontThreads, 1) agent_front_kernel(const Fro
         if (tid < FN1) sm.b1[tid] = sm.set.b1 ? __ldg(sm.set.b1 + tid) : 0.f;
         if (tid < FN2) sm.bih[tid] = sm.set.b_ih ? __ldg(sm.set.b_ih + tid) : 0.f;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
     }
-    FT_STAMP(warp == 0 ? 0 : warp == kWarpMma ? 1 : warp == kWarpE ? 2 : 3, 9002);
+    __syncthreads();
+    FT_STAMP(role, 9002);
 
-    if (warp < kWarpMma) {
-        // =========================================================== producers
-        const int ai[2] = {tid >> 2, (tid + kProd) >> 2}, ar = (tid & 3) * 4;        // A quads: rows ai[l], reduction offset ar
-        const int bj = tid >> 2;                                                      // B quad: row bj (< 64), same ar
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp >= kWarpC && warp < kWarpF) {
+        // =========================================================== converters: thread = tile row, group = k-tile parity
+        const int grp = (warp - kWarpC) >> 2;                                              // k-tiles g = grp, grp + 2, ...
+        const int q = warp & 3, row_in_tile = q * 32 + lane, ct = (tid - kWarpC * 32) & 127;   // ct: 0..127 inside the group
+        const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+        // this thread's two quads of the W1 k-tile: feature row bj, 16-byte chunk bc
+        const int bj[2] = {ct >> 2, (ct + 128) >> 2}, bc = ct & 3;
         const OpMat B{sm.set.w1, I, FN1, I, sm.set.vec_w1 != 0};
-        const OpMat::Row brow = B.row(bj);
-        OpLin A{};
-        OpLin::Row arow[2];
-        int f_it = -1, f_kt = nk - 1;                    // fetch cursor (tile iteration, k-tile); advanced before each fetch
-        float4 ra[kFrontDepth][2], rb[kFrontDepth];
-        auto fetch = [&](int set) {
-            if (++f_kt == nk) {
-                f_kt = 0; ++f_it;
-                if (f_it < n_my) {
-                    const int t = cta + f_it * n_ctas;
-                    const FrontStream& S = sm.s[sm.set.stream[t / tps]];
-                    const int m0 = (t % tps) * FM;
-                    A = OpLin{S.in, 0, rows, I, S.vec_in != 0, S.vec_in != 0 && vec2_ok(S.in)};
-                    arow[0] = A.row(m0 + ai[0]); arow[1] = A.row(m0 + ai[1]);
+        const OpMat::Row brow[2] = {B.row(bj[0]), B.row(bj[1])};
+        float4 wq[2];
+        auto load_w1 = [&](int kt) {                                                       // W1 slice of a k-tile (L2-resident)
+            const int kn = kt * FK + 4 * bc;
+            wq[0] = kn < I ? B.quad_at(brow[0], kn) : make_float4(0.f, 0.f, 0.f, 0.f);
+            wq[1] = kn < I ? B.quad_at(brow[1], kn) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        load_w1(grp < nk ? grp : 0);
+        // row context of the composed columns [K1, I): last action (shifted one step inside the episode) and agent id
+        const float* x2r = nullptr; int hot = -1, K1 = 0, K2 = 0;
+        const int bsel = grp;
+        int use = 0, it = 0, j = 0;
+        for (int bs = 0; bs < total_boxes; ++bs) {
+            const int r = bs % kRawSlots, kt = 2 * j + grp;
+            const uint32_t box_parity = (uint32_t)((bs / kRawSlots) & 1);
+            if (j == 0) {
+                const int t = cta + it * n_ctas;
+                const LinOperand& o = sm.s[sm.set.stream[t / tps]].in;
+                const int m = (t % tps) * FM + row_in_tile;
+                K1 = o.K1; K2 = o.K2; x2r = nullptr; hot = -1;
+                if (m < rows) {
+                    if (K2 > 0 && !(o.x2_shift && (m % o.x2_period) < o.x2_shift)) x2r = o.x2 + (long long)(m - o.x2_shift) * o.ldx2;
+                    if (o.onehot_mod) hot = K1 + K2 + (m % o.onehot_mod);
                 }
             }
-            if (f_it >= n_my) return;
-            const int r = f_kt * FK + ar;
-            ra[set][0] = r < I ? A.quad_at(arow[0], r) : zero4;
-            ra[set][1] = r < I ? A.quad_at(arow[1], r) : zero4;
-            rb[set] = r < I ? B.quad_at(brow, r) : zero4;
-        };
-        auto put = [&](float* hi, float* lo, int off, const float4& v) {
-            float4 h, l;
-            tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
-            *reinterpret_cast<float4*>(hi + off) = h;
-            *reinterpret_cast<float4*>(lo + off) = l;
-        };
-        const int total = n_my * nk;
-#pragma unroll
-        for (int d = 0; d < kFrontDepth; ++d) fetch(d);
-        for (int g0 = 0; g0 < total; g0 += kFrontDepth) {
-#pragma unroll
-            for (int d = 0; d < kFrontDepth; ++d) {                         // (unrolled: the register set index must be static)
-                const int g = g0 + d;
-                if (g >= total) break;
-                const int s = g % kFrontStages, use = g / kFrontStages;
-                FrontStage& st = sm.st[s];
-                mbar_wait(&sm.empty[s], (uint32_t)((use & 1) ^ 1));      // the MMAs that read this stage last time are done
-                FT_STAMP(0, g);
-                put(st.a_hi, st.a_lo, (ar >> 2) * FA_PITCH + ai[0] * 4, ra[d][0]);
-                put(st.a_hi, st.a_lo, (ar >> 2) * FA_PITCH + ai[1] * 4, ra[d][1]);
-                put(st.b_hi, st.b_lo, (ar >> 2) * FB_PITCH + bj * 4, rb[d]);
-                FT_STAMP(0, 2000 + g);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-                mbar_arrive(&sm.full[s]);
-                FT_STAMP(0, 1000 + g);
-                fetch(d);                                                    // k-tile g + kFrontDepth
-                FT_STAMP(0, 3000 + g);
+            const int jn = (j + 1 == nb) ? 0 : j + 1;
+            if (kt >= nk) {                                                   // odd number of k-tiles: the last box has no second half
+                mbar_wait(&sm.raw_full[r], box_parity);
+                mbar_arrive(&sm.raw_empty[r]);
+                j = jn; if (j == 0) ++it;
+                continue;
             }
+            const int k0 = kt * FK;
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = 0.f;
+            // the composed columns first (global loads in flight while the box is awaited)
+            if (k0 + FK > K1) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int k = k0 + e;
+                    if (k >= K1 && k < K1 + K2) { if (x2r) v[e] = __ldg(x2r + (k - K1)); }
+                    else if (k == hot) v[e] = 1.0f;
+                }
+            }
+            mbar_wait(&sm.raw_full[r], box_parity);
+            if (k0 < K1) {
+                // 128-byte swizzle: 16-byte chunk c of box row rr sits at chunk c ^ (rr & 7); this group's k-tile = chunks 4 grp ..
+                const unsigned char* box = sm.raw[r] + row_in_tile * 128;
+                const int sw = row_in_tile & 7;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(box + (((4 * grp + c) ^ sw) << 4));
+                    if (k0 + 4 * c + 3 < K1) { v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w; }
+                    else {
+                        if (k0 + 4 * c < K1) v[4 * c] = t4.x;
+                        if (k0 + 4 * c + 1 < K1) v[4 * c + 1] = t4.y;
+                        if (k0 + 4 * c + 2 < K1) v[4 * c + 2] = t4.z;
+                    }
+                }
+            }
+            mbar_arrive(&sm.raw_empty[r]);                                   // (values are in registers)
+            uint32_t h[16], l[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                float hh, ll;
+                tf32_split(v[e], hh, ll);
+                h[e] = __float_as_uint(hh); l[e] = __float_as_uint(ll);
+            }
+            mbar_wait(&sm.a_empty[bsel], (uint32_t)((use & 1) ^ 1));         // the MMAs that read this A / B buffer pair are done
+            tc_fence_after();
+            FT_STAMP(0, bs);
+            tmem_st16(tq + kColA + 32 * bsel, h);
+            tmem_st16(tq + kColA + 32 * bsel + 16, l);
+            FrontB& sb = sm.b[bsel];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                float4 hh, ll;
+                tf32_split(wq[u].x, hh.x, ll.x); tf32_split(wq[u].y, hh.y, ll.y); tf32_split(wq[u].z, hh.z, ll.z); tf32_split(wq[u].w, hh.w, ll.w);
+                *reinterpret_cast<float4*>(sb.hi + bc * FB_PITCH + bj[u] * 4) = hh;
+                *reinterpret_cast<float4*>(sb.lo + bc * FB_PITCH + bj[u] * 4) = ll;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&sm.a_full[bsel]);
+            FT_STAMP(0, 1000 + bs);
+            ++use;
+            j = jn; if (j == 0) ++it;
+            load_w1(2 * j + grp < nk ? 2 * j + grp : grp);                    // this group's next k-tile
         }
     } else if (warp == kWarpMma) {
         // =========================================================== MMA issue (lane 0)
         const uint32_t id1 = front_idesc(FN1), id2 = front_idesc(FN2);
-        auto gemm2 = [&](int j) {
-            mbar_wait(&sm.xa_ready, (uint32_t)(j & 1));                    // x(j) hi / lo are in TMEM
-            mbar_wait(&sm.acc2_free, (uint32_t)((j & 1) ^ 1));             // gi(j-1) has been read out of acc2
+        for (int it = 0; it < n_my; ++it) {
+            mbar_wait(&sm.acc1_free, (uint32_t)((it & 1) ^ 1));            // x(it-1) has been read out of acc1
             tc_fence_after();
-            FT_STAMP(1, 2000 + j);
+            for (int kt = 0; kt < nk; ++kt) {
+                const int bsel = kt & 1;                                   // converter group = k-tile parity inside the tile
+                const int use = (bsel ? it * (nk >> 1) : it * nb) + (kt >> 1);
+                mbar_wait(&sm.a_full[bsel], (uint32_t)(use & 1));
+                tc_fence_after();
+                FT_STAMP(1, it * nk + kt);
+                if (lane == 0) {
+                    const FrontB& sb = sm.b[bsel];
+                    const uint32_t ta = tmem + kColA + 32 * bsel;
+#pragma unroll
+                    for (int k8 = 0; k8 < FK / 8; ++k8) {
+                        const uint32_t bo = (uint32_t)(2 * k8) * FB_PITCH * 4;
+                        const uint64_t dbh = umma_desc(smem_u32(sb.hi) + bo, FB_PITCH * 4, 128), dbl = umma_desc(smem_u32(sb.lo) + bo, FB_PITCH * 4, 128);
+                        const uint32_t first = (kt | k8) ? 1u : 0u;
+                        fmma_ts(tmem + kColCorr1, ta + 16 + 8 * k8, dbh, id1, first);      // lo . hi
+                        fmma_ts(tmem + kColCorr1, ta + 8 * k8, dbl, id1, 1u);              // hi . lo
+                        fmma_ts(tmem + kColAcc1, ta + 8 * k8, dbh, id1, first);            // hi . hi
+                    }
+                    fcommit(&sm.a_empty[bsel]);
+                    if (kt == nk - 1) fcommit(&sm.acc1_full);
+                }
+                __syncwarp();
+            }
+            // GEMM 2 of this tile
+            mbar_wait(&sm.xa_ready, (uint32_t)(it & 1));                   // x(it) hi / lo are in TMEM
+            mbar_wait(&sm.acc2_free, (uint32_t)((it & 1) ^ 1));            // gi(it-1) has been read out of acc2
+            tc_fence_after();
+            FT_STAMP(1, 2000 + it);
             if (lane == 0) {
                 const uint32_t wh = smem_u32(sm.wih_hi), wl = smem_u32(sm.wih_lo);
 #pragma unroll
@@ -278,57 +365,29 @@ __global__ void __launch_bounds__(kFrontThreads, 1) agent_front_kernel(const Fro
                 }
                 fcommit(&sm.acc2_full);
             }
-            FT_STAMP(1, 3000 + j);
+            FT_STAMP(1, 3000 + it);
             __syncwarp();
-        };
-        int g = 0;
-        for (int it = 0; it < n_my; ++it) {
-            mbar_wait(&sm.acc1_free, (uint32_t)((it & 1) ^ 1));            // x(it-1) has been read out of acc1
-            tc_fence_after();
-            for (int kt = 0; kt < nk; ++kt, ++g) {
-                const int s = g % kFrontStages, use = g / kFrontStages;
-                mbar_wait(&sm.full[s], (uint32_t)(use & 1));
-                tc_fence_after();
-                FT_STAMP(1, g);
-                if (lane == 0) {
-                    const FrontStage& st = sm.st[s];
-#pragma unroll
-                    for (int k8 = 0; k8 < FK / 8; ++k8) {
-                        const uint32_t ao = (uint32_t)(2 * k8) * FA_PITCH * 4, bo = (uint32_t)(2 * k8) * FB_PITCH * 4;
-                        const uint64_t dah = umma_desc(smem_u32(st.a_hi) + ao, FA_PITCH * 4, 128), dal = umma_desc(smem_u32(st.a_lo) + ao, FA_PITCH * 4, 128);
-                        const uint64_t dbh = umma_desc(smem_u32(st.b_hi) + bo, FB_PITCH * 4, 128), dbl = umma_desc(smem_u32(st.b_lo) + bo, FB_PITCH * 4, 128);
-                        const uint32_t first = (kt | k8) ? 1u : 0u;
-                        fmma_ss(tmem + kColCorr1, dal, dbh, id1, first);
-                        fmma_ss(tmem + kColCorr1, dah, dbl, id1, 1u);
-                        fmma_ss(tmem + kColAcc1, dah, dbh, id1, first);
-                    }
-                    fcommit(&sm.empty[s]);
-                    if (kt == nk - 1) fcommit(&sm.acc1_full);
-                }
-                __syncwarp();
-            }
-            gemm2(it);
         }
-    } else if (warp < kWarpF) {
+    } else if (warp < kWarpC) {
         // =========================================================== E: acc1 -> x -> (TMEM hi/lo, global)
         const int q = warp & 3;                                            // TMEM lane quarter this warp may touch
         const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
-        float* stg = sm.stage_e[q];
+        float* blk = &sm.stage_e[q][0];
         for (int it = 0; it < n_my; ++it) {
-            const int t = cta + it * n_ctas;
-            const FrontStream& S = sm.s[sm.set.stream[t / tps]];
-            float* xout = S.store_x ? S.x : nullptr;
+            const int t = cta + it * n_ctas, si = sm.set.stream[t / tps];
+            const bool store_x = sm.s[si].store_x != 0;
             const int m0 = (t % tps) * FM;
             mbar_wait(&sm.acc1_full, (uint32_t)(it & 1));
-            tc_fence_after();
             FT_STAMP(2, it);
             if (it > 0) mbar_wait(&sm.acc2_full, (uint32_t)((it - 1) & 1));   // GEMM 2 of the previous tile has read x(it-1) from TMEM
             tc_fence_after();
-            FT_STAMP(2, 5500 + it);
-            // 16 columns at a time (registers: 17 warps are allocated as 20, i.e. 96 per thread): acc1 -> +b1 -> ReLU -> hi / lo
-            // back into TMEM; the fp32 values are parked in the warp's staging block and leave for global memory AFTER the
-            // hand-over, off the MMA warp's critical path
-#pragma unroll 1
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the last box of the previous tile has left the staging block
+            __syncwarp();
+            // 16 columns at a time: acc1 -> +b1 -> ReLU -> hi / lo back into TMEM.  The fp32 values of columns 0-31 are parked in
+            // the warp's staging box (lane = row, 16-byte chunk ch at ch ^ (row & 7): conflict-free), those of columns 32-63 in
+            // registers; both leave AFTER the hand-over, off the MMA warp's critical path
+            float keep[32];
+#pragma unroll
             for (int c = 0; c < FN1 / 16; ++c) {
                 uint32_t m[16], k[16];
                 tmem_ld16(tq + kColAcc1 + 16 * c, m);
@@ -344,59 +403,87 @@ __global__ void __launch_bounds__(kFrontThreads, 1) agent_front_kernel(const Fro
                         tf32_split(xv[e], hh, ll);
                         m[e4 + e] = __float_as_uint(hh); k[e4 + e] = __float_as_uint(ll);
                     }
-                    if (xout) *reinterpret_cast<float4*>(stg + lane * kStageE + 16 * c + e4) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+                    if (c < 2) {
+                        const int ch = c * 4 + (e4 >> 2);
+                        if (store_x) *reinterpret_cast<float4*>(blk + lane * 32 + 4 * (ch ^ (lane & 7))) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) keep[(c - 2) * 16 + e4 + e] = xv[e];
+                    }
                 }
                 tmem_st16(tq + kColXhi + 16 * c, m);
                 tmem_st16(tq + kColXlo + 16 * c, k);
             }
             tc_fence_before();
             mbar_arrive(&sm.acc1_free);
-            FT_STAMP(2, 6000 + it);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&sm.xa_ready);
             FT_STAMP(2, 1000 + it);
-            if (xout) {
+            if (store_x) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                staged_rows_out<kStageE>(stg, xout, FN1, m0 + q * 32, rows, 0, nullptr, false);
-                staged_rows_out<kStageE>(stg + 32, xout, FN1, m0 + q * 32, rows, 32, nullptr, false);
+                if (lane == 0) {
+                    tma_store_2d(&maps.x[si], 0, m0 + q * 32, blk);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
                 __syncwarp();
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    *reinterpret_cast<float4*>(blk + lane * 32 + 4 * (ch ^ (lane & 7))) = make_float4(keep[4 * ch], keep[4 * ch + 1], keep[4 * ch + 2], keep[4 * ch + 3]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&maps.x[si], 32, m0 + q * 32, blk);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
             }
             FT_STAMP(2, 2000 + it);
         }
-    } else {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else if (warp == kWarpTma) {
+        if (lane == 0) tma_issue(tma_prologue, total_boxes);
+        __syncwarp();
+    } else if (warp < kWarpMma) {
         // =========================================================== F: acc2 -> gi
         const int q = warp & 3;
         const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
-        float* stg = sm.stage_f[q];
+        int seq = 0;
         for (int it = 0; it < n_my; ++it) {
-            const int t = cta + it * n_ctas;
-            float* gout = sm.s[sm.set.stream[t / tps]].gi;
+            const int t = cta + it * n_ctas, si = sm.set.stream[t / tps];
             const int m0 = (t % tps) * FM;
             mbar_wait(&sm.acc2_full, (uint32_t)(it & 1));
             tc_fence_after();
             FT_STAMP(3, it);
 #pragma unroll 1
-            for (int c = 0; c < FN2 / 32; ++c) {
+            for (int c = 0; c < FN2 / 32; ++c, ++seq) {
                 uint32_t v[32];
                 tmem_ld32(tq + kColAcc2 + 32 * c, v);
+                float* blk = &sm.stage_f[q][seq & 1][0];
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used this block has read it
+                __syncwarp();
                 tmem_wait_ld();
-                if (it == 1) FT_STAMP(3, 5000 + c);
                 if (c == FN2 / 32 - 1) { tc_fence_before(); mbar_arrive(&sm.acc2_free); }
 #pragma unroll
-                for (int g4 = 0; g4 < 8; ++g4)
-                    *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * g4) =
-                        make_float4(__uint_as_float(v[4 * g4]), __uint_as_float(v[4 * g4 + 1]), __uint_as_float(v[4 * g4 + 2]), __uint_as_float(v[4 * g4 + 3]));
+                for (int g4 = 0; g4 < 8; ++g4) {
+                    const float4 b = *reinterpret_cast<const float4*>(&sm.bih[32 * c + 4 * g4]);
+                    *reinterpret_cast<float4*>(blk + lane * 32 + 4 * (g4 ^ (lane & 7))) =
+                        make_float4(__uint_as_float(v[4 * g4]) + b.x, __uint_as_float(v[4 * g4 + 1]) + b.y,
+                                    __uint_as_float(v[4 * g4 + 2]) + b.z, __uint_as_float(v[4 * g4 + 3]) + b.w);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (it == 1) FT_STAMP(3, 6000 + c);
-                staged_rows_out<kStagePitch>(stg, gout, FN2, m0 + q * 32, rows, 32 * c, sm.bih, false);
-                __syncwarp();
-                if (it == 1) FT_STAMP(3, 7000 + c);
+                if (lane == 0) {
+                    tma_store_2d(&maps.gi[si], 32 * c, m0 + q * 32, blk);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
             }
             FT_STAMP(3, 1000 + it);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
-    FT_STAMP(warp == 0 ? 0 : warp == kWarpMma ? 1 : warp == kWarpE ? 2 : 3, 9003);
+    FT_STAMP(role, 9003);
     pdl_trigger();
     tc_fence_before();
     __syncthreads();
@@ -409,19 +496,54 @@ bool front_enabled() {
     return on == 1;
 }
 
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+namespace {
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiled encoder() {
+    static EncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiled)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+// 2-D fp32 tensor [rows, cols] with a row pitch in floats
+bool make_map(CUtensorMap* m, const float* base, int cols, long long rows, long long pitch, int box_c, int box_r, CUtensorMapSwizzle sw) {
+    EncodeTiled enc = encoder();
+    if (!enc || !base || !aligned16(base) || (pitch & 3) || cols <= 0 || rows <= 0) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)pitch * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_r};
+    cuuint32_t est[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
 
 // Groups the streams into parameter sets and deals the CTAs of the grid to the sets in proportion to their tiles.
 // a.s[0 .. n_streams), a.rows, a.I are filled by the caller, together with one FrontSet per stream in a.set[i]
 // (w1 / b1 / w_ih / b_ih of stream i); this merges equal sets.
 bool front_plan(FrontArgs& a, int n_streams) {
-    if (!front_enabled() || n_streams < 1 || n_streams > kFrontMaxStreams || a.rows <= 0) return false;
+    if (!front_enabled() || !encoder() || n_streams < 1 || n_streams > kFrontMaxStreams || a.rows <= 0) return false;
     if (a.I <= 0 || a.I > 256) return false;            // GEMM 1 keeps one main accumulator: <= 32 accumulator updates
     for (int i = 0; i < n_streams; ++i) {
-        if (!aligned16(a.s[i].gi) || (a.s[i].x && !aligned16(a.s[i].x))) return false;
+        if (!aligned16(a.s[i].gi) || !a.s[i].x || !aligned16(a.s[i].x)) return false;
         if (!aligned16(a.set[i].w_ih)) return false;
         const LinOperand& o = a.s[i].in;
-        a.s[i].vec_in = (o.K1 == 0) ? 0 : (o.K1 >= 4 && o.x && aligned16(o.x) && (o.ldx & 3) == 0 && (o.K1 & 3) == 0);
+        // the first source goes through a tensor map: dense 16-byte-aligned rows
+        if (o.K1 <= 0 || !o.x || !aligned16(o.x) || (o.ldx & 3) || o.x_bs != 0) return false;
+        if (lin_width(o) != a.I) return false;
+        a.s[i].vec_in = 1;
         a.set[i].vec_w1 = aligned16(a.set[i].w1) && (a.I & 3) == 0;
     }
     FrontSet sets[kFrontMaxStreams];
@@ -450,15 +572,22 @@ bool front_plan(FrontArgs& a, int n_streams) {
     return true;
 }
 
-int front_launch(const FrontArgs& a, int prio, cudaStream_t st) {
+int front_launch(const FrontArgs& a, int n_streams, int prio, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(agent_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrontSmemBytes); attr_set = true; }
+    FrontMaps maps;
+    for (int i = 0; i < kFrontMaxStreams; ++i) {
+        const FrontStream& S = a.s[i < n_streams ? i : 0];
+        if (!make_map(&maps.obs[i], S.in.x, S.in.K1, a.rows, S.in.ldx, kBoxCols, FM, CU_TENSOR_MAP_SWIZZLE_128B)) return MARL_EINVAL;
+        if (!make_map(&maps.x[i], S.x, FN1, a.rows, FN1, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return MARL_EINVAL;
+        if (!make_map(&maps.gi[i], S.gi, FN2, a.rows, FN2, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return MARL_EINVAL;
+    }
     int grid = 0;
     for (int k = 0; k < a.n_sets; ++k) grid += a.set[k].n_ctas;
     ProfScope ps_("agent_front_kernel", st);
     FrontArgs b = a;
     b.trace = trace_buffer();
-    launch_pdl_prio(prio, agent_front_kernel, dim3(grid), dim3(kFrontThreads), kFrontSmemBytes, st, b);
+    launch_pdl_prio(prio, agent_front_kernel, dim3(grid), dim3(kFrontThreads), kFrontSmemBytes, st, b, maps);
     MARL_LAUNCH_CHECK();
     return MARL_OK;
 }

@@ -35,6 +35,6 @@ struct FrontArgs {
 bool front_enabled();
 // false: the shapes do not qualify (I > 256, misaligned outputs) -- the caller runs the layers one by one
 bool front_plan(FrontArgs& a, int n_streams);
-int front_launch(const FrontArgs& a, int prio, cudaStream_t st);
+int front_launch(const FrontArgs& a, int n_streams, int prio, cudaStream_t st);
 
 }  // namespace marl

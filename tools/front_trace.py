@@ -23,7 +23,7 @@ L.call("marl_tgemm_trace", 1, None)
 learner.train(db, 10)
 buf = (C.c_longlong * 2048)()
 L.call("marl_tgemm_trace", 0, C.cast(buf, C.c_void_p))
-names = ["prod", "mma ", "E   ", "F   "]
+names = ["conv", "mma ", "E   ", "F   "]
 ev = []
 for r in range(4):
     n = buf[r * 512 + 510]
