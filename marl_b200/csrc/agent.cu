@@ -455,6 +455,10 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
     __syncthreads();
 }
 
+#ifndef MARL_GRU_BWD_CTAS
+#define MARL_GRU_BWD_CTAS 2
+#endif
+constexpr int kGruBwdCtasPerSm = MARL_GRU_BWD_CTAS;      // 254 registers x 128 threads and ~55 KB of shared memory: two CTAs fit an SM
 constexpr size_t gru_bwd_smem_max() { return gru_bwd_smem(8) > gru_bwd_smem(4) ? gru_bwd_smem(8) : gru_bwd_smem(4); }
 
 __global__ void __launch_bounds__(kGruThreads) gru_unroll_bwd_kernel(GruBwdArgs a) {
@@ -710,7 +714,10 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
         // measured: launched programmatically the 148 recurrence CTAs come up while the producer still runs and the
         // step gets 10-27 us slower on every config; a plain launch here, PDL for its consumers
         pdl_small_problem() = false;
-        launch_pdl_prio(kGruPrio, gru_unroll_bwd_kernel, dim3(rows < kNumSMs ? rows : kNumSMs), dim3(kGruThreads), gru_bwd_smem_max(), st, ga);
+        // up to two rows per SM: one CTA per row -- two co-resident one-row CTAs overlap each other's latency, where one CTA with two
+        // rows serialises 2 x 96 packed FMAs per thread on the dependent chain (the 12 two-row CTAs of config 2 ended the kernel)
+        const int n_ctas = rows <= kGruBwdCtasPerSm * kNumSMs ? rows : kNumSMs;
+        launch_pdl_prio(kGruPrio, gru_unroll_bwd_kernel, dim3(n_ctas), dim3(kGruThreads), gru_bwd_smem_max(), st, ga);
         pdl_small_problem() = keep_;
     }
     MARL_LAUNCH_CHECK();
