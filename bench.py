@@ -374,7 +374,7 @@ def run_ours(opt):
     dev_max = float(max(tm.last_per_step))
 
     # ---- e2e (headline): the reference's own loop, runner.py:92-97 -- one freshly generated HOST episode is stored
-    # (pinned float64 -> H2D -> fp32 ring row), a batch of 32 is sampled, train() returns the loss to the host ----------------
+    # (pinned float64 -> read over PCIe by the cast kernel -> fp32 ring row), a batch of 32 is sampled, train() returns the loss ----
     rb_args = make_args()
     rb_args.buffer_size = 512
     buf = ReplayBuffer(rb_args)
@@ -578,19 +578,20 @@ def run_ours(opt):
                     "hbm_frac": (gru_bytes / (dom_us * 1e-6) / 1e9 / hbm_peak) if gru_bytes else None,
                     "peak_source": "fp32: marl_fma_probe on this GPU, the builder's own probe (MEASURED_PEAKS.json has no fp32 "
                                    "figure; nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4); hbm: " + peak_src}
-    gemm_us = sum(v["us_per_step"] for k, v in kernels.items() if k.startswith(("linear_", "tgemm_", "wgrad_reduce")))
+    gemm_us = sum(v["us_per_step"] for k, v in kernels.items() if k.startswith(("linear_", "tgemm_", "wgrad_reduce", "agent_front_")))
     gemm_flop = FLOP_PER_STEP - GRU_FWD_FLOP - GRU_FWD_FLOP / 3        # everything but the two recurrent kernels
     roofline_gemm = None
     if gemm_us:
         ach = gemm_flop / (gemm_us * 1e-6) / 1e12
-        roofline_gemm = {"kernel": "linear_{fwd,dgrad,wgrad}_kernel (tcgen05 kind::tf32, 3xTF32)", "bound": "tensor",
+        roofline_gemm = {"kernel": "agent_front_kernel + linear_{fwd,dgrad,wgrad}_kernel (tcgen05 kind::tf32, 3xTF32)", "bound": "tensor",
                          "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
                          "traffic": NCU_TRAFFIC.get("linear_fwd_kernel"), "us_per_step": gemm_us,
                          "note": "algorithmic fp32 FLOPs of all dense layers / summed launch time (launches on parallel streams "
                                  "overlap, so the sum overstates the wall time); peak = measured sustained bf16.  Measured "
-                                 "(tools/micro/mma_rate.cu): one tcgen05.mma kind::tf32 takes ~187 cycles whatever its N, i.e. "
-                                 "808 TFLOP/s at N = 256 and 202 at the N = 64 of these layers, and 3xTF32 issues every product "
-                                 "three times: 67 TFLOP/s is the ceiling of this scheme at these shapes"}
+                                 "(tools/micro/mma_rate2.cu): one tcgen05.mma kind::tf32 (K = 8, M = 128) takes max(44.5, N/2) "
+                                 "cycles, i.e. 1.19 PFLOP/s at N >= 128 and 0.79 at the N = 64 of these layers, and 3xTF32 issues "
+                                 "every product three times; the layers are bound by what surrounds the MMAs (operand staging, "
+                                 "hand-overs, epilogues), not by the tensor pipe (DESIGN.md section 4)"}
     step_tflops = FLOP_PER_STEP / (ms_dev * 1e-3) / 1e12
 
     cpu, gpu_base = None, None
@@ -625,8 +626,10 @@ def run_ours(opt):
                 "h2d_bytes_per_step": int(ep_bytes), "d2h_bytes_per_step": 8,
                 "how": "the reference's training loop (runner.py:92-97, n_episodes = 1, train_steps = 1) through the drop-in "
                        "classes: buffer.store_episode(one new float64 HOST episode, pinned) -> buffer.sample(32) -> "
-                       "learner.train(batch) -> loss as a Python float; the episode's H2D copy, its cast into the fp32 ring, "
-                       "the gather of the sampled rows and the loss read-back are all inside the timed region",
+                       "learner.train(batch) -> loss as a Python float; the episode crosses PCIe inside the timed region (its "
+                       "arrays are page-locked, so the float64 -> fp32 cast kernel reads them in place and store_episode returns "
+                       "when it has; pageable arrays take a packed staging copy instead), and so do the gather of the sampled "
+                       "rows and the loss read-back",
                 "host_dict_variant": {"value": B * world / (ms_e2e_host * 1e-3), "ms_per_step": ms_e2e_host,
                                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
                                       "how": "QLearner.train(whole float64 host batch) every step, next batch prefetched: "

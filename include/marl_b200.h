@@ -407,6 +407,9 @@ int marl_linear_wgrad(const float* dy, int lddy, const float* x, int ldx, float*
 /* FP32 FMA throughput probe (the compute-roofline denominator bench.py reports against):
  * launches `blocks` x 256 threads x 8 independent FMA chains x `iters`; *flops_out = FLOPs issued. */
 int marl_fma_probe(float* scratch_device, int iters, int blocks, double* flops_out_host, void* stream);
+/* Fused input layers of the agent unroll (csrc/front.cu: fc1 -> ReLU -> W_ih of every stream of marl_agent_unroll_fwd in one
+ * persistent launch; default on, MARL_B200_FRONT=0 turns it off).  Returns the previous setting.  No reference counterpart. */
+int marl_front_enable(int on);
 /* 1 when [p, p + bytes) is page-locked host memory the current device can read in place (the host pointer is the device
  * pointer), else 0.  No reference counterpart: lets ReplayBuffer.store_episode (common/replaybuffer.py:30-61) hand pinned
  * episode arrays to marl_ingest_f64 without a staging copy. */

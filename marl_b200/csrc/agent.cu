@@ -773,6 +773,7 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
     if ((rc = linear_wgrad(w_hh, fb.lane(1)))) return rc;
     if (a->h0 && (rc = linear_wgrad(w_h0, fb.lane(1)))) return rc;
     if ((rc = linear_wgrad(w_ih, fb.lane(2)))) return rc;
+    // (a launch priority on the dependent pair dx -> dW1, the tail's critical path, was measured: no change)
     if ((rc = linear_dgrad(g_dx, st))) return rc;
     if ((rc = linear_wgrad(w_fc1, st))) return rc;
     fb.join();

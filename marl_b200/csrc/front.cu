@@ -490,10 +490,10 @@ __global__ void __launch_bounds__(kFrontThreads, 1) agent_front_kernel(const Fro
     if (warp == kWarpMma) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kFrontTmemCols));
 }
 
+static int g_front_on = -1;
 bool front_enabled() {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("MARL_B200_FRONT"); on = (e && e[0] == '0') ? 0 : 1; }
-    return on == 1;
+    if (g_front_on < 0) { const char* e = getenv("MARL_B200_FRONT"); g_front_on = (e && e[0] == '0') ? 0 : 1; }
+    return g_front_on == 1;
 }
 
 namespace {
@@ -593,3 +593,10 @@ int front_launch(const FrontArgs& a, int n_streams, int prio, cudaStream_t st) {
 }
 
 }  // namespace marl
+
+// on = 0: the input layers run as separate launches (linear.cu) -- the A/B switch behind MARL_B200_FRONT; returns the previous setting
+extern "C" int marl_front_enable(int on) {
+    const int prev = marl::front_enabled() ? 1 : 0;
+    marl::g_front_on = on ? 1 : 0;
+    return prev;
+}

@@ -12,6 +12,7 @@
 #include "../../include/marl_b200.h"
 #include "profile.h"
 #include "select.cuh"
+#include "tgemm.h"
 
 namespace marl {
 
@@ -38,7 +39,17 @@ struct QmixMixArgs {
     const float* fc2_w; float* dhext;      // agent head W2 [A,H] and dL/dh through it [M,N,H], or null
     SelectArgs sel;                        // fused action-value selection (TD mode): q / q_t are then OUTPUTS
     float* g_wb2; float* g_bb2; float* scalars;
+    long long* trace;                      // debug (marl_tgemm_trace, -DMARL_MIX_TRACE builds): globaltimer stamps of one warp
 };
+#ifdef MARL_MIX_TRACE
+#define MIX_STAMP(tag)                                                                                    \
+    do {                                                                                                  \
+        if (trace && tn < 60) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));      \
+                                trace[2 * tn] = (tag); trace[2 * tn + 1] = t_; ++tn; trace[510] = tn; }   \
+    } while (0)
+#else
+#define MIX_STAMP(tag) do { } while (0)
+#endif
 
 // forward of one sample for one lane; returns q_tot (all lanes) and the lane's intermediates
 __device__ __forceinline__ float qmix_forward_lane(const float* __restrict__ y, const float* __restrict__ q, int N,
@@ -56,7 +67,13 @@ __device__ __forceinline__ float qmix_forward_lane(const float* __restrict__ y, 
 }
 
 __global__ void __launch_bounds__(kQmixWarps * 32, kQmixCtasPerSm) qmix_mix_kernel(QmixMixArgs a) {
+#ifdef MARL_MIX_TRACE
+    long long* trace = (a.trace && (blockIdx.x == 0 || blockIdx.x == 300) && threadIdx.x == 0) ? a.trace + (blockIdx.x ? 512 : 0) : nullptr;
+    int tn = 0;
+#endif
+    MIX_STAMP(0);
     pdl_enter();
+    MIX_STAMP(1);
     __shared__ float sdq[kQmixWarps][kQmixMaxAgents];
     __shared__ float sred[kQmixWarps][E + 1];
     __shared__ float ssel[kQmixWarps][2][kQmixMaxAgents];
@@ -68,6 +85,7 @@ __global__ void __launch_bounds__(kQmixWarps * 32, kQmixCtasPerSm) qmix_mix_kern
         heads = h;
         __syncthreads();
     }
+    MIX_STAMP(2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = a.N, C = N * E + 3 * E;
     const float wb2e = a.wb2[lane], bb2 = a.bb2[0];
@@ -82,9 +100,11 @@ __global__ void __launch_bounds__(kQmixWarps * 32, kQmixCtasPerSm) qmix_mix_kern
             warp_select(a.sel, m, N, a.A, lane, ssel_dyn + warp * select_warp_floats(N, a.A, a.sel.heads), ssel[warp][0], ssel[warp][1], heads);
             q = ssel[warp][0]; qt = ssel[warp][1];
         }
+        MIX_STAMP(3);
         float pre, hid, w2raw, hb2;
         const float tot = qmix_forward_lane(y, q, N, wb2e, bb2, lane, pre, hid, w2raw, hb2);
         if (lane == 0 && a.q_tot) a.q_tot[m] = tot;
+        MIX_STAMP(4);
         if (a.mode == QMIX_FWD) continue;
         float G;
         if (a.mode == QMIX_TD) {
@@ -100,6 +120,7 @@ __global__ void __launch_bounds__(kQmixWarps * 32, kQmixCtasPerSm) qmix_mix_kern
         } else {
             G = a.dq_tot_in[m];
         }
+        MIX_STAMP(5);
         // backward
         float* __restrict__ dy = a.dhy + (long long)m * C;
         const float dpre = G * fabsf(w2raw) * (pre > 0.0f ? 1.0f : (hid + 1.0f));   // elu'(x) = exp(x) for x <= 0
@@ -118,6 +139,7 @@ __global__ void __launch_bounds__(kQmixWarps * 32, kQmixCtasPerSm) qmix_mix_kern
             if (lane == 0) sdq[warp][n] = dqn;
         }
         __syncwarp();
+        MIX_STAMP(6);
         if (a.dq_small)
             for (int n = lane; n < N; n += 32) a.dq_small[(long long)m * N + n] = sdq[warp][n];
         if (a.dq_dense) {
@@ -129,6 +151,7 @@ __global__ void __launch_bounds__(kQmixWarps * 32, kQmixCtasPerSm) qmix_mix_kern
         }
         if (a.dhext) warp_dhext(a.fc2_w, a.u, m, N, lane, sdq[warp], a.dhext);
         __syncwarp();
+        MIX_STAMP(7);
     }
     if (a.mode == QMIX_FWD) return;
     // block reduction of the hyper_b2.2 gradient and the loss scalars
@@ -151,6 +174,7 @@ __global__ void __launch_bounds__(kQmixWarps * 32, kQmixCtasPerSm) qmix_mix_kern
             atomicAdd(a.scalars, v); atomicAdd(a.scalars + 1, b);
         }
     }
+    MIX_STAMP(8);
 }
 
 static int hyper_fwd(int M, int N, int S, const marl_qmix_params* p, const float* s, float* hy, cudaStream_t st) {
@@ -300,6 +324,7 @@ extern "C" int marl_qmix_td_fwd_bwd(const marl_dims* d, const marl_qmix_params* 
     a.fc2_w = fc2_w; a.dhext = dhext;
     if (sel) a.sel = select_args(sel, u, q_chosen, q_tc);
     a.g_wb2 = g->wb2; a.g_bb2 = g->bb2; a.scalars = scalars;
+    a.trace = trace_buffer();
     const size_t dyn = sel ? select_smem(kQmixWarps, d->N, d->A, sel->hidden_evals != nullptr) : 0;
     if (dyn > kSelectSmemMax) return MARL_EINVAL;
     if (dyn > 40 * 1024) {

@@ -99,3 +99,70 @@ def test_learner_step_on_tma_gemm_path_matches_oracle(alg):
                     assert PU.rel_err(mine.grad, info["clipped_grads"][f"{g}.{k}"]) < 1e-5, (g, k)
     finally:
         L.load().marl_tgemm_enable(prev)
+
+
+# ------------------------------------------------------------------------------------------ fused input layers (csrc/front.cu)
+@pytest.mark.parametrize("shape", [
+    (32, 120, 5, 11, 80),      # BASELINE config 2: 19 200 rows, I = 96
+    (3, 7, 2, 3, 4),           # tiny: one ragged tile, I = 9 (one k-tile, all of it composed or clipped)
+    (5, 33, 3, 5, 12),         # rows not a multiple of 128, I = 20
+    (2, 9, 8, 14, 128),        # 3s5z width: I = 150 (ten k-tiles, the last one partial)
+    (4, 6, 2, 6, 248),         # I = 256: the widest the fused kernel takes
+])
+def test_fused_input_layers_match_the_separate_launches_and_float64(shape):
+    """marl_agent_unroll_fwd with the fused front kernel (TMA in, A operands in tensor memory, TMA out) against the same entry
+    point with the layers launched one by one (marl_front_enable(0)) and against float64: x = relu(fc1([obs | last action | id])),
+    gi = W_ih x + b_ih (network/q_network.py:17-19), then the hidden states and q both paths feed."""
+    import ctypes as C
+    from marl_b200 import _lib as L
+    from marl_b200.network.q_network import AGENT_FLAT_ORDER, agent_param_struct
+    B, T, N, A, O = shape
+    I, H, rows = O + A + N, 64, B * T * N
+    torch.manual_seed(B * 1000 + T)
+    dev = "cuda"
+    obs = torch.randn(B, T, N, O, device=dev)
+    onehot = torch.zeros(B, T, N, A, device=dev)
+    onehot.scatter_(3, torch.randint(0, A, (B, T, N, 1), device=dev), 1.0)
+    sizes = {"fc1_w": (H, I), "fc1_b": (H,), "w_ih": (3 * H, H), "w_hh": (3 * H, H), "b_ih": (3 * H,), "b_hh": (3 * H,),
+             "fc2_w": (A, H), "fc2_b": (A,)}
+    flat = torch.empty(sum(int(np.prod(v)) + 3 & ~3 for v in sizes.values()), device=dev)     # 16-byte aligned parameters
+    params, off = {}, 0
+    for k in L.AGENT_KEYS:
+        n = int(np.prod(sizes[k]))
+        params[k] = flat[off:off + n].view(sizes[k]).normal_(0, 0.3)
+        off += n + 3 & ~3
+    named = {name: params[k].data_ptr() for k, name in zip(L.AGENT_KEYS, AGENT_FLAT_ORDER)}
+
+    def run(fused):
+        prev = L.load().marl_front_enable(1 if fused else 0)
+        try:
+            out = {k: torch.full(s, float("nan"), device=dev) for k, s in
+                   (("q", (rows, A)), ("hidden", (rows, H)), ("x", (rows, H)), ("gi", (rows, 3 * H)), ("gates", (rows, 4 * H)))}
+            st = L.UnrollStream()
+            st.obs, st.onehot, st.shift_onehot, st.full_input, st.h0_from, st.h0 = obs.data_ptr(), onehot.data_ptr(), 1, 0, -1, None
+            st.params = agent_param_struct(named)
+            st.q, st.hidden, st.h_last = out["q"].data_ptr(), out["hidden"].data_ptr(), None
+            st.x, st.gi, st.gates = out["x"].data_ptr(), out["gi"].data_ptr(), out["gates"].data_ptr()
+            d = L.Dims(B, T, N, A, O, 0)
+            L.profile(True)
+            L.call("marl_agent_unroll_fwd", C.byref(d), C.byref(st), 1, L.stream_ptr())
+            launched = L.profile_collect()
+            L.profile(False)
+            assert ("agent_front_kernel" in launched) == fused, launched       # the path under test really ran
+            return out
+        finally:
+            L.load().marl_front_enable(prev)
+
+    fused, plain = run(True), run(False)
+    last = torch.cat([torch.zeros(B, 1, N, A, device=dev), onehot[:, :-1]], 1)                  # share_params.py:92-101
+    ident = torch.eye(N, device=dev).expand(B, T, N, N)
+    inp = torch.cat([obs, last, ident], 3).reshape(rows, I).double()
+    x64 = torch.relu(inp @ params["fc1_w"].double().t() + params["fc1_b"].double())
+    gi64 = x64 @ params["w_ih"].double().t() + params["b_ih"].double()
+    for name, ref in (("x", x64), ("gi", gi64)):
+        for tag, got in (("fused", fused[name]), ("separate", plain[name])):
+            err = float((got.double() - ref).abs().max() / ref.abs().max())
+            assert err < 3e-6, (name, tag, err)
+    for name in ("hidden", "q"):
+        err = float((fused[name] - plain[name]).abs().max() / plain[name].abs().max())
+        assert err < 3e-6, (name, err)
