@@ -703,6 +703,11 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
         g.dx = a->dhext; g.lddx = MARL_H; g.M = rows_total; g.N = d->A; g.K = MARL_H; g.batch = 1;
         if ((rc = linear_dgrad(g, st))) return rc;
     }
+    // W_ih transposed for the data gradient behind the recurrence (both of its operands then stage with 128-bit stores):
+    // one small launch on a side lane, beside the BPTT kernel
+    ForkJoin ft(st, 2);
+    float* w_ih_t = rows_total >= 4096 ? tgemm_scratch((size_t)MARL_H * transposed_pitch(MARL_G) * sizeof(float)) : nullptr;
+    if (w_ih_t && (rc = transpose_weights(a->params.w_ih, MARL_H, 0, MARL_G, MARL_H, w_ih_t, ft.lane(1)))) return rc;
     GruBwdArgs ga{a->gates, a->hidden, a->dq ? a->dhext : nullptr, a->dhidden, a->params.w_hh, a->h0, a->dgi, a->dgh, a->dh0,
                   d->B, d->L, d->N, a->ep_len};
     const int rows = d->B * d->N;
@@ -746,10 +751,12 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
     g_dx.dy = a->dgi; g_dx.lddy = MARL_G; g_dx.w = a->params.w_ih; g_dx.ldw = MARL_H; g_dx.w_col0 = 0;
     g_dx.dx = a->dx; g_dx.lddx = MARL_H; g_dx.relu_src = a->x; g_dx.ldrs = MARL_H;
     g_dx.M = rows_total; g_dx.N = MARL_G; g_dx.K = MARL_H; g_dx.batch = 1;
+    g_dx.wt = w_ih_t; g_dx.ldwt = transposed_pitch(MARL_G);
     // dW1 += dx^T . [obs | last_action | agent_id] ; db1
     w_fc1.dy = a->dx; w_fc1.lddy = MARL_H; w_fc1.in = agent_input(d, a->obs, a->onehot, a->shift_onehot, a->full_input);
     w_fc1.dw = a->grads.fc1_w; w_fc1.ldw = I; w_fc1.db = a->grads.fc1_b; w_fc1.M = rows_total; w_fc1.N = MARL_H; w_fc1.batch = 1;
 
+    ft.join();                           // (the transposed W_ih; long done -- the BPTT kernel ran meanwhile)
     if (tgemm_enabled()) {
         // TMA path (csrc/tgemm.cu): the data gradient and the three weight gradients that only need the BPTT's outputs are
         // ONE grouped launch, the fc1 weight gradient (needs dx) a second, and one deterministic reduce folds every

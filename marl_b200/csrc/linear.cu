@@ -292,9 +292,14 @@ __global__ void __launch_bounds__(UTH) linear_dgrad_kernel(LinearDgrad a) {
     pdl_wait();
     const int z = blockIdx.z, m0 = blockIdx.x * UM, k0 = blockIdx.y * UN;
     const OpMat A{a.dy + (long long)z * a.dy_bs, a.lddy, a.M, a.N, VEC_A};               // rows m, reduction n (contiguous)
-    const OpMat B{a.w + (long long)z * a.w_bs + a.w_col0, a.ldw, a.N, a.K, VEC_B};       // rows n (reduction), cols k (contiguous)
     float unused[2][4];
-    umma_loop<true, false, false>(c, A, B, m0, k0, 0, a.N, unused);
+    if (a.wt) {
+        const OpMat Bt{a.wt, a.ldwt, a.K, a.N, true};                                    // rows k, reduction n (contiguous): pre-transposed
+        umma_loop<true, true, false>(c, A, Bt, m0, k0, 0, a.N, unused);
+    } else {
+        const OpMat B{a.w + (long long)z * a.w_bs + a.w_col0, a.ldw, a.N, a.K, VEC_B};   // rows n (reduction), cols k (contiguous)
+        umma_loop<true, false, false>(c, A, B, m0, k0, 0, a.N, unused);
+    }
     pdl_trigger();                       // main loop done: the next kernel's CTAs may take the freed slots
     float* dx = a.dx + (long long)z * a.dx_bs;
     const float* rs = a.relu_src ? a.relu_src + (long long)z * a.rs_bs : nullptr;
@@ -436,6 +441,7 @@ __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(LinearWgrad a, int s
     }
 }
 
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static int g_deterministic = -1;
 bool deterministic_wgrad() {
     if (g_deterministic < 0) { const char* e = getenv("MARL_B200_DETERMINISTIC"); g_deterministic = (e && e[0] == '1') ? 1 : 0; }
@@ -443,7 +449,6 @@ bool deterministic_wgrad() {
 }
 void set_deterministic_wgrad(int on) { g_deterministic = on ? 1 : 0; }
 
-static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // 128-bit loads are legal when the base is 16-byte aligned and row pitch / region start are multiples of 4 floats
@@ -481,9 +486,34 @@ int linear_fwd(const LinearFwd& a, cudaStream_t st) {
     return MARL_OK;
 }
 
+// 32 x 32 tiles through shared memory: coalesced on both sides
+__global__ void __launch_bounds__(256) transpose_weights_kernel(const float* __restrict__ w, int ldw, int col0, int N, int K, float* __restrict__ wt, int ldwt) {
+    pdl_enter();
+    __shared__ float tile[32][33];
+    const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int n = n0 + r, k = k0 + tx;
+        tile[r][tx] = (n < N && k < K) ? __ldg(w + (long long)n * ldw + col0 + k) : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, n = n0 + tx;
+        if (k < K && n < ldwt) wt[(long long)k * ldwt + n] = n < N ? tile[tx][r] : 0.f;
+    }
+}
+
+int transpose_weights(const float* w, int ldw, int col0, int N, int K, float* wt, cudaStream_t st) {
+    if (!w || !wt || N <= 0 || K <= 0) return MARL_EINVAL;
+    ProfScope ps_("transpose_weights_kernel", st);
+    launch_pdl_prio(linear_prio(), transpose_weights_kernel, dim3(cdiv(N, 32), cdiv(K, 32)), dim3(256), 0, st, w, ldw, col0, N, K, wt, transposed_pitch(N));
+    MARL_LAUNCH_CHECK();
+    return MARL_OK;
+}
+
 int linear_dgrad(const LinearDgrad& a, cudaStream_t st) {
     if (a.M <= 0 || a.K <= 0 || a.batch <= 0) return MARL_OK;
-    { TGBuilder tg; if (tg.add_dgrad(a)) return tg.launch(st); }
+    if (a.wt && a.batch != 1) return MARL_EINVAL;
+    if (!a.wt) { TGBuilder tg; if (tg.add_dgrad(a)) return tg.launch(st); }
     dim3 grid(cdiv(a.M, UM), cdiv(a.K, UN), a.batch);
     const bool va = vec_ok_mat(a.dy, a.lddy, a.dy_bs), vb = vec_ok_mat(a.w, a.ldw, a.w_bs, a.w_col0);
     { if (prof_enabled()) prof_note(a.M, a.K, a.N); ProfScope ps_("linear_dgrad_kernel", st); MARL_DISPATCH2(linear_dgrad_kernel, va, vb, grid, st, a); }

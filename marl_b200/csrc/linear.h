@@ -26,6 +26,9 @@ struct LinearDgrad {
     int M, N, K;
     int accumulate;
     int batch;
+    // optional: the weight slice already transposed, wt[k, n] = w[n, w_col0 + k] (row pitch ldwt) -- both operands are then
+    // contiguous along the reduction and take the 128-bit staging path (transpose_weights); batch must be 1
+    const float* wt; int ldwt;
 };
 
 // dw[N, 0:K] += dy[M,N]^T . in[M,K] ;  db[N] += colsum(dy)   (atomic split over M)
@@ -43,6 +46,9 @@ struct LinearWgrad {
 bool deterministic_wgrad();
 void set_deterministic_wgrad(int on);
 
+// wt[k, n] = w[n, col0 + k] for n < N, k < K (one small launch); wt pitch = N rounded up to 4 floats
+int transpose_weights(const float* w, int ldw, int col0, int N, int K, float* wt, cudaStream_t st);
+inline int transposed_pitch(int N) { return (N + 3) & ~3; }
 int linear_fwd(const LinearFwd& a, cudaStream_t st);
 int linear_dgrad(const LinearDgrad& a, cudaStream_t st);
 int linear_wgrad(const LinearWgrad& a, cudaStream_t st);
