@@ -114,6 +114,9 @@ typedef struct marl_unroll_stream {
     float* x;                /* workspace/out [B,L,N,H]: relu(fc1) (needed by the backward; the fused input-layer kernel only fills it when `gates` is given) */
     float* gi;               /* workspace [B,L,N,3H] */
     float* gates;            /* out [B,L,N,4H] (r, z, n, W_hn h + b_hn) for the backward, or NULL */
+    float* w_ih_t;           /* out [H, 3H] or NULL: params.w_ih transposed (written by the fused input-layer kernel on its way, by one
+                                small launch otherwise).  Hand it to marl_unroll_bwd.w_ih_t of the SAME step: the data gradient
+                                behind the recurrence then reads both operands along the reduction */
     const int* ep_len;       /* device [B] (marl_episode_lengths) or NULL.  Non-NULL: this stream's recurrence stops each row at
                                 its episode's length -- the padded steps behind it (q_learner.py:49-66 keeps them up to the
                                 batch maximum) are not computed; `hidden` / `q` keep whatever they held there (finite: the
@@ -143,6 +146,8 @@ typedef struct marl_unroll_bwd {
     float* dh0;              /* out [B*N,H] dL/dh0, or NULL */
     marl_agent_grads grads;
     int dhext_ready;         /* != 0: dhext already holds dq . fc2_w (marl_qmix_td_fwd_bwd wrote it); skip that product */
+    const float* w_ih_t;     /* [H, 3H] = params.w_ih transposed as marl_unroll_stream.w_ih_t produced it in this step's forward,
+                                or NULL (the data gradient then transposes W_ih while staging it) */
     const int* ep_len;       /* device [B] or NULL.  Non-NULL: the backward chain of a row starts at its episode's last real
                                 step; dgi / dgh of the padded steps behind it are written as zeros (what the full chain
                                 computes there: every upstream gradient is masked to zero) */

@@ -210,7 +210,7 @@ class QLearner:
             hidden=[th.zeros(B, Lq, N, H, dtype=th.float32, device=dev) for _ in range(3)],
             q=[th.zeros(B, Lq, N, A, dtype=th.float32, device=dev) for _ in range(3)],
             ep_len=th.ones(B, dtype=th.int32, device=dev),
-            h_last=[f(B * N, H) for _ in range(3)], gates=f(rows, 4 * H),
+            h_last=[f(B * N, H) for _ in range(3)], gates=f(rows, 4 * H), w_ih_t=f(H, 3 * H),
             q_chosen=f(B, Lq, N), q_tc=f(B, Lq, N), a_star=th.empty(B, Lq, N, dtype=th.int64, device=dev),
             q_tot=f(B, Lq, 1), q_tot_t=f(B, Lq, 1), dq=f(B, Lq, N, A),
             dhext=f(rows, H), dgi=f(rows, 3 * H), dgh=f(rows, 3 * H), dx=f(rows, H),
@@ -462,6 +462,7 @@ class QLearner:
             s.q = None if fused_heads else ws["q"][i].data_ptr()
             s.hidden, s.h_last = ws["hidden"][i].data_ptr(), ws["h_last"][i].data_ptr()
             s.x, s.gi, s.gates = ws["x"][i].data_ptr(), ws["gi"][i].data_ptr(), gates
+            s.w_ih_t = ws["w_ih_t"].data_ptr() if gates else None       # W_ih^T for the backward's data gradient (same step)
 
         fill(0, bt["o"], 1, pe, -1, ws["gates"].data_ptr())          # eval net on o          (q_learner.py:96-97)
         fill(1, bt["o_next"], 0, pt, -1, None)                        # target net on o_next   (:103-104)
@@ -543,6 +544,7 @@ class QLearner:
         bw.dhext, bw.dgi, bw.dgh, bw.dx = (ws[k].data_ptr() for k in ("dhext", "dgi", "dgh", "dx"))
         bw.dh0 = None
         bw.dhext_ready = int(dhext_fused)
+        bw.w_ih_t = ws["w_ih_t"].data_ptr()
         bw.ep_len = ep_len
         bw.grads = agent_param_struct({n: self._flat.ptr("agent." + n, self._flat.grad) for n in AGENT_FLAT_ORDER},
                                       L.AgentGrads)

@@ -83,6 +83,7 @@ class QTRANLearner(QLearner):
             s.h0_from, s.h0, s.params = -1, None, params
             s.q, s.hidden, s.h_last = ws["q"][i].data_ptr(), ws["hidden"][i].data_ptr(), ws["h_last"][i].data_ptr()
             s.x, s.gi, s.gates = ws["x"][i].data_ptr(), ws["gi"][i].data_ptr(), gates
+            s.w_ih_t = ws["w_ih_t"].data_ptr() if gates else None       # W_ih^T for the backward's data gradient (same step)
         L.call("marl_agent_unroll_fwd", C.byref(d), arr, 2, sp)
         L.call("marl_qtran_select", C.byref(d), ws["q"][0].data_ptr(), ws["q"][1].data_ptr(), bt["avail_u"].data_ptr(),
                bt["avail_u_next"].data_ptr(), bt["u"].data_ptr(), ws["oh_e"].data_ptr(), ws["oh_t"].data_ptr(),
@@ -121,6 +122,7 @@ class QTRANLearner(QLearner):
         bw.h0, bw.dq, bw.dhidden = None, ws["dq"].data_ptr(), ws["dhid"].data_ptr()
         bw.dhext, bw.dgi, bw.dgh, bw.dx = (ws[k].data_ptr() for k in ("dhext", "dgi", "dgh", "dx"))
         bw.dh0 = None
+        bw.w_ih_t = ws["w_ih_t"].data_ptr()
         bw.grads = agent_param_struct({n: fl.ptr("agent." + n, fl.grad) for n in AGENT_FLAT_ORDER}, L.AgentGrads)
         L.call("marl_agent_unroll_bwd", C.byref(d), C.byref(bw), sp)
         return 2 + 7 + 1 + 4 * 6 + 1 + 2 * 11 + 7

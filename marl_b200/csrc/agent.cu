@@ -594,12 +594,20 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
             fa.s[i].store_x = s[i].gates != nullptr;
             fa.set[i].w1 = s[i].params.fc1_w; fa.set[i].b1 = s[i].params.fc1_b;
             fa.set[i].w_ih = s[i].params.w_ih; fa.set[i].b_ih = s[i].params.b_ih;
+            fa.set[i].w_ih_t = s[i].w_ih_t;
         }
         if (front_plan(fa, n_streams)) {
             const int rc = front_launch(fa, n_streams, kGruPrio, st);
             if (rc) return rc;
             grouped = true;
         }
+    }
+    if (!grouped) {
+        for (int i = 0; i < n_streams; ++i)
+            if (s[i].w_ih_t) {
+                const int rc = transpose_weights(s[i].params.w_ih, MARL_H, 0, MARL_G, MARL_H, s[i].w_ih_t, st);
+                if (rc) return rc;
+            }
     }
     if (!grouped && tgemm_enabled()) {
         // TMA path: the streams of one layer are ONE grouped launch of persistent CTAs (csrc/tgemm.cu): 2 launches
@@ -703,11 +711,6 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
         g.dx = a->dhext; g.lddx = MARL_H; g.M = rows_total; g.N = d->A; g.K = MARL_H; g.batch = 1;
         if ((rc = linear_dgrad(g, st))) return rc;
     }
-    // W_ih transposed for the data gradient behind the recurrence (both of its operands then stage with 128-bit stores):
-    // one small launch on a side lane, beside the BPTT kernel
-    ForkJoin ft(st, 2);
-    float* w_ih_t = rows_total >= 4096 ? tgemm_scratch((size_t)MARL_H * transposed_pitch(MARL_G) * sizeof(float)) : nullptr;
-    if (w_ih_t && (rc = transpose_weights(a->params.w_ih, MARL_H, 0, MARL_G, MARL_H, w_ih_t, ft.lane(1)))) return rc;
     GruBwdArgs ga{a->gates, a->hidden, a->dq ? a->dhext : nullptr, a->dhidden, a->params.w_hh, a->h0, a->dgi, a->dgh, a->dh0,
                   d->B, d->L, d->N, a->ep_len};
     const int rows = d->B * d->N;
@@ -751,12 +754,11 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
     g_dx.dy = a->dgi; g_dx.lddy = MARL_G; g_dx.w = a->params.w_ih; g_dx.ldw = MARL_H; g_dx.w_col0 = 0;
     g_dx.dx = a->dx; g_dx.lddx = MARL_H; g_dx.relu_src = a->x; g_dx.ldrs = MARL_H;
     g_dx.M = rows_total; g_dx.N = MARL_G; g_dx.K = MARL_H; g_dx.batch = 1;
-    g_dx.wt = w_ih_t; g_dx.ldwt = transposed_pitch(MARL_G);
+    g_dx.wt = a->w_ih_t; g_dx.ldwt = MARL_G;      // W_ih transposed by this step's forward pass (both operands then stage with 128-bit stores)
     // dW1 += dx^T . [obs | last_action | agent_id] ; db1
     w_fc1.dy = a->dx; w_fc1.lddy = MARL_H; w_fc1.in = agent_input(d, a->obs, a->onehot, a->shift_onehot, a->full_input);
     w_fc1.dw = a->grads.fc1_w; w_fc1.ldw = I; w_fc1.db = a->grads.fc1_b; w_fc1.M = rows_total; w_fc1.N = MARL_H; w_fc1.batch = 1;
 
-    ft.join();                           // (the transposed W_ih; long done -- the BPTT kernel ran meanwhile)
     if (tgemm_enabled()) {
         // TMA path (csrc/tgemm.cu): the data gradient and the three weight gradients that only need the BPTT's outputs are
         // ONE grouped launch, the fc1 weight gradient (needs dx) a second, and one deterministic reduce folds every

@@ -210,6 +210,15 @@ __global__ void __launch_bounds__(kFrontThreads, 1) agent_front_kernel(const Fro
             *reinterpret_cast<float4*>(sm.wih_hi + c * FW_PITCH + n * 4) = h;
             *reinterpret_cast<float4*>(sm.wih_lo + c * FW_PITCH + n * 4) = l;
         }
+        if (sm.set.w_ih_t) {
+            // W_ih^T for the data gradient of this step's backward pass: each CTA of the set writes its slice
+            const int total_e = FN2 * MARL_H, per = (total_e + n_ctas - 1) / n_ctas;
+            const int e0 = cta * per, e1 = min(total_e, e0 + per);
+            for (int e = e0 + tid; e < e1; e += kWarpTma * 32) {
+                const int k = e / FN2, n = e - k * FN2;                   // consecutive threads: consecutive n of one row of W_ih^T
+                sm.set.w_ih_t[e] = __ldg(w + (long long)n * MARL_H + k);
+            }
+        }
         if (tid < FN1) sm.b1[tid] = sm.set.b1 ? __ldg(sm.set.b1 + tid) : 0.f;
         if (tid < FN2) sm.bih[tid] = sm.set.b_ih ? __ldg(sm.set.b_ih + tid) : 0.f;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -553,6 +562,7 @@ bool front_plan(FrontArgs& a, int n_streams) {
         for (int k = 0; k < ns; ++k)
             if (sets[k].w1 == a.set[i].w1 && sets[k].b1 == a.set[i].b1 && sets[k].w_ih == a.set[i].w_ih && sets[k].b_ih == a.set[i].b_ih) hit = k;
         if (hit < 0) { sets[ns] = a.set[i]; sets[ns].n_streams = 0; hit = ns++; }
+        else if (a.set[i].w_ih_t) sets[hit].w_ih_t = a.set[i].w_ih_t;
         sets[hit].stream[sets[hit].n_streams++] = i;
     }
     a.tiles_per_stream = (a.rows + FM - 1) / FM;

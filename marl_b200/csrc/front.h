@@ -20,6 +20,7 @@ struct FrontSet {
     int vec_w1;
     int n_streams; int stream[kFrontMaxStreams];
     int cta0, n_ctas;       // CTAs [cta0, cta0 + n_ctas) of the grid work on this set
+    float* w_ih_t;          // [64, 192] or null: W_ih transposed for the backward's data gradient, written by this set's CTAs
 };
 
 struct FrontArgs {

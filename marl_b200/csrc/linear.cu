@@ -27,12 +27,28 @@ constexpr int kKChunks = UK / 4;                       // 16-byte k-chunks per k
 // keeps both the 128-bit stores of k-contiguous operands and the scalar stores of transposed operands
 // (almost) free of bank conflicts.
 constexpr int A_PITCH = UM * 4 + 8, B_PITCH = UN * 4 + 8;
+// MN-major layout for operands whose memory is contiguous along the OUTPUT index (both operands of a weight gradient, W of a
+// data gradient).  For 32-bit operands the tensor core knows exactly one: SWIZZLE_128B_BASE32B (cutlass sm100_common.inl: "for
+// mn-major tf32 operands, SW128_32B is the only available smem layout"; validated with TMA-written tiles in tools/micro/
+// tma_probe.cu).  A "box" is 32 output indices wide: per reduction index k one 128-byte row of 32 consecutive output elements;
+// atoms of 4 k-rows (512 B, SBO), two atoms per K = 8 step, boxes LBO apart; inside a row the four 32-byte chunks are XORed with
+// (k & 3).  A quad of 4 consecutive output indices at one k is ONE 128-bit store -- no transposing scalar stores.
+#ifndef MARL_MN_MAJOR
+#define MARL_MN_MAJOR 1
+#endif
+constexpr bool kMnMajor = MARL_MN_MAJOR != 0;
+constexpr int MN_BOX_BYTES = UK * 128;                                // one box of a k-tile: UK rows x 128 B
+// >= the K-major (8320 / 4224 B) and MN-major (8192 / 4096 B) tiles, multiples of 512 B (the swizzle atom); two stages + alignment
+// slack stay under 56 KB so that four CTAs share an SM (at 57 KB -- three CTAs -- the step was 20 us slower)
+constexpr int kAFloats = kMnMajor ? 8704 / 4 : kKChunks * A_PITCH, kBFloats = kMnMajor ? 4608 / 4 : kKChunks * B_PITCH;
+static_assert(!kMnMajor || (kAFloats * 4 >= (UM / 32) * MN_BOX_BYTES && kBFloats * 4 >= (UN / 32) * MN_BOX_BYTES), "MN-major tile");
+static_assert(kAFloats >= kKChunks * A_PITCH && kBFloats >= kKChunks * B_PITCH, "K-major tile");
 
-struct alignas(128) UmmaStage {
-    float a_hi[kKChunks * A_PITCH];
-    float a_lo[kKChunks * A_PITCH];
-    float b_hi[kKChunks * B_PITCH];
-    float b_lo[kKChunks * B_PITCH];
+struct alignas(kMnMajor ? 1024 : 128) UmmaStage {
+    float a_hi[kAFloats];
+    float a_lo[kAFloats];
+    float b_hi[kBFloats];
+    float b_lo[kBFloats];
 };
 constexpr int kUmmaStages = 2;
 // k-tiles a producer thread keeps in flight in registers.  Measured 2 / 3 / 4 / 6 deep (gpurun_out/ab_fd.txt): no gain
@@ -49,15 +65,15 @@ constexpr int kAccMain = 3, kAccAll = kAccMain + 1, kTmemCols = 256;
 static_assert(kAccAll * UN <= kTmemCols, "TMEM allocation too small");
 // short reductions (<= 32 accumulator updates) keep one main accumulator: reading TMEM back costs ~0.25 us each
 __host__ __device__ __forceinline__ int acc_main_count(int nsteps) { return nsteps > 32 ? kAccMain : 1; }
-constexpr size_t kUmmaSmem = kUmmaStages * sizeof(UmmaStage) + 128;
+constexpr size_t kUmmaSmem = kUmmaStages * sizeof(UmmaStage) + (kMnMajor ? 1024 : 128);
 
 // 32-bit instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
 constexpr uint32_t kUmmaIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t idesc = kUmmaIdesc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kUmmaIdesc), "r"(accumulate) : "memory");
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -72,22 +88,31 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 template <bool RED, int ROWS, int NQ>
 struct QuadMap {
     int i[NQ], r[NQ];
-    __device__ __forceinline__ QuadMap() {
+    int off[NQ];             // where the quad lands in a stage array (floats), fixed for the whole loop
+    __device__ __forceinline__ QuadMap(int pitch = ROWS * 4 + 8) {
 #pragma unroll
         for (int l = 0; l < NQ; ++l) {
             const int q = threadIdx.x + l * UT;
-            if (RED) { i[l] = q >> 2; r[l] = (q & 3) * 4; } else { i[l] = (q >> 4) * 4; r[l] = q & 15; }
+            if (RED) { i[l] = q >> 2; r[l] = (q & 3) * 4; }
+            else if (kMnMajor) {      // a warp = 8 quads (one 128-byte box row) x 4 reduction indices: coalesced loads, conflict-free stores
+                const int u = q & 7, kr4 = (q >> 3) & 3, box = (q >> 5) % (ROWS / 32), kg = q / (ROWS);
+                i[l] = (box * 8 + u) * 4; r[l] = kg * 4 + kr4;
+            }
+            else { i[l] = (q >> 4) * 4; r[l] = q & 15; }
+            if (RED) off[l] = (r[l] >> 2) * pitch + i[l] * 4;
+            else if (kMnMajor) {
+                const int u = (i[l] >> 2) & 7, box = i[l] >> 5;        // 16-byte unit inside the box row, box
+                off[l] = (box * MN_BOX_BYTES + (r[l] >> 2) * 512 + (r[l] & 3) * 128 + ((((u >> 1) ^ (r[l] & 3)) << 5) | ((u & 1) << 4))) >> 2;
+            } else off[l] = (r[l] >> 2) * pitch + i[l] * 4 + (r[l] & 3);
         }
     }
-    static __device__ __forceinline__ void store(float* hi, float* lo, int pitch, int i, int r, const float4& v) {
+    static __device__ __forceinline__ void store(float* hi, float* lo, int off, const float4& v) {
         float4 h, l;
         tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
-        if (RED) {
-            const int off = (r >> 2) * pitch + i * 4;
+        if (RED || kMnMajor) {
             *reinterpret_cast<float4*>(hi + off) = h;
             *reinterpret_cast<float4*>(lo + off) = l;
         } else {
-            const int off = (r >> 2) * pitch + i * 4 + (r & 3);
             hi[off] = h.x; hi[off + 4] = h.y; hi[off + 8] = h.z; hi[off + 12] = h.w;
             lo[off] = l.x; lo[off + 4] = l.y; lo[off + 8] = l.z; lo[off + 12] = l.w;
         }
@@ -107,7 +132,8 @@ __device__ __forceinline__ UmmaCtx umma_setup(unsigned char* smem_raw, int nstep
     __shared__ uint64_t bars[kUmmaStages];
     __shared__ uint32_t tmem_base;
     UmmaCtx c;
-    c.stages = reinterpret_cast<UmmaStage*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    constexpr uintptr_t kAlign = kMnMajor ? 1023 : 127;
+    c.stages = reinterpret_cast<UmmaStage*>((reinterpret_cast<uintptr_t>(smem_raw) + kAlign) & ~kAlign);
     c.bars = bars;
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -170,14 +196,22 @@ __device__ __forceinline__ void umma_loop(const UmmaCtx& c, const OA& A, const O
                 UmmaStage& st = c.stages[s];
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
+                constexpr bool A_MN = !A_RED && kMnMajor, B_MN = !B_RED && kMnMajor;
+                constexpr uint32_t idesc = kUmmaIdesc | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
                 for (int k8 = 0; k8 < UK / 8; ++k8) {
-                    const uint32_t ao = (uint32_t)(2 * k8) * A_PITCH * 4, bo = (uint32_t)(2 * k8) * B_PITCH * 4;
-                    const uint64_t dah = umma_desc(smem_u32(st.a_hi) + ao, A_PITCH * 4, 128), dal = umma_desc(smem_u32(st.a_lo) + ao, A_PITCH * 4, 128);
-                    const uint64_t dbh = umma_desc(smem_u32(st.b_hi) + bo, B_PITCH * 4, 128), dbl = umma_desc(smem_u32(st.b_lo) + bo, B_PITCH * 4, 128);
+                    // K-major: two 16-byte k-chunks per step, LBO = chunk pitch, SBO = 128 B between 8-row groups
+                    // MN-major: two 4-row atoms (1 KB) per step, LBO = box pitch, SBO = 512 B between atoms
+                    const uint32_t ao = A_MN ? (uint32_t)k8 * 1024u : (uint32_t)(2 * k8) * A_PITCH * 4;
+                    const uint32_t bo = B_MN ? (uint32_t)k8 * 1024u : (uint32_t)(2 * k8) * B_PITCH * 4;
+                    const uint32_t albo = A_MN ? MN_BOX_BYTES : A_PITCH * 4, asbo = A_MN ? 512 : 128;
+                    const uint32_t blbo = B_MN ? MN_BOX_BYTES : B_PITCH * 4, bsbo = B_MN ? 512 : 128;
+                    const uint64_t amn = A_MN ? ((uint64_t)1 << 61) : 0, bmn = B_MN ? ((uint64_t)1 << 61) : 0;   // layout type 1 = SWIZZLE_128B_BASE32B
+                    const uint64_t dah = umma_desc(smem_u32(st.a_hi) + ao, albo, asbo) | amn, dal = umma_desc(smem_u32(st.a_lo) + ao, albo, asbo) | amn;
+                    const uint64_t dbh = umma_desc(smem_u32(st.b_hi) + bo, blbo, bsbo) | bmn, dbl = umma_desc(smem_u32(st.b_lo) + bo, blbo, bsbo) | bmn;
                     const int step = kt * (UK / 8) + k8;                       // global k8 index of this CTA
-                    umma_tf32(c.tmem + nmain * UN, dal, dbh, step ? 1u : 0u);      // corrections
-                    umma_tf32(c.tmem + nmain * UN, dah, dbl, 1u);
-                    umma_tf32(c.tmem + (step % nmain) * UN, dah, dbh, step >= nmain ? 1u : 0u);
+                    umma_tf32(c.tmem + nmain * UN, dal, dbh, step ? 1u : 0u, idesc);      // corrections
+                    umma_tf32(c.tmem + nmain * UN, dah, dbl, 1u, idesc);
+                    umma_tf32(c.tmem + (step % nmain) * UN, dah, dbh, step >= nmain ? 1u : 0u, idesc);
                 }
                 umma_commit(&c.bars[s]);
             }
@@ -198,10 +232,10 @@ __device__ __forceinline__ void umma_loop(const UmmaCtx& c, const OA& A, const O
 #pragma unroll
             for (int l = 0; l < 2; ++l) {
                 const float4 v = ra[d][l];
-                QuadMap<A_RED, UM, 2>::store(st.a_hi, st.a_lo, A_PITCH, ma.i[l], ma.r[l], v);
+                QuadMap<A_RED, UM, 2>::store(st.a_hi, st.a_lo, ma.off[l], v);
                 if (BIAS) { bsum[l][0] += v.x; bsum[l][1] += v.y; bsum[l][2] += v.z; bsum[l][3] += v.w; }
             }
-            QuadMap<B_RED, UN, 1>::store(st.b_hi, st.b_lo, B_PITCH, mb.i[0], mb.r[0], rb[d]);
+            QuadMap<B_RED, UN, 1>::store(st.b_hi, st.b_lo, mb.off[0], rb[d]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "n"(UTH) : "memory");   // hand the stage to the MMA warp, do not wait for it
@@ -284,7 +318,7 @@ __global__ void __launch_bounds__(UTH) linear_fwd_kernel(LinearFwd a) {
 }
 
 // dx[M,K] (+)= (dy[M,N] . w[N, col0:col0+K]) * (relu_src > 0)
-template <bool VEC_A, bool VEC_B>
+template <bool VEC_A, bool VEC_B, bool WT = false>
 __global__ void __launch_bounds__(UTH) linear_dgrad_kernel(LinearDgrad a) {
     extern __shared__ unsigned char umma_smem[];
     const int nsteps = ((a.N + UK - 1) / UK) * (UK / 8);
@@ -293,7 +327,7 @@ __global__ void __launch_bounds__(UTH) linear_dgrad_kernel(LinearDgrad a) {
     const int z = blockIdx.z, m0 = blockIdx.x * UM, k0 = blockIdx.y * UN;
     const OpMat A{a.dy + (long long)z * a.dy_bs, a.lddy, a.M, a.N, VEC_A};               // rows m, reduction n (contiguous)
     float unused[2][4];
-    if (a.wt) {
+    if (WT) {
         const OpMat Bt{a.wt, a.ldwt, a.K, a.N, true};                                    // rows k, reduction n (contiguous): pre-transposed
         umma_loop<true, true, false>(c, A, Bt, m0, k0, 0, a.N, unused);
     } else {
@@ -338,7 +372,7 @@ __global__ void __launch_bounds__(UTH) linear_dgrad_kernel(LinearDgrad a) {
 // split stores its tile to part[blockIdx.z][N][ldp] and wgrad_reduce_kernel adds the splits in a fixed order (bitwise
 // reproducible gradients); without one the splits meet in atomics on the output.
 template <bool VEC_A, bool VEC_B>
-__global__ void __launch_bounds__(UTH) linear_wgrad_kernel(LinearWgrad a, int splits, int chunk, float* part, float* part_b, int ldp) {
+__global__ void __launch_bounds__(UTH, 3) linear_wgrad_kernel(LinearWgrad a, int splits, int chunk, float* part, float* part_b, int ldp) {
     extern __shared__ unsigned char umma_smem[];
     const int zb = blockIdx.z / splits, sp = blockIdx.z % splits;
     const int i0 = blockIdx.x * UM, j0 = blockIdx.y * UN;
@@ -354,7 +388,31 @@ __global__ void __launch_bounds__(UTH) linear_wgrad_kernel(LinearWgrad a, int sp
     if (want_bias) umma_loop<false, false, true>(c, A, B, i0, j0, mbeg, mend, bsum);
     else umma_loop<false, false, false>(c, A, B, i0, j0, mbeg, mend, bsum);
     pdl_trigger();                       // main loop done: the next kernel's CTAs may take the freed slots
-    if (want_bias && threadIdx.x < UT) {
+    if (kMnMajor) {
+        // the quads of one 4-wide output group are spread over 8 threads (two reduction indices each): fold them through shared
+        // memory, the first 128 threads publish
+        // (the stage ring is free again: umma_loop returns when every MMA has read it.  A static array here would push the CTA
+        // past 56 KB and cost the fourth CTA per SM)
+        float (*sb)[UM] = reinterpret_cast<float (*)[UM]>(c.stages);
+        if (want_bias && threadIdx.x < UT) {
+            const QuadMap<false, UM, 2> ma;                            // both quads of a thread sit on the same output group
+            const int slot = ((threadIdx.x >> 3) & 3) + 4 * (threadIdx.x >> 7);      // (reduction index mod 4, k-group): 8 threads per group
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sb[slot][ma.i[0] + e] = bsum[0][e] + bsum[1][e];
+        }
+        __syncthreads();
+        if (want_bias && threadIdx.x < UM) {
+            const float bmul = a.db_mul != 0.f ? a.db_mul : 1.0f;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < UT / 32; ++w) v += sb[w][threadIdx.x];
+            const int n = i0 + threadIdx.x;
+            if (n < a.N) {
+                if (part_b) part_b[(long long)blockIdx.z * a.N + n] = bmul * v;
+                else atomicAdd(a.db + (long long)zb * a.db_bs + n, bmul * v);
+            }
+        }
+    } else if (want_bias && threadIdx.x < UT) {
         // the 16 reduction indices of a k-tile sit in 16 neighbouring lanes: fold them, lane r == 0 publishes
         const QuadMap<false, UM, 2> ma;
         const float bmul = a.db_mul != 0.f ? a.db_mul : 1.0f;
@@ -516,6 +574,20 @@ int linear_dgrad(const LinearDgrad& a, cudaStream_t st) {
     if (!a.wt) { TGBuilder tg; if (tg.add_dgrad(a)) return tg.launch(st); }
     dim3 grid(cdiv(a.M, UM), cdiv(a.K, UN), a.batch);
     const bool va = vec_ok_mat(a.dy, a.lddy, a.dy_bs), vb = vec_ok_mat(a.w, a.ldw, a.w_bs, a.w_col0);
+    if (a.wt) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(linear_dgrad_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);
+            cudaFuncSetAttribute(linear_dgrad_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);
+            attr_done = true;
+        }
+        if (prof_enabled()) prof_note(a.M, a.K, a.N);
+        ProfScope ps_("linear_dgrad_kernel", st);
+        if (va) launch_pdl_prio(linear_prio(), linear_dgrad_kernel<true, true, true>, grid, dim3(UTH), kUmmaSmem, st, a);
+        else launch_pdl_prio(linear_prio(), linear_dgrad_kernel<false, true, true>, grid, dim3(UTH), kUmmaSmem, st, a);
+        MARL_LAUNCH_CHECK();
+        return MARL_OK;
+    }
     { if (prof_enabled()) prof_note(a.M, a.K, a.N); ProfScope ps_("linear_dgrad_kernel", st); MARL_DISPATCH2(linear_dgrad_kernel, va, vb, grid, st, a); }
     MARL_LAUNCH_CHECK();
     return MARL_OK;

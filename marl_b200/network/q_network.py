@@ -47,6 +47,7 @@ class _UnrollFn(torch.autograd.Function):
         x = torch.empty(rows, H, **f32)
         gi = torch.empty(rows, 3 * H, **f32)
         gates = torch.empty(rows, 4 * H, **f32)
+        w_ih_t = torch.empty(H, 3 * H, **f32)        # W_ih^T, produced by the forward for the backward's data gradient
         st = L.UnrollStream()
         st.obs, st.onehot = obs.data_ptr(), (None if onehot is None else onehot.data_ptr())
         st.shift_onehot, st.full_input, st.h0_from = int(shift), int(full_input), -1
@@ -54,9 +55,10 @@ class _UnrollFn(torch.autograd.Function):
         st.params = agent_param_struct({n: p.data_ptr() for n, p in zip(AGENT_FLAT_ORDER, params)})
         st.q, st.hidden, st.h_last = q.data_ptr(), hidden.data_ptr(), h_last.data_ptr()
         st.x, st.gi, st.gates = x.data_ptr(), gi.data_ptr(), gates.data_ptr()
+        st.w_ih_t = w_ih_t.data_ptr()
         L.call("marl_agent_unroll_fwd", C.byref(d), C.byref(st), 1, L.stream_ptr())
         ctx.save_for_backward(obs, onehot if onehot is not None else obs, h0 if h0 is not None else obs,
-                              hidden, x, gates, *params)
+                              hidden, x, gates, w_ih_t, *params)
         ctx.meta = (dims, int(shift), int(full_input), onehot is None, h0 is not None)
         ctx.mark_non_differentiable(h_last)
         return q, hidden, h_last
@@ -64,7 +66,7 @@ class _UnrollFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dq, dhidden, _dh_last):
         dims, shift, full_input, no_onehot, had_h0 = ctx.meta
-        obs, onehot, h0, hidden, x, gates, *params = ctx.saved_tensors
+        obs, onehot, h0, hidden, x, gates, w_ih_t, *params = ctx.saved_tensors
         B, Lq, N, A, O = dims
         dev = obs.device
         rows = B * Lq * N
@@ -75,6 +77,7 @@ class _UnrollFn(torch.autograd.Function):
         a.shift_onehot, a.full_input = shift, full_input
         a.params = agent_param_struct({n: p.data_ptr() for n, p in zip(AGENT_FLAT_ORDER, params)})
         a.hidden, a.x, a.gates = hidden.data_ptr(), x.data_ptr(), gates.data_ptr()
+        a.w_ih_t = w_ih_t.data_ptr()
         dq = None if dq is None else dq.contiguous()
         dhidden = None if dhidden is None else dhidden.contiguous()
         a.dq, a.dhidden = L.ptr(dq), L.ptr(dhidden)
