@@ -679,7 +679,9 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         launch_pdl_prio(kGruPrio, gru_unroll_fwd_kernel, grid, dim3(kGruThreads * kGruGroups), sm, st, ga);
     }
     MARL_LAUNCH_CHECK();
-    // phase C
+    // phase C.  (The fork / join pair stays even when a fused mixer evaluates the heads and nothing is launched here: it takes the
+    // programmatic launch edge between the recurrence and the mixing kernel, whose 480 early-resident CTAs otherwise sit on the
+    // SMs beside the last steps of the recurrence -- measured 333 us per step with the pair, 345-354 us without.)
     ForkJoin fc(st, n_streams);
     for (int i = 0; i < n_streams; ++i) {
         if (!s[i].q) continue;
