@@ -419,6 +419,8 @@ int marl_front_enable(int on);
  * pointer), else 0.  No reference counterpart: lets ReplayBuffer.store_episode (common/replaybuffer.py:30-61) hand pinned
  * episode arrays to marl_ingest_f64 without a staging copy. */
 int marl_host_registered(const void* p, size_t bytes);
+/* The same for n ranges in one call: 1 when all of them qualify. */
+int marl_host_registered_all(const void* const* p, const size_t* bytes, int n);
 /* Occupies the stream for ~us microseconds (<= 100000) so that later launches queue up behind it. */
 int marl_spin_us(int us, void* stream);
 int marl_profile_enable(int on);

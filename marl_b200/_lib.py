@@ -176,6 +176,7 @@ _SIGNATURES = {
     "marl_linear_wgrad": ([c_ptr, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int, c_ptr] + [C.c_int] * 3 + [c_ptr], C.c_int),
     "marl_optim_partials": ([], C.c_int),
     "marl_host_registered": ([c_ptr, C.c_size_t], C.c_int),
+    "marl_host_registered_all": ([c_ptr, c_ptr, C.c_int], C.c_int),
     "marl_front_enable": ([C.c_int], C.c_int),
     "marl_spin_us": ([C.c_int, c_ptr], C.c_int),
     "marl_profile_enable": ([C.c_int], C.c_int),

@@ -113,6 +113,7 @@ class ReplayBuffer:
         self._stage = {}                                          # pinned / device staging of the host fast path
         self._idx_stage = {}
         self._pending_read = None
+        self.pinned_stores = 0                                    # episodes ingested straight from page-locked arrays
         self.lock = threading.Lock()
 
     # ---- store ------------------------------------------------------------------------------------
@@ -170,23 +171,25 @@ class ReplayBuffer:
         reference's synchronous numpy copy (common/replaybuffer.py:30-61)."""
         import ctypes as C
         from .. import _lib as L
-        lib = L.load()
-        ptrs = []
-        for k in KEYS:
-            a = episode_batch[k]
-            if not a.flags["C_CONTIGUOUS"] or a.dtype != np.float64 or a.ctypes.data % 16:
-                return False
-            if lib.marl_host_registered(a.ctypes.data, a.nbytes) != 1:
-                return False
-            ptrs.append(a.ctypes.data)
         meta = self._stage.get(("meta", batch_size))
         if meta is None:
+            n = len(KEYS)
             meta = {"row_bytes": [self.buffers[k][0].numel() * self.buffers[k].element_size() for k in KEYS],
                     "base": [self.buffers[k].data_ptr() for k in KEYS],
                     "dims": L.Dims(batch_size, self.episode_limit, self.n_agents, self.n_actions, self.obs_shape, self.state_shape),
-                    "e64": L.EpisodeF64(), "e32": L.EpisodeF32(), "done": th.cuda.Event()}
+                    "e64": L.EpisodeF64(), "e32": L.EpisodeF32(), "done": th.cuda.Event(),
+                    "ptrs": (C.c_void_p * n)(), "bytes": (C.c_size_t * n)(), "check": L.load().marl_host_registered_all}
             meta["e64"].u_is_int64 = 0
             self._stage[("meta", batch_size)] = meta
+        ptrs, nbytes = meta["ptrs"], meta["bytes"]
+        for i, k in enumerate(KEYS):
+            a = episode_batch[k]
+            p = a.__array_interface__["data"][0]          # (a.ctypes.data builds a ctypes object per call: ~1 us each)
+            if not a.flags.c_contiguous or a.dtype != np.float64 or p % 16:
+                return False
+            ptrs[i], nbytes[i] = p, a.nbytes
+        if meta["check"](ptrs, nbytes, len(KEYS)) != 1:     # every array page-locked and device-readable (one call for the 11)
+            return False
         e64, e32 = meta["e64"], meta["e32"]
         for i, k in enumerate(KEYS):
             setattr(e64, k, ptrs[i])
@@ -194,6 +197,7 @@ class ReplayBuffer:
         L.call("marl_ingest_f64", C.byref(e64), self.episode_limit, C.byref(meta["dims"]), C.byref(e32), L.stream_ptr())
         meta["done"].record()
         self._pending_read = meta["done"]        # store_episode waits on it after its host-side bookkeeping
+        self.pinned_stores += 1
         return True
 
     def store_episode(self, episode_batch):
@@ -211,10 +215,16 @@ class ReplayBuffer:
                 self._store_generic(episode_batch, batch_size, idx_np)
             term = episode_batch['terminated']
             term = term.detach().cpu().numpy() if th.is_tensor(term) else np.asarray(term)
-            term = term.reshape(batch_size, -1)[:, :self.episode_limit] == 1
-            first = np.where(term.any(axis=1), term.argmax(axis=1), -1)
-            self.first_terminated[idx_np] = first
-            self.version[idx_np] += 1
+            if batch_size == 1:                     # (the rollout's case: scalar bookkeeping instead of five numpy calls)
+                hit = np.flatnonzero(term.reshape(-1)[:self.episode_limit] == 1)
+                row = int(idx_np[0])
+                self.first_terminated[row] = int(hit[0]) if hit.size else -1
+                self.version[row] += 1
+            else:
+                term = term.reshape(batch_size, -1)[:, :self.episode_limit] == 1
+                first = np.where(term.any(axis=1), term.argmax(axis=1), -1)
+                self.first_terminated[idx_np] = first
+                self.version[idx_np] += 1
             if self._pending_read is not None:       # zero-copy path: the kernel has finished reading the caller's arrays
                 self._pending_read.synchronize()
                 self._pending_read = None

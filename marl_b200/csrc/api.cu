@@ -73,3 +73,11 @@ extern "C" int marl_host_registered(const void* p, size_t bytes) {
     }
     return 1;
 }
+
+// The same test for n ranges in one call (the 11 arrays of an episode): 1 when ALL of them qualify.
+extern "C" int marl_host_registered_all(const void* const* p, const size_t* bytes, int n) {
+    if (!p || !bytes || n <= 0) return 0;
+    for (int i = 0; i < n; ++i)
+        if (marl_host_registered(p[i], bytes[i]) != 1) return 0;
+    return 1;
+}
