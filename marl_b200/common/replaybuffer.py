@@ -254,8 +254,8 @@ class ReplayBuffer:
         with self.lock:
             ft = self.first_terminated[idx]
             versions = self.version[idx].copy()
-        has = ft >= 0
-        max_len = int(ft[has].max()) + 1 if has.any() else int(self.episode_limit)   # q_learner.py:49-61
+        m = int(ft.max())                         # episodes that never terminate (-1) do not count (q_learner.py:49-61)
+        max_len = m + 1 if m >= 0 else int(self.episode_limit)
         return DeviceEpisodeBatch(self.buffers, idx, self._indices_to_device(idx), max_len, owner=self, versions=versions)
 
     def _indices_to_device(self, idx):
@@ -266,12 +266,19 @@ class ReplayBuffer:
         n = idx.shape[0]
         ring = self._idx_stage.get(n)
         if ring is None:
-            ring = {"host": [th.empty(n, dtype=th.int64).pin_memory() for _ in range(4)], "seq": 0}
+            host = [th.empty(n, dtype=th.int64).pin_memory() for _ in range(4)]
+            ring = {"host": host, "view": [h.numpy() for h in host], "done": [None] * 4, "seq": 0}
             self._idx_stage[n] = ring
-        h = ring["host"][ring["seq"] & 3]
+        slot = ring["seq"] & 3                    # (the pinned slot is only needed until its asynchronous copy has run)
         ring["seq"] += 1
-        h.numpy()[:] = idx
-        return h.to(self.device, non_blocking=True)
+        if ring["done"][slot] is not None:
+            ring["done"][slot].synchronize()      # four samples ahead of the device: wait for that copy before reusing its source
+        ring["view"][slot][:] = idx
+        dev = th.empty(n, dtype=th.int64, device=self.device).copy_(ring["host"][slot], non_blocking=True)
+        if ring["done"][slot] is None:
+            ring["done"][slot] = th.cuda.Event()
+        ring["done"][slot].record()
+        return dev
 
     # ---- ring indices (common/replaybuffer.py:63-80) -----------------------------------------------
     def _get_storage_idx(self, inc=None):
