@@ -281,9 +281,13 @@ def dp_check(torch, dist, world, rank, make_learner):
     single = make_learner(shape, seed=11)
     db = to_device_batch(torch, hb, shape["T"])
     losses_dp, losses_1 = [], []
+    gerr = None
     for i in range(3):
         losses_dp.append(dp.train(dict(db), i))          # every rank passes the GLOBAL batch; the learner takes its shard
         losses_1.append(single.train(dict(db), i))
+        if i == 0:      # same parameters on both sides: the exchanged, normalised, clipped gradient must be the single-GPU one
+            g_dp, g_1 = dp._flat.grad, single._flat.grad
+            gerr = float((g_dp - g_1).abs().max() / g_1.abs().max())
     p_dp, p_1 = dp._flat.data.clone(), single._flat.data
     gathered = [torch.empty_like(p_dp) for _ in range(world)]
     dist.all_gather(gathered, p_dp)
@@ -291,9 +295,12 @@ def dp_check(torch, dist, world, rank, make_learner):
     scale = float(p_1.abs().max())
     perr = float((p_dp - p_1).abs().max()) / scale
     lerr = max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(losses_dp, losses_1))
-    # RMSprop divides by ~|g| on the first steps: parameters are compared at the noise floor documented in tests/parity_util.py
-    ok = identical and lerr <= 1e-5 and perr <= 1e-5 + 0.25 * dp.lr * 3 / scale
-    return {"replicas_bit_identical": identical, "loss_rel_err_vs_1gpu": lerr, "param_rel_err_vs_1gpu": perr, "steps": 3,
+    # The well-conditioned statements are the gradient of the first step and the losses.  The parameters are reported, not gated:
+    # RMSprop's first updates are lr * g / sqrt(0.01 g^2) = 10 lr sign(g), so a gradient element at the summation-order noise
+    # floor can land 2 * 10 * lr apart per step whatever the exchange does (tests/parity_util.py documents the same floor)
+    ok = identical and lerr <= 1e-5 and gerr is not None and gerr <= 1e-5
+    return {"replicas_bit_identical": identical, "loss_rel_err_vs_1gpu": lerr, "grad_rel_err_vs_1gpu_step0": gerr,
+            "param_rel_err_vs_1gpu": perr, "param_noise_floor": 2 * 10 * dp.lr * 3 / scale, "steps": 3,
             "global_batch": Bg, "exchange": "peer" if getattr(dp, "_peer", None) is not None else "nccl", "ok": bool(ok)}
 
 
