@@ -11,8 +11,21 @@
 #include "forkjoin.h"
 #include "../../include/marl_b200.h"
 #include "profile.h"
-#include "select.cuh"
 #include "tgemm.h"
+
+#ifdef MARL_MIX_TRACE
+// (select.cuh's optional stamps write into the kernel's trace through these file-scope device variables: one warp traces)
+__device__ long long* g_mix_trace_ptr = nullptr;
+#define MIX_SEL_STAMP(tag)                                                                                      \
+    do {                                                                                                        \
+        if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 300) && g_mix_trace_ptr) {                     \
+            long long* t__ = g_mix_trace_ptr + (blockIdx.x ? 512 : 0);                                           \
+            long long now__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now__));                           \
+            const int n__ = (int)t__[510]; if (n__ < 60) { t__[2 * n__] = (tag); t__[2 * n__ + 1] = now__; t__[510] = n__ + 1; } \
+        }                                                                                                       \
+    } while (0)
+#endif
+#include "select.cuh"
 
 namespace marl {
 
@@ -42,11 +55,7 @@ struct QmixMixArgs {
     long long* trace;                      // debug (marl_tgemm_trace, -DMARL_MIX_TRACE builds): globaltimer stamps of one warp
 };
 #ifdef MARL_MIX_TRACE
-#define MIX_STAMP(tag)                                                                                    \
-    do {                                                                                                  \
-        if (trace && tn < 60) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));      \
-                                trace[2 * tn] = (tag); trace[2 * tn + 1] = t_; ++tn; trace[510] = tn; }   \
-    } while (0)
+#define MIX_STAMP(tag) MIX_SEL_STAMP(tag)
 #else
 #define MIX_STAMP(tag) do { } while (0)
 #endif
@@ -68,8 +77,7 @@ __device__ __forceinline__ float qmix_forward_lane(const float* __restrict__ y, 
 
 __global__ void __launch_bounds__(kQmixWarps * 32, kQmixCtasPerSm) qmix_mix_kernel(QmixMixArgs a) {
 #ifdef MARL_MIX_TRACE
-    long long* trace = (a.trace && (blockIdx.x == 0 || blockIdx.x == 300) && threadIdx.x == 0) ? a.trace + (blockIdx.x ? 512 : 0) : nullptr;
-    int tn = 0;
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 300)) g_mix_trace_ptr = a.trace;      // (same value from both writers)
 #endif
     MIX_STAMP(0);
     pdl_enter();
@@ -80,11 +88,16 @@ __global__ void __launch_bounds__(kQmixWarps * 32, kQmixCtasPerSm) qmix_mix_kern
     extern __shared__ __align__(16) float ssel_dyn[];         // fused selection: select_warp_floats() per warp
     const float* heads = nullptr;
     if (a.sel.q && a.sel.heads) {
+        // this warp's first sample: its hidden rows are on their way (cp.async) while the CTA stages the head matrices
+        const int m_first = blockIdx.x * kQmixWarps + (threadIdx.x >> 5);
+        if (m_first < a.M)
+            warp_stage_hidden_async(a.sel, m_first, a.N, a.A, threadIdx.x & 31, ssel_dyn + (threadIdx.x >> 5) * select_warp_floats(a.N, a.A, true));
         float* h = ssel_dyn + kQmixWarps * select_warp_floats(a.N, a.A, true);
         stage_heads(a.sel, a.A, h);
         heads = h;
         __syncthreads();
     }
+    bool prestaged = a.sel.q && a.sel.heads;
     MIX_STAMP(2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = a.N, C = N * E + 3 * E;
@@ -97,7 +110,8 @@ __global__ void __launch_bounds__(kQmixWarps * 32, kQmixCtasPerSm) qmix_mix_kern
         const float* q = a.q + (long long)m * N;
         const float* qt = a.q_t + (long long)m * N;
         if (a.sel.q) {
-            warp_select(a.sel, m, N, a.A, lane, ssel_dyn + warp * select_warp_floats(N, a.A, a.sel.heads), ssel[warp][0], ssel[warp][1], heads);
+            warp_select(a.sel, m, N, a.A, lane, ssel_dyn + warp * select_warp_floats(N, a.A, a.sel.heads), ssel[warp][0], ssel[warp][1], heads, prestaged);
+            prestaged = false;
             q = ssel[warp][0]; qt = ssel[warp][1];
         }
         MIX_STAMP(3);

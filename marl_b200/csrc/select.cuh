@@ -6,6 +6,10 @@
 #include "common.cuh"
 #include "../../include/marl_b200.h"
 
+#ifndef MIX_SEL_STAMP
+#define MIX_SEL_STAMP(tag) do { } while (0)
+#endif
+
 namespace marl {
 
 constexpr float kNegBig = -9999999.0f;   // algorithm/q_learner.py:105,112,126
@@ -65,10 +69,28 @@ __device__ __forceinline__ void stage_heads(const SelectArgs& s, int A, float* d
     }
 }
 
+// The sample's three hidden slabs [N][kHeadLd] -> this warp's staging area, asynchronously (cp.async): issued before the CTA stages
+// the head matrices so that the two global round trips overlap; warp_select(.., prestaged = true) waits for them.
+__device__ __forceinline__ void warp_stage_hidden_async(const SelectArgs& s, long long m, int N, int A, int lane, float* stage) {
+    constexpr int Q = MARL_H / 4, LQ = kHeadLd / 4;
+    const int NA = N * A;
+    float4* she = (float4*)(stage + ((3 * NA + 3) & ~3));
+    float4* sht = she + N * LQ;
+    float4* shn = sht + N * LQ;
+    const float4* ge = (const float4*)(s.h_e + m * N * MARL_H);
+    const float4* gt = (const float4*)(s.h_t + m * N * MARL_H);
+    const float4* gn = s.h_n ? (const float4*)(s.h_n + m * N * MARL_H) : ge;
+    for (int i = lane; i < N * Q; i += 32) {
+        const int n = i / Q, k = i - n * Q;
+        cp_async16(she + n * LQ + k, ge + i); cp_async16(sht + n * LQ + k, gt + i); cp_async16(shn + n * LQ + k, gn + i);
+    }
+    cp_async_commit();
+}
+
 // stage: 2 * N * A floats of this warp; qc / tc: N floats each of this warp (q_chosen, q_targets_chosen on return)
 // heads: the staged head matrices (stage_heads) when s.heads, else unused.
 __device__ __forceinline__ void warp_select(const SelectArgs& s, long long m, int N, int A, int lane, float* stage,
-                                            float* qc, float* tc, const float* heads) {
+                                            float* qc, float* tc, const float* heads, bool prestaged = false) {
     const int NA = N * A;
     const long long o = m * NA;
     float* sn = stage;
@@ -80,37 +102,51 @@ __device__ __forceinline__ void warp_select(const SelectArgs& s, long long m, in
         float4* she = (float4*)(stage + ((3 * NA + 3) & ~3));
         float4* sht = she + N * LQ;
         float4* shn = sht + N * LQ;
-        const float4* ge = (const float4*)(s.h_e + m * N * MARL_H);
-        const float4* gt = (const float4*)(s.h_t + m * N * MARL_H);
-        const float4* gn = s.h_n ? (const float4*)(s.h_n + m * N * MARL_H) : ge;
-        for (int i = lane; i < N * Q; i += 32) {
-            const int n = i / Q, k = i - n * Q;
-            she[n * LQ + k] = __ldg(ge + i); sht[n * LQ + k] = __ldg(gt + i); shn[n * LQ + k] = __ldg(gn + i);
-        }
+        if (!prestaged) warp_stage_hidden_async(s, m, N, A, lane, stage);
+        cp_async_wait<0>();
         __syncwarp();
-        for (int i = lane; i < NA; i += 32) {
-            const int n = i / A, a = i - n * A;
-            const float4* w = (const float4*)(heads + a * kHeadLd);
-            const float4* wt = (const float4*)(heads + (A + a) * kHeadLd);
+        MIX_SEL_STAMP(31);
+        // one lane = one agent and TWO actions: the agent's three hidden rows are read once for both, 7 instead of 10 128-bit
+        // shared-memory loads per 24 FMAs (the loop is bound by shared-memory bandwidth, tools/mix_trace.py)
+        const int A2 = (A + 1) >> 1;
+        for (int i = lane; i < N * A2; i += 32) {
+            const int n = i / A2, ap = i - n * A2, a0 = 2 * ap, a1 = a0 + 1 < A ? a0 + 1 : a0;
+            const float4* w0 = (const float4*)(heads + a0 * kHeadLd);
+            const float4* w1 = (const float4*)(heads + a1 * kHeadLd);
+            const float4* v0 = (const float4*)(heads + (A + a0) * kHeadLd);
+            const float4* v1 = (const float4*)(heads + (A + a1) * kHeadLd);
             const float4* he = she + n * LQ;
             const float4* ht = sht + n * LQ;
             const float4* hn = shn + n * LQ;
-            float4 ce = make_float4(0.f, 0.f, 0.f, 0.f), cn = ce, ct = ce;     // 12 independent FMA chains
-#pragma unroll 4
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 ce0 = z4, cn0 = z4, ct0 = z4, ce1 = z4, cn1 = z4, ct1 = z4;      // 24 independent FMA chains
+#pragma unroll 2
             for (int k = 0; k < Q; ++k) {
-                const float4 a4 = w[k], b4 = wt[k], e4 = he[k], t4 = ht[k], n4 = hn[k];
-                ce.x = fmaf(a4.x, e4.x, ce.x); ce.y = fmaf(a4.y, e4.y, ce.y); ce.z = fmaf(a4.z, e4.z, ce.z); ce.w = fmaf(a4.w, e4.w, ce.w);
-                cn.x = fmaf(a4.x, n4.x, cn.x); cn.y = fmaf(a4.y, n4.y, cn.y); cn.z = fmaf(a4.z, n4.z, cn.z); cn.w = fmaf(a4.w, n4.w, cn.w);
-                ct.x = fmaf(b4.x, t4.x, ct.x); ct.y = fmaf(b4.y, t4.y, ct.y); ct.z = fmaf(b4.z, t4.z, ct.z); ct.w = fmaf(b4.w, t4.w, ct.w);
+                const float4 e4 = he[k], t4 = ht[k], n4 = hn[k];
+                const float4 a4 = w0[k], b4 = v0[k];
+                ce0.x = fmaf(a4.x, e4.x, ce0.x); ce0.y = fmaf(a4.y, e4.y, ce0.y); ce0.z = fmaf(a4.z, e4.z, ce0.z); ce0.w = fmaf(a4.w, e4.w, ce0.w);
+                cn0.x = fmaf(a4.x, n4.x, cn0.x); cn0.y = fmaf(a4.y, n4.y, cn0.y); cn0.z = fmaf(a4.z, n4.z, cn0.z); cn0.w = fmaf(a4.w, n4.w, cn0.w);
+                ct0.x = fmaf(b4.x, t4.x, ct0.x); ct0.y = fmaf(b4.y, t4.y, ct0.y); ct0.z = fmaf(b4.z, t4.z, ct0.z); ct0.w = fmaf(b4.w, t4.w, ct0.w);
+                const float4 c4 = w1[k], d4 = v1[k];
+                ce1.x = fmaf(c4.x, e4.x, ce1.x); ce1.y = fmaf(c4.y, e4.y, ce1.y); ce1.z = fmaf(c4.z, e4.z, ce1.z); ce1.w = fmaf(c4.w, e4.w, ce1.w);
+                cn1.x = fmaf(c4.x, n4.x, cn1.x); cn1.y = fmaf(c4.y, n4.y, cn1.y); cn1.z = fmaf(c4.z, n4.z, cn1.z); cn1.w = fmaf(c4.w, n4.w, cn1.w);
+                ct1.x = fmaf(d4.x, t4.x, ct1.x); ct1.y = fmaf(d4.y, t4.y, ct1.y); ct1.z = fmaf(d4.z, t4.z, ct1.z); ct1.w = fmaf(d4.w, t4.w, ct1.w);
             }
-            float qe = (ce.x + ce.y) + (ce.z + ce.w), qn = (cn.x + cn.y) + (cn.z + cn.w), qt = (ct.x + ct.y) + (ct.z + ct.w);
-            const float be = heads[2 * A * kHeadLd + a], bt = heads[2 * A * kHeadLd + A + a];
-            qe += be; qn += be; qt += bt;
-            const bool off = s.avail_next[o + i] == 0.0f;
-            if (off) qt = kNegBig;                                     // q_learner.py:105
-            s.q[o + i] = qe; s.qt[o + i] = qt;
-            se[i] = qe; st[i] = qt;
-            if (s.qn) { s.qn[o + i] = qn; sn[i] = off ? kNegBig : qn; }     // :110-112 (the masked copy is not kept)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int a = h ? a1 : a0;
+                if (h && a1 == a0) break;                                  // odd A: the last lane of an agent has one action
+                const float4 ce = h ? ce1 : ce0, cn = h ? cn1 : cn0, ct = h ? ct1 : ct0;
+                float qe = (ce.x + ce.y) + (ce.z + ce.w), qn = (cn.x + cn.y) + (cn.z + cn.w), qt = (ct.x + ct.y) + (ct.z + ct.w);
+                const float be = heads[2 * A * kHeadLd + a], bt = heads[2 * A * kHeadLd + A + a];
+                qe += be; qn += be; qt += bt;
+                const int j = n * A + a;
+                const bool off = s.avail_next[o + j] == 0.0f;
+                if (off) qt = kNegBig;                                     // q_learner.py:105
+                s.q[o + j] = qe; s.qt[o + j] = qt;
+                se[j] = qe; st[j] = qt;
+                if (s.qn) { s.qn[o + j] = qn; sn[j] = off ? kNegBig : qn; }     // :110-112 (the masked copy is not kept)
+            }
         }
     } else {
         for (int i = lane; i < NA; i += 32) {
@@ -122,6 +158,7 @@ __device__ __forceinline__ void warp_select(const SelectArgs& s, long long m, in
         }
     }
     __syncwarp();
+    MIX_SEL_STAMP(32);
     for (int n = lane; n < N; n += 32) {
         const long long i = m * N + n;
         const float c = s.heads ? se[n * A + (int)s.u[i]] : s.q[i * A + s.u[i]];   // :100

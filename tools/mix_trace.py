@@ -23,7 +23,7 @@ L.call("marl_tgemm_trace", 1, None)
 learner.train(db, 10)
 buf = (C.c_longlong * 2048)()
 L.call("marl_tgemm_trace", 0, C.cast(buf, C.c_void_p))
-names = {0: "kernel entry", 1: "after pdl wait", 2: "heads staged (+ barrier)", 3: "selection done (hidden loads, heads, scan)", 4: "eval forward",
+names = {31: "  hidden rows staged", 32: "  heads computed (q, qn, qt written)", 0: "kernel entry", 1: "after pdl wait", 2: "heads staged (+ barrier)", 3: "selection done (hidden loads, heads, scan)", 4: "eval forward",
          5: "target forward + TD", 6: "dhy stores + dq", 7: "dq_dense / dhext", 8: "block reduction, end"}
 for base, blk in ((0, 0), (512, 300)):
     n = buf[base + 510]
@@ -31,5 +31,5 @@ for base, blk in ((0, 0), (512, 300)):
     prev = None
     for i in range(n):
         tag, t = buf[base + 2 * i], buf[base + 2 * i + 1]
-        print(f"   {names.get(tag, tag):45s} {'' if prev is None else f'+{t - prev:6d} ns'}")
+        print(f"   {str(names.get(tag, tag)):45s} {'' if prev is None else f'+{t - prev:6d} ns'}")
         prev = t
