@@ -257,6 +257,10 @@ __device__ __forceinline__ void cta_rows(int rows, int chain, int& begin, int& c
 }
 
 constexpr int kGruGroups = 2;      // chains advanced side by side in one CTA (one 128-thread group each)
+#ifndef MARL_GRU_SPARE_SMS
+#define MARL_GRU_SPARE_SMS 16
+#endif
+constexpr int kGruFwdSpareSMs = MARL_GRU_SPARE_SMS;
 constexpr int kGruMaxRows = 8;     // rows per group and pass
 constexpr size_t gru_fwd_smem(int R) { return (size_t)(2 * R * MARL_H + kGiDepth * R * MARL_G) * sizeof(float); }
 
@@ -671,7 +675,12 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         const size_t sm = kGruGroups * gru_fwd_smem(kGruMaxRows);
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(gru_unroll_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); attr_set = true; }
-        const int n_ctas = rows < kNumSMs ? rows : kNumSMs;
+        // A recurrence CTA takes an SM's whole register file, so nothing else runs beside it.  When leaving a few SMs out does not
+        // add a row to the fullest CTA, they go to the kernels sibling streams have queued (the target hyper-network forward of
+        // QMIX otherwise waits for this kernel to END, in front of the mixing kernel).
+        int n_ctas = rows < kNumSMs ? rows : kNumSMs;
+        if (rows > kNumSMs && (rows + kNumSMs - kGruFwdSpareSMs - 1) / (kNumSMs - kGruFwdSpareSMs) == (rows + kNumSMs - 1) / kNumSMs)
+            n_ctas = kNumSMs - kGruFwdSpareSMs;
         if ((rows + n_ctas - 1) / n_ctas + 2 > 65535) return MARL_EINVAL;
         plan_rows(ga, rows, n_ctas);
         ga.trace = trace_buffer();
