@@ -266,19 +266,15 @@ class ReplayBuffer:
         n = idx.shape[0]
         ring = self._idx_stage.get(n)
         if ring is None:
-            host = [th.empty(n, dtype=th.int64).pin_memory() for _ in range(4)]
-            ring = {"host": host, "view": [h.numpy() for h in host], "done": [None] * 4, "seq": 0}
+            host = [th.empty(n, dtype=th.int64).pin_memory() for _ in range(16)]
+            ring = {"host": host, "view": [h.numpy() for h in host], "seq": 0}
             self._idx_stage[n] = ring
-        slot = ring["seq"] & 3                    # (the pinned slot is only needed until its asynchronous copy has run)
+        # (a pinned slot is only needed until its asynchronous copy has run; sixteen of them: a caller would have to queue
+        # sixteen samples without ever touching their data for a slot to be rewritten early)
+        slot = ring["seq"] & 15
         ring["seq"] += 1
-        if ring["done"][slot] is not None:
-            ring["done"][slot].synchronize()      # four samples ahead of the device: wait for that copy before reusing its source
         ring["view"][slot][:] = idx
-        dev = th.empty(n, dtype=th.int64, device=self.device).copy_(ring["host"][slot], non_blocking=True)
-        if ring["done"][slot] is None:
-            ring["done"][slot] = th.cuda.Event()
-        ring["done"][slot].record()
-        return dev
+        return ring["host"][slot].to(self.device, non_blocking=True)
 
     # ---- ring indices (common/replaybuffer.py:63-80) -----------------------------------------------
     def _get_storage_idx(self, inc=None):
