@@ -794,7 +794,8 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
     if (a->h0 && (rc = linear_wgrad(w_h0, fb.lane(1)))) return rc;
     if ((rc = linear_wgrad(w_ih, fb.lane(2)))) return rc;
     // (a launch priority on the dependent pair dx -> dW1, the tail's critical path, was measured: no change)
-    // (also measured: this data gradient launched plainly instead of programmatically behind the BPTT kernel, +12 us)
+    // (also measured: this data gradient launched plainly instead of programmatically behind the BPTT kernel, +12 us; the three
+    // independent weight gradients forked behind the data gradient instead of beside it, +3 us)
     if ((rc = linear_dgrad(g_dx, st))) return rc;
     if ((rc = linear_wgrad(w_fc1, st))) return rc;
     fb.join();
