@@ -123,6 +123,17 @@ typedef struct marl_unroll_stream {
                                 loss masks them) and h_last is the hidden after the last REAL step.  Never set it on a
                                 stream another stream continues from (h0_from): the reference carries the hidden state through
                                 the padded steps (q_learner.py:96,110), so that one must run to L. */
+    const float* padded;     /* [B,L] fp32 or NULL.  Non-NULL (with ep_len): the call computes ep_len from it first -- exactly
+                                marl_episode_lengths, launched on a forked lane beside the input layers instead of in front of
+                                them -- so ep_len is then an OUTPUT of the call (and of every stream that shares the array) */
+    int* row_order;          /* device scratch [B*N] ints or NULL.  When the streams of a chain (a stream and the ones that continue
+                                it through h0_from) carry an ep_len and a row_order, the chain's rows (b, n) are dealt to the
+                                recurrence CTAs sorted by episode length -- the CTAs that advance the most rows get the shortest
+                                ones, rows that advance in lock-step have similar lengths -- instead of in index order.  Results
+                                are unchanged (rows are independent); the call fills the array itself.  (Batches of more than 4096
+                                episodes keep the index order, here and in the backward.) */
+    int* row_order_bwd;      /* out [B*N] ints or NULL (needs an ep_len on some stream of the call): the same deal for the plan
+                                of marl_agent_unroll_bwd; hand it to marl_unroll_bwd.row_order of the SAME step */
 } marl_unroll_stream;
 
 /* ep_len[b] = 1 + the last step with padded[b, t] == 0 (at least 1): every step at or beyond it has mask = 0 in the loss
@@ -151,6 +162,8 @@ typedef struct marl_unroll_bwd {
     const int* ep_len;       /* device [B] or NULL.  Non-NULL: the backward chain of a row starts at its episode's last real
                                 step; dgi / dgh of the padded steps behind it are written as zeros (what the full chain
                                 computes there: every upstream gradient is masked to zero) */
+    const int* row_order;    /* [B*N] = marl_unroll_stream.row_order_bwd of this step's forward call, or NULL (index order); only
+                                read together with ep_len */
 } marl_unroll_bwd;
 
 int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* a, void* stream);

@@ -18,6 +18,8 @@
 #include "forkjoin.h"
 #include "../../include/marl_b200.h"
 #include "profile.h"
+#include <algorithm>
+#include <memory>
 
 namespace marl {
 
@@ -31,6 +33,8 @@ constexpr int kGruThreads = 128;   // 64 hidden units x 2-way split of the reduc
 #define MARL_BWD_DEPTH 6
 #endif
 constexpr int kGiDepth = MARL_GI_DEPTH;   // cp.async ring depth (time steps) of the forward's input gates
+constexpr int kGruGroups = 2;      // chains advanced side by side in one CTA (one 128-thread group each)
+constexpr int kGruMaxRows = 8;     // rows per group and pass
 
 // MUFU-based gate non-linearities: ex2.approx / rcp.approx are accurate to ~2 ulp, i.e. <= 2e-7 absolute on
 // the (0,1) / (-1,1) outputs -- the same order as the fp32 rounding of the reference's own libm path.
@@ -71,6 +75,7 @@ struct GruFwdArgs {
     const float* h0[kMaxStreams];
     int n_chains, B, L, N;
     unsigned short rows_of[kMaxStreams][kNumSMs];   // rows of chain c advanced by CTA i (balanced on the host, see plan_rows)
+    const int* row_order[kMaxStreams];              // per chain: logical position -> row (b*N + n), or null = identity (row_order_kernel)
     long long* trace;                                // debug (marl_tgemm_trace): clock64 phase stamps of steps 8..15, CTA 0 / CTA 100
 };
 #ifdef MARL_GRU_TRACE      // tools/gru_trace.py with an A/B build (tools/ab_build.py trace -DMARL_GRU_TRACE)
@@ -94,11 +99,18 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
     float (*ring)[R][MARL_G] = reinterpret_cast<float (*)[R][MARL_G]>(smem + 2 * R * MARL_H);       // [D][R][3H]
     const int tid = threadIdx.x & (kGruThreads - 1), ks = tid & 1, j = tid >> 1;
     const int L = a.L, N = a.N;
+    // logical position (what the CTAs are dealt) -> row b*N + n: identity, or the length-sorted deal of row_order_kernel
+    // (resolved once per pass into shared memory: the previous pass ended with a group barrier)
+    __shared__ int srow_all[kGruGroups][kGruMaxRows];
+    int* srow = srow_all[bar_id - 1];
+    if (tid < R) { const int* order = a.row_order[chain]; srow[tid] = (order && tid < nrows) ? __ldg(order + row0 + tid) : row0 + tid; }
+    group_sync(bar_id);
+    auto row_at = [&](int rr) { return srow[rr]; };
     constexpr int OWN = (R + 1) / 2;                  // rows whose gate math this lane owns: rr = ks + 2q
     bool own[OWN]; long long base[OWN];
 #pragma unroll
     for (int q = 0; q < OWN; ++q) {
-        const int rr = ks + 2 * q, row = row0 + rr;
+        const int rr = ks + 2 * q, row = row_at(rr);
         own[q] = rr < nrows;
         base[q] = own[q] ? ((long long)(row / N) * L * N + (row % N)) : 0;
     }
@@ -107,7 +119,7 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
     long long csrc[NCH]; int cdst[NCH];
 #pragma unroll
     for (int l = 0; l < NCH; ++l) {
-        const int c = tid + l * kGruThreads, rr = c / 48, ch = c % 48, row = row0 + rr;
+        const int c = tid + l * kGruThreads, rr = c / 48, ch = c % 48, row = row_at(rr);
         if (c < R * 48 && rr < nrows) {
             csrc[l] = ((long long)(row / N) * L * N + (row % N)) * MARL_G + ch * 4;
             cdst[l] = rr * MARL_G + ch * 4;
@@ -120,7 +132,7 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
 #endif
     const float* h0 = a.h0[chain];
     for (int idx = tid; idx < R * MARL_H; idx += kGruThreads) {
-        const int rr = idx / MARL_H, jj = idx % MARL_H, row = row0 + rr;
+        const int rr = idx / MARL_H, jj = idx % MARL_H, row = row_at(rr);
         hs[0][rr][jj] = (h0 && rr < nrows) ? h0[(long long)row * MARL_H + jj] : 0.0f;
     }
     int cur = 0;
@@ -147,7 +159,7 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
         int Lp = L;
         if (S.ep_len) {
             Lp = 1;
-            for (int rr = 0; rr < nrows; ++rr) Lp = max(Lp, min(L, __ldg(S.ep_len + (row0 + rr) / N)));
+            for (int rr = 0; rr < nrows; ++rr) Lp = max(Lp, min(L, __ldg(S.ep_len + row_at(rr) / N)));
         }
         auto issue = [&](int t) {
             if (t < Lp) {
@@ -241,7 +253,7 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
         if (S.h_last) {
 #pragma unroll
             for (int q = 0; q < OWN; ++q)
-                if (own[q]) S.h_last[(long long)(row0 + ks + 2 * q) * MARL_H + j] = hs[cur][ks + 2 * q][j];
+                if (own[q]) S.h_last[(long long)row_at(ks + 2 * q) * MARL_H + j] = hs[cur][ks + 2 * q][j];
         }
     }
 }
@@ -256,12 +268,10 @@ __device__ __forceinline__ void cta_rows(int rows, int chain, int& begin, int& c
     begin = pos * base + (pos < rem ? pos : rem);
 }
 
-constexpr int kGruGroups = 2;      // chains advanced side by side in one CTA (one 128-thread group each)
 #ifndef MARL_GRU_SPARE_SMS
 #define MARL_GRU_SPARE_SMS 16
 #endif
 constexpr int kGruFwdSpareSMs = MARL_GRU_SPARE_SMS;
-constexpr int kGruMaxRows = 8;     // rows per group and pass
 constexpr size_t gru_fwd_smem(int R) { return (size_t)(2 * R * MARL_H + kGiDepth * R * MARL_G) * sizeof(float); }
 
 __global__ void __launch_bounds__(kGruThreads * kGruGroups) gru_unroll_fwd_kernel(GruFwdArgs a) {
@@ -296,6 +306,7 @@ struct GruBwdArgs {
     float* dh0;            // [B*N,H] or null
     int B, L, N;
     const int* ep_len;     // [B] or null: a row's chain starts at its episode's last real step
+    const int* row_order;  // [B*N] or null: logical position -> row (row_order_kernel)
 };
 
 constexpr int kBwdSlot = 7 * MARL_H;     // r, z, n, gh_n (4H) | h_prev | dh_ext | dh_ext2   per row and time step
@@ -309,11 +320,15 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
     float (*ring)[R][kBwdSlot] = reinterpret_cast<float (*)[R][kBwdSlot]>(gru_smem + 2 * R * MARL_G); // [D][R][7H]
     const int tid = threadIdx.x, ks = tid & 1, j = tid >> 1;
     const int L = a.L, N = a.N;
+    __shared__ int srow[kGruMaxRows];         // (the previous pass ended with a block barrier)
+    if (tid < R) srow[tid] = (a.row_order && tid < nrows) ? __ldg(a.row_order + row0 + tid) : row0 + tid;
+    __syncthreads();
+    auto row_at = [&](int rr) { return srow[rr]; };
     constexpr int OWN = (R + 1) / 2;
     bool own[OWN]; long long base[OWN]; float dh_carry[OWN];
 #pragma unroll
     for (int q = 0; q < OWN; ++q) {
-        const int rr = ks + 2 * q, row = row0 + rr;
+        const int rr = ks + 2 * q, row = row_at(rr);
         own[q] = rr < nrows;
         base[q] = own[q] ? ((long long)(row / N) * L * N + (row % N)) : 0;
         dh_carry[q] = 0.0f;
@@ -332,7 +347,7 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
     const float* csrc[NCH]; int cstride[NCH], cdst[NCH], ckind[NCH];
 #pragma unroll
     for (int l = 0; l < NCH; ++l) {
-        const int c = tid + l * kGruThreads, rr = c / 112, ch = c % 112, row = row0 + rr;
+        const int c = tid + l * kGruThreads, rr = c / 112, ch = c % 112, row = row_at(rr);
         csrc[l] = nullptr; cstride[l] = 0; cdst[l] = rr * kBwdSlot + ch * 4; ckind[l] = 0;
         if (c < R * 112 && rr < nrows) {
             const long long idx0 = (long long)(row / N) * L * N + (row % N);
@@ -343,7 +358,6 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
             else { if (a.dh_ext2) { csrc[l] = a.dh_ext2 + idx0 * MARL_H + (ch - 96) * 4; cstride[l] = N * MARL_H; } }
         }
     }
-    const float* h0row = a.h0 ? a.h0 + (long long)row0 * MARL_H : nullptr;
     auto issue = [&](int t) {
         if (t >= 0) {
             float* slot = &ring[t % D][0][0];
@@ -351,7 +365,7 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
             for (int l = 0; l < NCH; ++l) {
                 if (!csrc[l]) continue;
                 if (ckind[l] != 0 && t == 0) {      // h_prev of the first step: h0 (or zeros, handled by the consumer)
-                    if (ckind[l] == 2) cp_async16(slot + cdst[l], h0row + (cdst[l] / kBwdSlot) * MARL_H + (cdst[l] % kBwdSlot - 4 * MARL_H));
+                    if (ckind[l] == 2) cp_async16(slot + cdst[l], a.h0 + (long long)row_at(cdst[l] / kBwdSlot) * MARL_H + (cdst[l] % kBwdSlot - 4 * MARL_H));
                     continue;
                 }
                 cp_async16(slot + cdst[l], csrc[l] + (long long)t * cstride[l]);
@@ -373,11 +387,11 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
     int Lp = L;
     if (a.ep_len) {
         Lp = 1;
-        for (int rr = 0; rr < nrows; ++rr) Lp = max(Lp, min(L, __ldg(a.ep_len + (row0 + rr) / N)));
+        for (int rr = 0; rr < nrows; ++rr) Lp = max(Lp, min(L, __ldg(a.ep_len + row_at(rr) / N)));
         const int tail = L - Lp;
         for (int idx = tid; idx < tail * nrows * (MARL_G / 4); idx += kGruThreads) {
             const int c4 = idx % (MARL_G / 4), rr = (idx / (MARL_G / 4)) % nrows, t = Lp + idx / ((MARL_G / 4) * nrows);
-            const int row = row0 + rr;
+            const int row = row_at(rr);
             const long long off = (((long long)(row / N) * L + t) * N + (row % N)) * MARL_G + 4 * c4;
             *reinterpret_cast<float4*>(a.dgi + off) = make_float4(0.f, 0.f, 0.f, 0.f);
             *reinterpret_cast<float4*>(a.dgh + off) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -454,7 +468,7 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
     if (a.dh0) {
 #pragma unroll
         for (int q = 0; q < OWN; ++q)
-            if (own[q]) a.dh0[(long long)(row0 + ks + 2 * q) * MARL_H + j] = dh_carry[q];
+            if (own[q]) a.dh0[(long long)row_at(ks + 2 * q) * MARL_H + j] = dh_carry[q];
     }
     __syncthreads();
 }
@@ -463,6 +477,8 @@ __device__ __forceinline__ void gru_rows_bwd(const GruBwdArgs& a, int row0, int 
 #define MARL_GRU_BWD_CTAS 2
 #endif
 constexpr int kGruBwdCtasPerSm = MARL_GRU_BWD_CTAS;      // 254 registers x 128 threads and ~55 KB of shared memory: two CTAs fit an SM
+// up to two rows per SM: one CTA per row (see marl_agent_unroll_bwd)
+static int gru_bwd_ctas(int rows) { return rows <= kGruBwdCtasPerSm * kNumSMs ? rows : kNumSMs; }
 constexpr size_t gru_bwd_smem_max() { return gru_bwd_smem(8) > gru_bwd_smem(4) ? gru_bwd_smem(8) : gru_bwd_smem(4); }
 
 __global__ void __launch_bounds__(kGruThreads) gru_unroll_bwd_kernel(GruBwdArgs a) {
@@ -514,6 +530,103 @@ static void plan_rows(GruFwdArgs& ga, int rows, int n_ctas) {
         }
         for (int i = 0; i < n_ctas; ++i) { ga.rows_of[c][i] = (unsigned short)cnt[i]; load[i] += w * cnt[i]; }
     }
+}
+
+// ---- length-sorted row deal ------------------------------------------------------------------------------
+// With per-episode early exit a CTA's time is (steps of its rows) x (cost of a step at its row count), and rows that share a
+// pass advance in lock-step to the longest of them.  The plans above fix HOW MANY rows each CTA takes; this kernel decides
+// WHICH: rows are ranked by episode length (longest first, ties by index: the agents of an episode stay together) and dealt pass
+// by pass -- the first pass (up to 8 rows) of every CTA, then the second, ... -- within a pass level to the CTAs in the order
+// `seq` (fewest rows first: at config 2 the 28 CTAs that carry two rows of the 240-step chain get the 56 shortest rows), the
+// direction alternating from level to level so that the sums stay balanced.  out[logical position] = row.
+constexpr int kMaxOrderCtas = 2 * kNumSMs;      // the BPTT kernel runs up to two one-row CTAs per SM
+constexpr int kMaxOrderEpisodes = 4096;          // (larger batches keep the index order)
+constexpr int kOrderWarps = 8;
+template <int C>
+struct OrderPlan {
+    int n_ctas;                 // 0: unused
+    int* out;                   // [B*N]
+    const int* ep_len;          // [B]
+    unsigned short cnt[C];      // rows of CTA c (its logical positions are contiguous, CTA after CTA)
+    unsigned short pos[C];      // place of CTA c in the deal: 0 gets the longest rows of a pass level, n_ctas - 1 the shortest
+};
+struct OrderArgs {
+    OrderPlan<kNumSMs> fwd[kMaxStreams];
+    OrderPlan<kMaxOrderCtas> bwd;
+    int B, N;
+};
+
+// grid (ceil(n_ctas / 8), plans), one warp per CTA of the plan
+__global__ void __launch_bounds__(kOrderWarps * 32) row_order_kernel(const __grid_constant__ OrderArgs a) {
+    pdl_enter();
+    __shared__ unsigned short cnt[kMaxOrderCtas], pos[kMaxOrderCtas];
+    __shared__ unsigned short ep_of_rank[kMaxOrderEpisodes];
+    __shared__ int s_n;
+    const int k = blockIdx.y;
+    int* out; const int* ep_len;
+    if (k < kMaxStreams) {
+        out = a.fwd[k].out; ep_len = a.fwd[k].ep_len;
+        if (threadIdx.x == 0) s_n = a.fwd[k].n_ctas;
+        for (int i = threadIdx.x; i < kNumSMs; i += blockDim.x) { cnt[i] = a.fwd[k].cnt[i]; pos[i] = a.fwd[k].pos[i]; }
+    } else {
+        out = a.bwd.out; ep_len = a.bwd.ep_len;
+        if (threadIdx.x == 0) s_n = a.bwd.n_ctas;
+        for (int i = threadIdx.x; i < kMaxOrderCtas; i += blockDim.x) { cnt[i] = a.bwd.cnt[i]; pos[i] = a.bwd.pos[i]; }
+    }
+    __syncthreads();
+    const int n_ctas = s_n, B = a.B, N = a.N;
+    if (n_ctas == 0 || (int)blockIdx.x * kOrderWarps >= n_ctas) return;
+    // rank of every episode: the episodes in front of b are the longer ones and the equally long earlier ones
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int len = __ldg(ep_len + b);
+        int rank = 0;
+        for (int o = 0; o < B; ++o) { const int lo = __ldg(ep_len + o); rank += (lo > len || (lo == len && o < b)) ? 1 : 0; }
+        ep_of_rank[rank] = (unsigned short)b;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, c = blockIdx.x * kOrderWarps + (threadIdx.x >> 5);
+    if (c >= n_ctas) return;
+    const int mine = cnt[c], mypos = pos[c];
+    int begin = 0;                                  // logical position of this CTA's first row
+    for (int o = lane; o < c; o += 32) begin += cnt[o];
+    begin = (int)warp_sum((float)begin);            // (exact: < 2^24 rows)
+    int level_start = 0;                            // sorted position of the first row of pass level p
+    for (int p = 0; p * kGruMaxRows < mine; ++p) {
+        int before = 0, width = 0;                  // rows of level p dealt before this CTA's / in the whole level
+        for (int o = lane; o < n_ctas; o += 32) {
+            const int w = min(max((int)cnt[o] - kGruMaxRows * p, 0), kGruMaxRows);
+            width += w;
+            if ((p & 1) ? pos[o] > mypos : pos[o] < mypos) before += w;        // the deal runs backwards on odd levels
+        }
+        before = (int)warp_sum((float)before); width = (int)warp_sum((float)width);
+        const int w = min(mine - kGruMaxRows * p, kGruMaxRows);
+        if (lane < w) {
+            const int sorted = level_start + before + lane;
+            out[begin + kGruMaxRows * p + lane] = (int)ep_of_rank[sorted / N] * N + sorted % N;
+        }
+        level_start += width;
+    }
+}
+
+// pos = place of every CTA when the CTAs are sorted by (rows, index) ascending.  BPTT with one-row CTAs and more CTAs than SMs: the
+// CTAs that have an SM to themselves come first, the ones that share one (i and i + kNumSMs, as the block scheduler places them) last
+template <int C>
+static void order_plan_fill(OrderPlan<C>& pl, const unsigned short* cnt, int n_ctas, const int* ep_len, int* out) {
+    pl.n_ctas = n_ctas; pl.out = out; pl.ep_len = ep_len;
+    unsigned short seq[C];
+    for (int c = 0; c < C; ++c) { pl.cnt[c] = c < n_ctas ? cnt[c] : 0; pl.pos[c] = 0; }
+    int m = 0;
+    unsigned short mx = 0;
+    for (int c = 0; c < n_ctas; ++c) mx = cnt[c] > mx ? cnt[c] : mx;
+    const int shared = (mx <= 1 && n_ctas > kNumSMs) ? n_ctas - kNumSMs : 0;
+    if (shared) {
+        for (int c = shared; c < kNumSMs; ++c) seq[m++] = (unsigned short)c;
+        for (int c = 0; c < shared; ++c) { seq[m++] = (unsigned short)c; seq[m++] = (unsigned short)(c + kNumSMs); }
+    } else {
+        for (int c = 0; c < n_ctas; ++c) seq[m++] = (unsigned short)c;
+        std::stable_sort(seq, seq + n_ctas, [&](unsigned short x, unsigned short y) { return cnt[x] < cnt[y]; });
+    }
+    for (int i = 0; i < n_ctas; ++i) pl.pos[seq[i]] = (unsigned short)i;
 }
 
 // (O may be 0 or negative for a FULL input, where only O + A + N = the network's input width is meaningful; the entry points
@@ -570,6 +683,88 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         if (!s[i].full_input && d->O <= 0) return MARL_EINVAL;
         if (s[i].h0_from >= i) return MARL_EINVAL;
         if (s[i].h0_from >= 0 && s[s[i].h0_from].ep_len) return MARL_EINVAL;     // a continued stream must run to L (header)
+    }
+    // phase B: build chains (a stream whose h0_from == j continues chain of j; j must be a chain tail)
+    GruFwdArgs ga{};
+    ga.B = d->B; ga.L = d->L; ga.N = d->N;
+    int order[kMaxStreams], n_ordered = 0;
+    bool used[kMaxStreams] = {};
+    for (int i = 0; i < n_streams; ++i) {
+        if (s[i].h0_from >= 0) continue;
+        int c = ga.n_chains++;
+        ga.chain_start[c] = n_ordered;
+        ga.h0[c] = s[i].h0;
+        int cur = i;
+        while (cur >= 0) {
+            order[n_ordered++] = cur; used[cur] = true;
+            int nxt = -1;
+            for (int k = cur + 1; k < n_streams; ++k)
+                if (!used[k] && s[k].h0_from == cur) { nxt = k; break; }
+            cur = nxt;
+        }
+        ga.chain_len[c] = n_ordered - ga.chain_start[c];
+    }
+    if (n_ordered != n_streams) return MARL_EINVAL;   // two successors of one stream are not supported
+    for (int k = 0; k < n_streams; ++k) {
+        const marl_unroll_stream& u = s[order[k]];
+        ga.seg[k] = GruSegment{u.gi, u.params.w_hh, u.params.b_hh, u.hidden, u.gates, u.h_last, u.ep_len};
+    }
+    // A recurrence CTA takes an SM's whole register file, so nothing else runs beside it.  When leaving a few SMs out does not
+    // add a row to the fullest CTA, they go to the kernels sibling streams have queued (the target hyper-network forward of
+    // QMIX otherwise waits for this kernel to END, in front of the mixing kernel).
+    const int rows = d->B * d->N;
+    int n_ctas = rows < kNumSMs ? rows : kNumSMs;
+    if (rows > kNumSMs && (rows + kNumSMs - kGruFwdSpareSMs - 1) / (kNumSMs - kGruFwdSpareSMs) == (rows + kNumSMs - 1) / kNumSMs)
+        n_ctas = kNumSMs - kGruFwdSpareSMs;
+    if ((rows + n_ctas - 1) / n_ctas + 2 > 65535) return MARL_EINVAL;
+    plan_rows(ga, rows, n_ctas);
+    std::unique_ptr<ForkJoin> order_lane;
+    {
+        // length-sorted deal of the rows (row_order_kernel): a chain whose streams carry an episode-length array and a scratch
+        // array; the order for this step's BPTT kernel (same rule on ITS plan) comes out of the same launch
+        OrderArgs oa{};
+        oa.B = d->B; oa.N = d->N;
+        bool any = false;
+        for (int c = 0; c < ga.n_chains; ++c) {
+            const int* len = nullptr; int* out = nullptr;
+            for (int k = ga.chain_start[c]; k < ga.chain_start[c] + ga.chain_len[c]; ++k) {
+                if (!len) len = s[order[k]].ep_len;
+                if (!out) out = s[order[k]].row_order;
+            }
+            if (!len || !out || d->B > kMaxOrderEpisodes) continue;
+            order_plan_fill(oa.fwd[c], ga.rows_of[c], n_ctas, len, out);
+            ga.row_order[c] = out;
+            any = true;
+        }
+        for (int i = 0; i < n_streams && !oa.bwd.n_ctas; ++i)
+            if (s[i].row_order_bwd && d->B <= kMaxOrderEpisodes) {
+                const int* len = nullptr;
+                for (int k = 0; k < n_streams && !len; ++k) len = s[k].ep_len;
+                if (!len) return MARL_EINVAL;
+                unsigned short cnt[kMaxOrderCtas];
+                const int nb = gru_bwd_ctas(rows);
+                for (int c = 0; c < nb; ++c) cnt[c] = (unsigned short)(rows / nb + (c < rows % nb ? 1 : 0));     // cta_rows()
+                order_plan_fill(oa.bwd, cnt, nb, len, s[i].row_order_bwd);
+                any = true;
+            }
+        // episode lengths + row orders run on a forked lane BESIDE the input layers; the recurrence waits for both
+        const float* padded = nullptr; int* len_out = nullptr;
+        for (int i = 0; i < n_streams && !padded; ++i)
+            if (s[i].padded && s[i].ep_len) { padded = s[i].padded; len_out = const_cast<int*>(s[i].ep_len); }
+        if (any || padded) {
+            order_lane.reset(new ForkJoin(st, 2));
+            cudaStream_t ls = order_lane->lane(1);
+            if (padded) {
+                ProfScope ps_("episode_lengths_kernel", ls);
+                launch_pdl(episode_lengths_kernel, dim3((d->B + 7) / 8), dim3(256), 0, ls, padded, d->B, d->L, len_out);
+                MARL_LAUNCH_CHECK();
+            }
+            if (any) {
+                ProfScope ps_("row_order_kernel", ls);
+                launch_pdl(row_order_kernel, dim3((gru_bwd_ctas(rows) + kOrderWarps - 1) / kOrderWarps, kMaxStreams + 1), dim3(kOrderWarps * 32), 0, ls, oa);
+                MARL_LAUNCH_CHECK();
+            }
+        }
     }
     // phase A: x = relu(fc1(input)), gi = W_ih x + b_ih for every stream
     auto fc1_of = [&](int i) {
@@ -643,47 +838,14 @@ extern "C" int marl_agent_unroll_fwd(const marl_dims* d, const marl_unroll_strea
         }
         fa.join();
     }
-    // phase B: build chains (a stream whose h0_from == j continues chain of j; j must be a chain tail)
-    GruFwdArgs ga{};
-    ga.B = d->B; ga.L = d->L; ga.N = d->N;
-    int order[kMaxStreams], n_ordered = 0;
-    bool used[kMaxStreams] = {};
-    for (int i = 0; i < n_streams; ++i) {
-        if (s[i].h0_from >= 0) continue;
-        int c = ga.n_chains++;
-        ga.chain_start[c] = n_ordered;
-        ga.h0[c] = s[i].h0;
-        int cur = i;
-        while (cur >= 0) {
-            order[n_ordered++] = cur; used[cur] = true;
-            int nxt = -1;
-            for (int k = cur + 1; k < n_streams; ++k)
-                if (!used[k] && s[k].h0_from == cur) { nxt = k; break; }
-            cur = nxt;
-        }
-        ga.chain_len[c] = n_ordered - ga.chain_start[c];
-    }
-    if (n_ordered != n_streams) return MARL_EINVAL;   // two successors of one stream are not supported
-    for (int k = 0; k < n_streams; ++k) {
-        const marl_unroll_stream& u = s[order[k]];
-        ga.seg[k] = GruSegment{u.gi, u.params.w_hh, u.params.b_hh, u.hidden, u.gates, u.h_last, u.ep_len};
-    }
-    const int rows = d->B * d->N;
     {
         // one CTA per SM; each CTA advances its share of every chain side by side (one 128-thread group per chain)
         ProfScope ps_("gru_unroll_fwd_kernel", st);
         const size_t sm = kGruGroups * gru_fwd_smem(kGruMaxRows);
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(gru_unroll_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); attr_set = true; }
-        // A recurrence CTA takes an SM's whole register file, so nothing else runs beside it.  When leaving a few SMs out does not
-        // add a row to the fullest CTA, they go to the kernels sibling streams have queued (the target hyper-network forward of
-        // QMIX otherwise waits for this kernel to END, in front of the mixing kernel).
-        int n_ctas = rows < kNumSMs ? rows : kNumSMs;
-        if (rows > kNumSMs && (rows + kNumSMs - kGruFwdSpareSMs - 1) / (kNumSMs - kGruFwdSpareSMs) == (rows + kNumSMs - 1) / kNumSMs)
-            n_ctas = kNumSMs - kGruFwdSpareSMs;
-        if ((rows + n_ctas - 1) / n_ctas + 2 > 65535) return MARL_EINVAL;
-        plan_rows(ga, rows, n_ctas);
         ga.trace = trace_buffer();
+        if (order_lane) order_lane->join();
         dim3 grid(n_ctas, (ga.n_chains + kGruGroups - 1) / kGruGroups);
         launch_pdl_prio(kGruPrio, gru_unroll_fwd_kernel, grid, dim3(kGruThreads * kGruGroups), sm, st, ga);
     }
@@ -723,7 +885,7 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
         if ((rc = linear_dgrad(g, st))) return rc;
     }
     GruBwdArgs ga{a->gates, a->hidden, a->dq ? a->dhext : nullptr, a->dhidden, a->params.w_hh, a->h0, a->dgi, a->dgh, a->dh0,
-                  d->B, d->L, d->N, a->ep_len};
+                  d->B, d->L, d->N, a->ep_len, (a->ep_len && d->B <= kMaxOrderEpisodes) ? a->row_order : nullptr};
     const int rows = d->B * d->N;
     {
         ProfScope ps_("gru_unroll_bwd_kernel", st);
@@ -735,7 +897,7 @@ extern "C" int marl_agent_unroll_bwd(const marl_dims* d, const marl_unroll_bwd* 
         pdl_small_problem() = false;
         // up to two rows per SM: one CTA per row -- two co-resident one-row CTAs overlap each other's latency, where one CTA with two
         // rows serialises 2 x 96 packed FMAs per thread on the dependent chain (the 12 two-row CTAs of config 2 ended the kernel)
-        const int n_ctas = rows <= kGruBwdCtasPerSm * kNumSMs ? rows : kNumSMs;
+        const int n_ctas = gru_bwd_ctas(rows);
         launch_pdl_prio(kGruPrio, gru_unroll_bwd_kernel, dim3(n_ctas), dim3(kGruThreads), gru_bwd_smem_max(), st, ga);
         pdl_small_problem() = keep_;
     }

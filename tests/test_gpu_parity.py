@@ -510,6 +510,39 @@ def test_early_exit_unroll_changes_nothing_the_loss_reads(alg, double_q):
     assert abs(le[0] - oloss) <= TOL * abs(oloss)
 
 
+@pytest.mark.parametrize("B", [20, 40, 64, 400])
+def test_early_exit_sorted_row_deal(B):
+    """Under args.early_exit the recurrence rows are dealt to the CTAs sorted by episode length (row_order_kernel in agent.cu:
+    the CTAs with the most rows get the shortest ones, lock-step passes hold rows of similar length).  Row counts that give
+    one row per CTA (B = 20), one-row CTAs sharing an SM in the BPTT kernel (40), several rows per CTA (64) and several passes per
+    CTA (400): every
+    order array is a permutation of the rows, agents of an episode stay together, and loss / gradients equal the un-sorted
+    full-length run's."""
+    T, N = 10, 5
+    rb = synthetic_batch(5, B, T, N, 11, 80, 120, full_length_first=True, min_len=2)
+    out = {}
+    for early in (False, True):
+        args = PU.make_args("qmix", N, 11, 80, 120, T, double_q=True, early_exit=early, cuda_graph=False)
+        learner, _ = PU.build_pair(args)
+        loss = learner.train({k: v.copy() for k, v in rb.items()}, 0)
+        out[early] = (loss, learner._flat.grad.clone(), learner.last["ws"])
+    (lf, gf, _), (le, ge, ws) = out[False], out[True]
+    assert abs(lf - le) <= 1e-6 * abs(lf) and PU.rel_err(ge, gf) < 2e-6
+    lens = ws["ep_len"].cpu().numpy()
+    order = ws["row_order"].cpu().numpy()
+    for k in (1, 2, 3):                                  # target chain, double-Q chain (continues stream 0), BPTT
+        assert np.array_equal(np.sort(order[k]), np.arange(B * N)), k
+    # the longest episode's rows sit where the plan has the fewest rows per CTA, the shortest where it has the most: with one
+    # row per CTA everywhere that is plain descending order, ties in index order
+    if B == 20:
+        want = np.repeat(np.argsort(-lens, kind="stable"), N) * N + np.tile(np.arange(N), B)
+        for k in (1, 2, 3):
+            assert np.array_equal(order[k], want), k
+    if B == 40:
+        sh, un = np.r_[0:B * N - 148, 148:B * N], np.arange(B * N - 148, 148)     # BPTT: one-row CTAs that share an SM / do not
+        assert lens[order[3][sh] // N].max() <= lens[order[3][un] // N].min()
+
+
 def test_early_exit_matches_ragged_reference_golden():
     """The reference-generated ragged golden (truncation L < T, episodes of different lengths) with early exit on."""
     z = GU.load("ragged_qmix_rms")
