@@ -130,7 +130,7 @@ typedef struct marl_unroll_stream {
                                 it through h0_from) carry an ep_len and a row_order, the chain's rows (b, n) are dealt to the
                                 recurrence CTAs sorted by episode length -- the CTAs that advance the most rows get the shortest
                                 ones, rows that advance in lock-step have similar lengths -- instead of in index order.  Results
-                                are unchanged (rows are independent); the call fills the array itself.  (Batches of more than 4096
+                                are unchanged (rows are independent); the call fills the array itself.  (Batches of more than 1024
                                 episodes keep the index order, here and in the backward.) */
     int* row_order_bwd;      /* out [B*N] ints or NULL (needs an ep_len on some stream of the call): the same deal for the plan
                                 of marl_agent_unroll_bwd; hand it to marl_unroll_bwd.row_order of the SAME step */

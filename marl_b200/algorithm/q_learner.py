@@ -450,11 +450,13 @@ class QLearner:
 
         # per-episode early exit of the recurrences.  The eval unroll on `o` must run to L when the double-Q
         # unroll continues from its final hidden state (the reference carries it through the padded steps, q_learner.py:96,110)
-        # args.early_exit: True / False, or None (default) = on from 512 agent rows: measured on ragged batches (lengths
-        # U{T/2..T}, tools/early_exit_bench.py) the step is 5 % / 6 % shorter at B = 256 / 1024, while at B = 32 the shorter
-        # recurrences (-4 us forward, -4 us BPTT) only pay for the two small launches that find the lengths and deal the rows
+        # args.early_exit: True / False, or None (default) = on from 640 agent rows when there is a time axis to cut.  Measured on
+        # ragged batches (lengths U{T/2..T}, tools/early_exit_bench.py, profiles/r2c_early_exit.txt): the QMIX step is 7 % / 5.5 % / 6 %
+        # shorter at B = 128 / 256 / 1024 (640 / 1280 / 5120 rows); at config 2 (160 rows, one or two per CTA) the kernels still end
+        # with the CTA that holds the longest episode and the shorter chains of the others (-4 us forward, -4 us BPTT in isolation)
+        # do not show in the step: 317.6 us either way
         ee = getattr(a, "early_exit", None)
-        early = (B * a.n_agents >= 512) if ee is None else bool(ee)
+        early = (B * a.n_agents >= 640 and Lq >= 16) if ee is None else bool(ee)
         if early:
             n_launch += 2      # episode lengths + row orders, launched by marl_agent_unroll_fwd beside the input layers
         ep_len = ws["ep_len"].data_ptr() if early else None

@@ -540,7 +540,7 @@ static void plan_rows(GruFwdArgs& ga, int rows, int n_ctas) {
 // `seq` (fewest rows first: at config 2 the 28 CTAs that carry two rows of the 240-step chain get the 56 shortest rows), the
 // direction alternating from level to level so that the sums stay balanced.  out[logical position] = row.
 constexpr int kMaxOrderCtas = 2 * kNumSMs;      // the BPTT kernel runs up to two one-row CTAs per SM
-constexpr int kMaxOrderEpisodes = 4096;          // (larger batches keep the index order)
+constexpr int kMaxOrderEpisodes = 1024;          // (larger batches keep the index order: the ranking below is O(B^2 / 256) per block)
 constexpr int kOrderWarps = 8;
 template <int C>
 struct OrderPlan {
