@@ -41,6 +41,20 @@ inline bool select_ok(const marl_select_fused* s) {
     return (((uintptr_t)s->hidden_evals | (uintptr_t)s->hidden_targets | (uintptr_t)s->hidden_evals_next |
              (uintptr_t)s->fc2_w | (uintptr_t)s->fc2_w_target) & 15) == 0;
 }
+#ifndef MARL_HEADS_MMA
+#define MARL_HEADS_MMA 1
+#endif
+// x = hi + lo, both rounded to TF32 (integer add + mask = round to nearest, ties away: umma.cuh tf32_rna)
+__device__ __forceinline__ void head_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
+}
+// d[16x8] += a[16x8] . b[8x8]   (row.col, fp32 accumulate; fragment layout of the PTX ISA: lane = 4 g + t holds a(g, t), a(g+8, t),
+// a(g, t+4), a(g+8, t+4); b(t, g), b(t+4, g); d(g, 2t), d(g, 2t+1), d(g+8, 2t), d(g+8, 2t+1))
+__device__ __forceinline__ void head_mma(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
 constexpr int kHeadLd = MARL_H + 4;    // padded row of the staged head weights / hidden slabs (floats)
 // floats of one warp's staging area: [N, A] slabs (2, or 3 with heads) rounded up to 16 bytes, then (heads) the sample's
 // three hidden slabs [N][kHeadLd]
@@ -103,9 +117,84 @@ __device__ __forceinline__ void warp_select(const SelectArgs& s, long long m, in
         float4* sht = she + N * LQ;
         float4* shn = sht + N * LQ;
         if (!prestaged) warp_stage_hidden_async(s, m, N, A, lane, stage);
+#if MARL_HEADS_MMA
+        // the availability mask of the sample: its global round trip overlaps the wait for the hidden rows
+        float av_pre[2];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) av_pre[it] = lane + 32 * it < NA ? s.avail_next[o + lane + 32 * it] : 1.0f;
+#endif
         cp_async_wait<0>();
         __syncwarp();
         MIX_SEL_STAMP(31);
+#if MARL_HEADS_MMA
+        // The three head products of the sample, q = W2 h + b2 for its 3 N hidden rows, on the tensor cores (mma.sync m16n8k8,
+        // TF32 operands split hi + lo in registers, lo.hi + hi.lo in their own accumulator, hi.hi in the main one: the 3xTF32
+        // scheme of linear.cu).  The slabs [e | t | n] are one row-major [3N][kHeadLd] matrix = the A operand (fragment loads
+        // hit 32 different banks: row stride 68), a head matrix row = a column of B.  Both weight sets run over every row
+        // tile that holds one of their rows; a row keeps the product with its own set.  The raw products land in the [N, A] slabs; a second pass, lane = slab entry, masks them and writes q / qt / qn
+        // with coalesced stores.  The FFMA form of this loop (below) was bound by shared-memory wavefronts: 112 128-bit loads per
+        // lane and sample (tools/mix_trace.py: 10.5 of the kernel's 32 us).
+        {
+            const int R3 = 3 * N, g = lane >> 2, t = lane & 3;
+            const float* hrows = (const float*)she;
+            const float* bias = heads + 2 * A * kHeadLd;
+            for (int m0 = 0; m0 < R3; m0 += 16) {
+                const int ra = m0 + g, rb = m0 + g + 8;
+                const float* pa = hrows + min(ra, R3 - 1) * kHeadLd + t;
+                const float* pb = hrows + min(rb, R3 - 1) * kHeadLd + t;
+                // rows of the target net: slab 1 = [N, 2N); rows of the online net: the rest
+                const bool has_t = m0 < 2 * N && m0 + 16 > N, has_e = m0 < N || m0 + 16 > 2 * N;
+                for (int set = 0; set < 2; ++set) {           // (one weight set at a time: both at once is 32 accumulators and spills)
+                    if (set ? !has_t : !has_e) continue;
+                    for (int c0 = 0; c0 < A; c0 += 16) {
+                        const bool two = c0 + 8 < A;
+                        const float* w0 = heads + (set * A + min(c0 + g, A - 1)) * kHeadLd + t;
+                        const float* w1 = heads + (set * A + min(c0 + 8 + g, A - 1)) * kHeadLd + t;
+                        float am[2][4] = {}, ac[2][4] = {};                               // per column tile: main, corrections
+#pragma unroll
+                        for (int ks = 0; ks < MARL_H / 8; ++ks) {
+                            uint32_t ah[4], al[4];
+                            head_split(pa[8 * ks], ah[0], al[0]); head_split(pb[8 * ks], ah[1], al[1]);
+                            head_split(pa[8 * ks + 4], ah[2], al[2]); head_split(pb[8 * ks + 4], ah[3], al[3]);
+#pragma unroll
+                            for (int jj = 0; jj < 2; ++jj) {
+                                if (jj && !two) continue;
+                                const float* w = jj ? w1 : w0;
+                                uint32_t bh[2], bl[2];
+                                head_split(w[8 * ks], bh[0], bl[0]); head_split(w[8 * ks + 4], bh[1], bl[1]);
+                                head_mma(ac[jj], al, bh); head_mma(ac[jj], ah, bl); head_mma(am[jj], ah, bh);
+                            }
+                        }
+                        MIX_SEL_STAMP(33);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int r = h ? rb : ra;
+                            if (r >= R3) continue;
+                            const int slab = r / N, n = r - slab * N;          // 0: eval(o), 1: target(o_next), 2: eval(o_next)
+                            if ((slab == 1) != (set == 1)) continue;
+                            float* dst = (slab == 0 ? se : slab == 1 ? st : sn) + n * A;
+#pragma unroll
+                            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const int a = c0 + 8 * jj + 2 * t + e;
+                                    if (a < A) dst[a] = (am[jj][2 * h + e] + ac[jj][2 * h + e]) + bias[set * A + a];
+                                }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            MIX_SEL_STAMP(34);
+            for (int i = lane, it = 0; i < NA; i += 32, ++it) {
+                const bool off = (it < 2 ? av_pre[it & 1] : s.avail_next[o + i]) == 0.0f;
+                s.q[o + i] = se[i];
+                const float qt = off ? kNegBig : st[i];                                      // q_learner.py:105
+                s.qt[o + i] = qt; st[i] = qt;
+                if (s.qn) { const float qn = sn[i]; s.qn[o + i] = qn; sn[i] = off ? kNegBig : qn; }     // :110-112 (the masked copy is not kept)
+            }
+        }
+#else
         // one lane = one agent and TWO actions: the agent's three hidden rows are read once for both, 7 instead of 10 128-bit
         // shared-memory loads per 24 FMAs (the loop is bound by shared-memory bandwidth, tools/mix_trace.py)
         const int A2 = (A + 1) >> 1;
@@ -148,6 +237,7 @@ __device__ __forceinline__ void warp_select(const SelectArgs& s, long long m, in
                 if (s.qn) { s.qn[o + j] = qn; sn[j] = off ? kNegBig : qn; }     // :110-112 (the masked copy is not kept)
             }
         }
+#endif
     } else {
         for (int i = lane; i < NA; i += 32) {
             const bool off = s.avail_next[o + i] == 0.0f;
