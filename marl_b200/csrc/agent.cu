@@ -155,6 +155,10 @@ __device__ __forceinline__ void gru_chain_fwd(const GruFwdArgs& a, int chain, in
             gp_out[q] = S.gates ? S.gates + base[q] * (4 * MARL_H) + j : nullptr;
         }
         const long long hstep = (long long)N * MARL_H, gstep = (long long)N * 4 * MARL_H;
+        // (measured and dropped: the time loop of the one- and two-row passes unrolled by the ring depth, ring slots and h-buffer side as
+        // compile-time constants -- the loop-back went from 90 to 28 cycles and the refill from 60 to 40 in the clock64 trace, the
+        // two-row CTAs from 720 to ~635 cycles per step, but the CTAs that run a target group beside their eval row stayed at ~730
+        // and the step got 2.5 us SLOWER (four times the code in two groups at different places: instruction cache))
         // early exit: the rows of this pass advance in lock-step, so the pass runs to the longest of its episodes
         int Lp = L;
         if (S.ep_len) {
