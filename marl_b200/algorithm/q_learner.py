@@ -527,15 +527,22 @@ class QLearner:
             g = qplex_struct(lambda n: self._flat.ptr("mixer." + n, self._flat.grad), K, L.QplexGrads, layers=nl)
             wse, wst, dws = ws_struct(ws["qp"]), ws_struct(ws["qp_t"]), ws_struct(ws["dqp"])
             # q_tot = v_tot + a_tot (q_learner.py:120-135); target likewise with the eval net's argmax (:138-158)
+            # the target mixer only shares the selection's outputs with the eval mixer: its chain of products runs beside it
+            if self._side is None:
+                self._side = th.cuda.Stream()
+            self._side.wait_stream(cur)
+            with th.cuda.stream(self._side):
+                sps = L.stream_ptr()
+                if double_q:
+                    L.call("marl_qplex_fwd", M, C.byref(qd), C.byref(ptg), ws["q_tc"].data_ptr(), bt["s_next"].data_ptr(),
+                           ws["oh_star"].data_ptr(), ws["qt_max"].data_ptr(), C.byref(wst), None, None,
+                           ws["q_tot_t"].data_ptr(), sps)
+                else:
+                    L.call("marl_qplex_fwd", M, C.byref(qd), C.byref(ptg), ws["q_tc"].data_ptr(), bt["s_next"].data_ptr(),
+                           None, None, C.byref(wst), ws["q_tot_t"].data_ptr(), None, None, sps)
             L.call("marl_qplex_fwd", M, C.byref(qd), C.byref(p), ws["q_chosen"].data_ptr(), bt["s"].data_ptr(),
                    bt["u_onehot"].data_ptr(), ws["max_q"].data_ptr(), C.byref(wse), None, None, ws["q_tot"].data_ptr(), sp)
-            if double_q:
-                L.call("marl_qplex_fwd", M, C.byref(qd), C.byref(ptg), ws["q_tc"].data_ptr(), bt["s_next"].data_ptr(),
-                       ws["oh_star"].data_ptr(), ws["qt_max"].data_ptr(), C.byref(wst), None, None,
-                       ws["q_tot_t"].data_ptr(), sp)
-            else:
-                L.call("marl_qplex_fwd", M, C.byref(qd), C.byref(ptg), ws["q_tc"].data_ptr(), bt["s_next"].data_ptr(),
-                       None, None, C.byref(wst), ws["q_tot_t"].data_ptr(), None, None, sp)
+            cur.wait_stream(self._side)
             L.call("marl_td_loss", M, ws["q_tot"].data_ptr(), ws["q_tot_t"].data_ptr(), bt["r"].data_ptr(),
                    bt["terminated"].data_ptr(), bt["padded"].data_ptr(), float(self.gamma), ws["dq_tot"].data_ptr(),
                    scalars, sp)

@@ -12,6 +12,7 @@
 // followed by one warp-per-sample kernel (lane = agent) doing the transformation, the lambda heads and
 // the dueling sums; its backward emits d(o3), d(wv), dq and the GEMM chain is walked in reverse.
 #include "linear.h"
+#include "forkjoin.h"
 #include "../../include/marl_b200.h"
 #include "profile.h"
 
@@ -240,11 +241,16 @@ extern "C" int marl_qplex_bwd(int M, const marl_qplex_dims* d, const marl_qplex_
         { ProfScope ps_("qplex_mix_kernel", st); qplex_mix_kernel<<<blocks, 256, 0, st>>>(a); }
         MARL_LAUNCH_CHECK();
     }
+    // The data gradients form the dependent chain (LFV, L3k, L3n, L2: small, latency-bound products); every weight gradient only
+    // reads what the chain has already produced, so they run on a forked lane BESIDE it instead of between its links (eager
+    // timeline of config 3, profiles/r2c_cfg3_timeline.txt: 1.34 ms of alternating weight / data gradients on one stream).
+    ForkJoin fw(st, 2);
+    cudaStream_t wl = fw.lane(1);
     {   // LFV backward: weights, then dh1[:, 0:2he] (through relu)
         LinearWgrad w{};
         w.dy = dws->wv; w.lddy = 2 * l.N; w.dy_bs = l.N; w.in = plain_operand(ws->h1, l.W1, l.he, l.he);
         w.dw = g->wfv; w.ldw = l.he; w.dw_bs = (long long)l.N * l.he; w.db = g->bfv; w.db_bs = l.N; w.M = M; w.N = l.N; w.batch = 2;
-        if ((rc = linear_wgrad(w, st))) return rc;
+        if ((rc = linear_wgrad(w, wl))) return rc;
         LinearDgrad dg{};
         dg.dy = dws->wv; dg.lddy = 2 * l.N; dg.dy_bs = l.N; dg.w = p->wfv; dg.ldw = l.he; dg.w_bs = (long long)l.N * l.he;
         dg.dx = dws->h1; dg.lddx = l.W1; dg.dx_bs = l.he; dg.relu_src = ws->h1; dg.ldrs = l.W1; dg.rs_bs = l.he;
@@ -256,13 +262,13 @@ extern "C" int marl_qplex_bwd(int M, const marl_qplex_dims* d, const marl_qplex_
         LinearWgrad w{};
         w.dy = dws->o3; w.lddy = l.W3; w.in = plain_operand(s, l.S, l.S);
         w.dw = g->w3k; w.ldw = l.S; w.db = g->b3k; w.M = M; w.N = l.K + l.K * l.N; w.batch = 1;
-        if ((rc = linear_wgrad(w, st))) return rc;
+        if ((rc = linear_wgrad(w, wl))) return rc;
         LinearWgrad w2{};
         LinOperand in = plain_operand(s, l.S, l.S);
         in.x2 = actions; in.ldx2 = l.N * l.A; in.K2 = l.N * l.A;
         w2.dy = dws->o3 + l.K + l.K * l.N; w2.lddy = l.W3; w2.in = in;
         w2.dw = g->w3n; w2.ldw = l.S + l.N * l.A; w2.db = g->b3n; w2.M = M; w2.N = l.K * l.N; w2.batch = 1;
-        if ((rc = linear_wgrad(w2, st))) return rc;
+        if ((rc = linear_wgrad(w2, wl))) return rc;
     } else if (with_adv) {
         int hp, dhp;
         const float* hx = ext_hidden(l, ws, hp);
@@ -271,7 +277,7 @@ extern "C" int marl_qplex_bwd(int M, const marl_qplex_dims* d, const marl_qplex_
             LinearWgrad w{};
             w.dy = dws->o3; w.lddy = l.W3; w.dy_bs = 1; w.in = plain_operand(hx, hp, l.ae, l.ae);
             w.dw = g->w3k; w.ldw = l.ae; w.dw_bs = l.ae; w.db = g->b3k; w.db_bs = 1; w.M = M; w.N = 1; w.batch = l.K;
-            if ((rc = linear_wgrad(w, st))) return rc;
+            if ((rc = linear_wgrad(w, wl))) return rc;
             LinearDgrad dg{};
             dg.dy = dws->o3; dg.lddy = l.W3; dg.dy_bs = 1; dg.w = p->w3k; dg.ldw = l.ae; dg.w_bs = l.ae;
             dg.dx = dhx; dg.lddx = dhp; dg.dx_bs = l.ae; dg.relu_src = hx; dg.ldrs = hp; dg.rs_bs = l.ae;
@@ -281,7 +287,7 @@ extern "C" int marl_qplex_bwd(int M, const marl_qplex_dims* d, const marl_qplex_
             w2.dy = dws->o3 + l.K; w2.lddy = l.W3; w2.dy_bs = l.N; w2.in = plain_operand(hx + l.K * l.ae, hp, l.ae, l.ae);
             w2.dw = g->w3n; w2.ldw = l.ae; w2.dw_bs = (long long)l.N * l.ae; w2.db = g->b3n; w2.db_bs = l.N;
             w2.M = M; w2.N = l.N; w2.batch = 2 * l.K;
-            if ((rc = linear_wgrad(w2, st))) return rc;
+            if ((rc = linear_wgrad(w2, wl))) return rc;
             LinearDgrad d2{};
             d2.dy = dws->o3 + l.K; d2.lddy = l.W3; d2.dy_bs = l.N; d2.w = p->w3n; d2.ldw = l.ae; d2.w_bs = (long long)l.N * l.ae;
             d2.dx = dhx + l.K * l.ae; d2.lddx = dhp; d2.dx_bs = l.ae; d2.relu_src = hx + l.K * l.ae; d2.ldrs = hp;
@@ -293,7 +299,8 @@ extern "C" int marl_qplex_bwd(int M, const marl_qplex_dims* d, const marl_qplex_
             w.dy = dws->h2; w.lddy = l.W2; w.dy_bs = l.ae; w.in = plain_operand(ws->h1 + 2 * l.he, l.W1, l.ae, l.ae);
             w.dw = g->w2; w.ldw = l.ae; w.dw_bs = (long long)l.ae * l.ae; w.db = g->b2; w.db_bs = l.ae;
             w.M = M; w.N = l.ae; w.batch = 3 * l.K;
-            if ((rc = linear_wgrad(w, st))) return rc;
+            ForkJoin f2(st, 2);            // (same side stream: behind the weight gradients above, and behind the dh2 the chain just wrote)
+            if ((rc = linear_wgrad(w, f2.lane(1)))) return rc;
             LinearDgrad dg{};
             dg.dy = dws->h2; dg.lddy = l.W2; dg.dy_bs = l.ae; dg.w = p->w2; dg.ldw = l.ae; dg.w_bs = (long long)l.ae * l.ae;
             dg.dx = dws->h1 + 2 * l.he; dg.lddx = l.W1; dg.dx_bs = l.ae; dg.relu_src = ws->h1 + 2 * l.he; dg.ldrs = l.W1;
@@ -306,7 +313,8 @@ extern "C" int marl_qplex_bwd(int M, const marl_qplex_dims* d, const marl_qplex_
             in.x2 = actions; in.ldx2 = l.N * l.A; in.K2 = l.N * l.A;
             w.dy = dws->h1 + l.Ws; w.lddy = l.W1; w.in = in;
             w.dw = g->w1a; w.ldw = l.S + l.N * l.A; w.db = g->b1a; w.M = M; w.N = l.K * l.ae; w.batch = 1;
-            if ((rc = linear_wgrad(w, st))) return rc;
+            ForkJoin f3(st, 2);            // dh1 is complete: this one beside the L1s weight gradient below
+            if ((rc = linear_wgrad(w, f3.lane(1)))) return rc;
         }
     }
     {   // L1s weights (only the heads that were evaluated)
@@ -315,6 +323,7 @@ extern "C" int marl_qplex_bwd(int M, const marl_qplex_dims* d, const marl_qplex_
         w.dw = g->w1s; w.ldw = l.S; w.db = g->b1s; w.M = M; w.N = with_adv ? l.Ws : 2 * l.he; w.batch = 1;
         if ((rc = linear_wgrad(w, st))) return rc;
     }
+    fw.join();                             // every lane above is the same side stream: one join covers them
     return MARL_OK;
 }
 

@@ -36,5 +36,6 @@ print(f"sum {tot/P*1e3:.1f} us/step")
 # the longest launches of the last step
 last = rows[-(len(rows) // P):] if rows else []
 t0 = last[0][1] if last else 0
-for n, s, e in sorted(last, key=lambda r: -(r[2]-r[1]))[:14]:
+full = os.environ.get("MARL_FULL_TIMELINE", "0") == "1"      # every launch of the step in start order instead of the 14 longest
+for n, s, e in (sorted(last, key=lambda r: r[1]) if full else sorted(last, key=lambda r: -(r[2]-r[1]))[:14]):
     print(f"   {s - t0:9.1f} {e - t0:9.1f} {e - s:8.1f}  {n}")
