@@ -97,15 +97,28 @@ class QTRANLearner(QLearner):
         hid_e, hid_t = ws["hidden"][0].data_ptr(), ws["hidden"][1].data_ptr()
         wq, wqt, wqh, wv = (net_ws_struct(ws[k]) for k in ("nq", "nqt", "nqh", "nv"))
         dwq, dwv = net_ws_struct(ws["dnq"]), net_ws_struct(ws["dnv"])
-        # get_qtran (qtran_learner.py:165-200)
-        L.call("marl_qtran_net_fwd", M, N, S, A, qh, C.byref(pq), bt["s"].data_ptr(), hid_e, bt["u_onehot"].data_ptr(),
-               C.byref(wq), ws["jq"].data_ptr(), sp)
-        L.call("marl_qtran_net_fwd", M, N, S, A, qh, C.byref(pqt), bt["s_next"].data_ptr(), hid_t, ws["oh_t"].data_ptr(),
-               C.byref(wqt), ws["jq_t"].data_ptr(), sp)
-        L.call("marl_qtran_net_fwd", M, N, S, A, qh, C.byref(pq), bt["s"].data_ptr(), hid_e, ws["oh_e"].data_ptr(),
-               C.byref(wqh), ws["jq_hat"].data_ptr(), sp)
-        L.call("marl_qtran_net_fwd", M, N, S, 0, qh, C.byref(pv), bt["s"].data_ptr(), hid_e, None, C.byref(wv),
-               ws["vv"].data_ptr(), sp)
+        # get_qtran (qtran_learner.py:165-200): the four network evaluations (joint Q at the taken actions, target joint Q, joint Q at
+        # the greedy actions, V) only share their inputs -- chains of small, latency-bound products: three of them run on side
+        # streams beside the first
+        cur = th.cuda.current_stream()
+        if getattr(self, "_net_streams", None) is None:
+            self._net_streams = [th.cuda.Stream() for _ in range(3)]
+        calls = (
+            (pq, bt["s"].data_ptr(), hid_e, bt["u_onehot"].data_ptr(), wq, ws["jq"], A),
+            (pqt, bt["s_next"].data_ptr(), hid_t, ws["oh_t"].data_ptr(), wqt, ws["jq_t"], A),
+            (pq, bt["s"].data_ptr(), hid_e, ws["oh_e"].data_ptr(), wqh, ws["jq_hat"], A),
+            (pv, bt["s"].data_ptr(), hid_e, None, wv, ws["vv"], 0),
+        )
+        for k, (pp, st_, hid, act, w_, out, a_enc) in enumerate(calls):
+            if k == 0:
+                L.call("marl_qtran_net_fwd", M, N, S, a_enc, qh, C.byref(pp), st_, hid, act, C.byref(w_), out.data_ptr(), sp)
+                continue
+            side = self._net_streams[k - 1]
+            side.wait_stream(cur)
+            with th.cuda.stream(side):
+                L.call("marl_qtran_net_fwd", M, N, S, a_enc, qh, C.byref(pp), st_, hid, act, C.byref(w_), out.data_ptr(), L.stream_ptr())
+        for side in self._net_streams:
+            cur.wait_stream(side)
         L.call("marl_qtran_losses_fwd_bwd", C.byref(d), ws["jq"].data_ptr(), ws["jq_t"].data_ptr(), ws["jq_hat"].data_ptr(),
                ws["vv"].data_ptr(), ws["q_max"].data_ptr(), ws["q_taken"].data_ptr(), ws["opt_e"].data_ptr(),
                bt["u"].data_ptr(), bt["avail_u"].data_ptr(), bt["r"].data_ptr(), bt["terminated"].data_ptr(),

@@ -160,7 +160,7 @@ __device__ __forceinline__ void umma_teardown(const UmmaCtx& c, int nsteps) {
 // Main loop over the reduction range [rbeg, rend): global -> registers (two k-tiles ahead) -> shared (hi, lo)
 // -> tcgen05.mma.  FA(i, r) / FB(j, r) return the operand quad as a float4.  BIAS (weight gradient only)
 // also accumulates the column sums of the A operand into bsum.
-template <bool A_RED, bool B_RED, bool BIAS, class OA, class OB>
+template <bool A_RED, bool B_RED, int BIAS, class OA, class OB>      // BIAS: 0 none, 1 column sums of the A operand, 2 of the B operand
 __device__ __forceinline__ void umma_loop(const UmmaCtx& c, const OA& A, const OB& B, int i0, int j0, int rbeg, int rend, float (&bsum)[2][4]) {
     const QuadMap<A_RED, UM, 2> ma;
     const QuadMap<B_RED, UN, 1> mb;
@@ -233,9 +233,10 @@ __device__ __forceinline__ void umma_loop(const UmmaCtx& c, const OA& A, const O
             for (int l = 0; l < 2; ++l) {
                 const float4 v = ra[d][l];
                 QuadMap<A_RED, UM, 2>::store(st.a_hi, st.a_lo, ma.off[l], v);
-                if (BIAS) { bsum[l][0] += v.x; bsum[l][1] += v.y; bsum[l][2] += v.z; bsum[l][3] += v.w; }
+                if (BIAS == 1) { bsum[l][0] += v.x; bsum[l][1] += v.y; bsum[l][2] += v.z; bsum[l][3] += v.w; }
             }
             QuadMap<B_RED, UN, 1>::store(st.b_hi, st.b_lo, mb.off[0], rb[d]);
+            if (BIAS == 2) { bsum[0][0] += rb[d].x; bsum[0][1] += rb[d].y; bsum[0][2] += rb[d].z; bsum[0][3] += rb[d].w; }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "n"(UTH) : "memory");   // hand the stage to the MMA warp, do not wait for it
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(UTH) linear_fwd_kernel(LinearFwd a) {
     const OpLin A{a.in, z, a.M, K, VEC_A, VEC_A && vec2_ok(a.in)};               // rows m, reduction k (contiguous)
     const OpMat B{a.w + (long long)z * a.w_bs, a.ldw, a.N, K, VEC_B};             // rows n, reduction k (contiguous)
     float unused[2][4];
-    umma_loop<true, true, false>(c, A, B, m0, n0, 0, K, unused);
+    umma_loop<true, true, 0>(c, A, B, m0, n0, 0, K, unused);
     pdl_trigger();                       // main loop done: the next kernel's CTAs may take the freed slots
     const float* bias = a.bias ? a.bias + (long long)z * a.b_bs : nullptr;
     float* y = a.y + (long long)z * a.y_bs;
@@ -329,10 +330,10 @@ __global__ void __launch_bounds__(UTH) linear_dgrad_kernel(LinearDgrad a) {
     float unused[2][4];
     if (WT) {
         const OpMat Bt{a.wt, a.ldwt, a.K, a.N, true};                                    // rows k, reduction n (contiguous): pre-transposed
-        umma_loop<true, true, false>(c, A, Bt, m0, k0, 0, a.N, unused);
+        umma_loop<true, true, 0>(c, A, Bt, m0, k0, 0, a.N, unused);
     } else {
         const OpMat B{a.w + (long long)z * a.w_bs + a.w_col0, a.ldw, a.N, a.K, VEC_B};   // rows n (reduction), cols k (contiguous)
-        umma_loop<true, false, false>(c, A, B, m0, k0, 0, a.N, unused);
+        umma_loop<true, false, 0>(c, A, B, m0, k0, 0, a.N, unused);
     }
     pdl_trigger();                       // main loop done: the next kernel's CTAs may take the freed slots
     float* dx = a.dx + (long long)z * a.dx_bs;
@@ -385,8 +386,8 @@ __global__ void __launch_bounds__(UTH, 3) linear_wgrad_kernel(LinearWgrad a, int
     const OpLin B{a.in, zb, a.M, K, VEC_B, VEC_B && vec2_ok(a.in)};             // rows m (reduction), cols k
     float bsum[2][4] = {};
     const bool want_bias = a.db != nullptr && blockIdx.y == 0;
-    if (want_bias) umma_loop<false, false, true>(c, A, B, i0, j0, mbeg, mend, bsum);
-    else umma_loop<false, false, false>(c, A, B, i0, j0, mbeg, mend, bsum);
+    if (want_bias) umma_loop<false, false, 1>(c, A, B, i0, j0, mbeg, mend, bsum);
+    else umma_loop<false, false, 0>(c, A, B, i0, j0, mbeg, mend, bsum);
     pdl_trigger();                       // main loop done: the next kernel's CTAs may take the freed slots
     if (kMnMajor) {
         // the quads of one 4-wide output group are spread over 8 threads (two reduction indices each): fold them through shared
@@ -461,6 +462,71 @@ __global__ void __launch_bounds__(UTH, 3) linear_wgrad_kernel(LinearWgrad a, int
     umma_teardown(c, nsteps);
 }
 
+// The same product with the roles of the operands swapped: the tile's 128 rows walk the INPUT width k, its 64 columns the
+// outputs n (acc[k][n] = sum_m in[m][k] dy[m][n], stored transposed).  Fewer tiles whenever N <= 64 < K (fc1 of the agent:
+// 64 x 96 -> one tile instead of two, 64 x 150 -> two instead of three, 64 x 348 -> three instead of six), each with a full A
+// operand instead of a half-empty one; the column sums of dy (db) come from the B operand of the k-tile 0 CTAs.
+template <bool VEC_A, bool VEC_B>
+__global__ void __launch_bounds__(UTH, 3) linear_wgrad_swap_kernel(LinearWgrad a, int splits, int chunk, float* part, float* part_b, int ldp) {
+    extern __shared__ unsigned char umma_smem[];
+    const int zb = blockIdx.z / splits, sp = blockIdx.z % splits;
+    const int k0 = blockIdx.x * UM, n0 = blockIdx.y * UN;
+    const int K = lin_width(a.in);
+    const int mbeg = sp * chunk, mend = min(a.M, mbeg + chunk);
+    const int nsteps = mend > mbeg ? ((mend - mbeg + UK - 1) / UK) * (UK / 8) : 0;
+    const UmmaCtx c = umma_setup(umma_smem, nsteps);
+    pdl_wait();
+    const OpLin A{a.in, zb, a.M, K, VEC_B, VEC_B && vec2_ok(a.in)};             // rows m (reduction), cols k
+    const OpMat B{a.dy + (long long)zb * a.dy_bs, a.lddy, a.M, a.N, VEC_A};      // rows m (reduction), cols n
+    float bsum[2][4] = {};
+    const bool want_bias = a.db != nullptr && blockIdx.x == 0;
+    if (want_bias) umma_loop<false, false, 2>(c, A, B, k0, n0, mbeg, mend, bsum);
+    else umma_loop<false, false, 0>(c, A, B, k0, n0, mbeg, mend, bsum);
+    pdl_trigger();
+    {
+        // the quad of a thread: outputs n0 + i .. i + 3 at reduction index r of the k-tile (QuadMap<false, UN, 1>): the 16
+        // reduction indices of an output group meet through shared memory (the stage ring is free again)
+        float (*sb)[UN] = reinterpret_cast<float (*)[UN]>(c.stages);
+        if (want_bias && threadIdx.x < UT) {
+            const QuadMap<false, UN, 1> mb;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sb[mb.r[0]][mb.i[0] + e] = bsum[0][e];
+        }
+        __syncthreads();
+        if (want_bias && threadIdx.x < UN) {
+            const float bmul = a.db_mul != 0.f ? a.db_mul : 1.0f;
+            float v = 0.f;
+#pragma unroll
+            for (int r = 0; r < UK; ++r) v += sb[r][threadIdx.x];
+            const int n = n0 + threadIdx.x;
+            if (n < a.N) {
+                if (part_b) part_b[(long long)blockIdx.z * a.N + n] = bmul * v;
+                else atomicAdd(a.db + (long long)zb * a.db_bs + n, bmul * v);
+            }
+        }
+    }
+    float* dw = a.dw + (long long)zb * a.dw_bs;
+    if (part && mbeg >= mend) {
+        for (int idx = threadIdx.x; idx < UM * UN; idx += UTH) {
+            const int k = k0 + idx % UM, n = n0 + idx / UM;
+            if (n < a.N && k < K) part[((long long)blockIdx.z * a.N + n) * ldp + k] = 0.f;
+        }
+    }
+    if (mbeg < mend)
+        umma_epilogue(c, nsteps, [&](int i, int j, float (&v)[4]) {      // tile row i = k (a warp's lanes: 32 consecutive k), columns j .. j + 3 = n
+            const int k = k0 + i;
+            if (k >= K) return;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int n = n0 + j + e;
+                if (n >= a.N) continue;
+                if (part) part[((long long)blockIdx.z * a.N + n) * ldp + k] = v[e];
+                else atomicAdd(dw + (long long)n * a.ldw + k, v[e]);
+            }
+        });
+    umma_teardown(c, nsteps);
+}
+
 // second stage of the split weight gradient: fixed summation order.  blockDim = (32, 32): threadIdx.x walks 32 consecutive
 // outputs (one coalesced 128-byte read per split), threadIdx.y deals the splits round-robin over 32 groups -- every thread has
 // at most ceil(splits / 32) independent loads in flight, i.e. one memory round trip -- and one thread per output then adds the
@@ -501,6 +567,12 @@ __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(LinearWgrad a, int s
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static int g_deterministic = -1;
+// MARL_B200_WGRAD_SWAP=0: keep the default tile orientation everywhere (A/B switch)
+static bool wgrad_swap_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("MARL_B200_WGRAD_SWAP"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
 bool deterministic_wgrad() {
     if (g_deterministic < 0) { const char* e = getenv("MARL_B200_DETERMINISTIC"); g_deterministic = (e && e[0] == '1') ? 1 : 0; }
     return g_deterministic == 1;
@@ -600,12 +672,20 @@ int linear_wgrad(const LinearWgrad& a, cudaStream_t st) {
         if (tg.add_wgrad(a)) { const int rc = tg.launch(st); return rc ? rc : tg.launch_reduce(st); }
     }
     const int K = lin_width(a.in);
-    const int tiles = cdiv(a.N, UM) * cdiv(K, UN) * a.batch;
+    // tile orientation: outputs n along the 128 tile rows (default) or the input width k (linear_wgrad_swap_kernel), whichever
+    // covers dw with fewer tiles
+    // covers dw with fewer tiles -- provided the swapped grid still fills the machine: measured stand-alone (profiles/
+    // r2c_gemm_linear.txt vs r2b_gemm_linear.txt) 153600 x 64 x 152: 165.6 -> 90.2 us, 5760 x 64 x 1232: 41.0 -> 24.4 us, but
+    // 19200 x 64 x 192 (150 CTAs instead of 225): 17.7 -> 24.2 us, and config 2's fc1 (75 CTAs instead of 150) cost the step 10 us
+    const int tiles_n = cdiv(a.N, UM) * cdiv(K, UN) * a.batch, tiles_s = cdiv(K, UM) * cdiv(a.N, UN) * a.batch;
+    const int ctas_s = tiles_s * max(1, min(cdiv(2 * kNumSMs, tiles_s), cdiv(a.M, 256)));
+    const bool swap = kMnMajor && wgrad_swap_enabled() && tiles_s < tiles_n && 2 * ctas_s >= 3 * kNumSMs;
+    const int tiles = swap ? tiles_s : tiles_n;
     int splits = cdiv(2 * kNumSMs, tiles);
     splits = max(1, min(splits, cdiv(a.M, 256)));   // 128 / 512 rows per split measured slower (r1d)
     int chunk = cdiv(cdiv(a.M, splits), UK) * UK;
     splits = cdiv(a.M, chunk);
-    dim3 grid(cdiv(a.N, UM), cdiv(K, UN), a.batch * splits);
+    dim3 grid(swap ? cdiv(K, UM) : cdiv(a.N, UM), swap ? cdiv(a.N, UN) : cdiv(K, UN), a.batch * splits);
     const bool va = vec_ok_mat(a.dy, a.lddy, a.dy_bs), vb = vec_ok_lin(a.in);
     // deterministic path (marl_set_deterministic / MARL_B200_DETERMINISTIC=1; measured +13 us per weight gradient at the cfg-2
     // sizes, hence opt-in): per-split tiles in the scratch arena (marl_set_scratch) + a fixed-order reduce
@@ -613,7 +693,8 @@ int linear_wgrad(const LinearWgrad& a, cudaStream_t st) {
     const size_t pw = (size_t)a.batch * splits * a.N * ldp * sizeof(float), pb = a.db ? (size_t)a.batch * splits * a.N * sizeof(float) : 0;
     float* part = (splits * a.batch > 0 && deterministic_wgrad()) ? tgemm_scratch(pw + 256 + pb) : nullptr;
     float* part_b = (part && a.db) ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(part) + ((pw + 255) & ~(size_t)255)) : nullptr;
-    { if (prof_enabled()) prof_note(a.N, K, a.M); ProfScope ps_("linear_wgrad_kernel", st); MARL_DISPATCH2(linear_wgrad_kernel, va, vb, grid, st, a, splits, chunk, part, part_b, ldp); }
+    if (swap) { if (prof_enabled()) prof_note(a.N, K, a.M); ProfScope ps_("linear_wgrad_kernel", st); MARL_DISPATCH2(linear_wgrad_swap_kernel, va, vb, grid, st, a, splits, chunk, part, part_b, ldp); }
+    else { if (prof_enabled()) prof_note(a.N, K, a.M); ProfScope ps_("linear_wgrad_kernel", st); MARL_DISPATCH2(linear_wgrad_kernel, va, vb, grid, st, a, splits, chunk, part, part_b, ldp); }
     MARL_LAUNCH_CHECK();
     if (part) {
         const long long total = (long long)a.N * K + a.N;

@@ -7,6 +7,7 @@
 //     sum_n (W2 x_n + b2) = W2 (sum_n x_n) + N b2,
 // which divides its cost by N; concatenations are never materialised (two-source GEMM operands).
 #include "linear.h"
+#include "forkjoin.h"
 #include "../../include/marl_b200.h"
 #include "profile.h"
 
@@ -154,10 +155,15 @@ static int joint_bwd(int M, const JointLayout& l, const marl_qtran_net_params* p
                      float* dhidden, int accumulate_dhidden, const marl_qtran_net_grads* g, cudaStream_t st) {
     int rc;
     const int rows = M * l.N;
+    // The data gradients are the dependent chain; each weight gradient only reads the dy its layer already has, so it goes to a
+    // forked lane (one side stream, forked anew behind every producer) and runs beside the rest of the chain -- the eager timeline
+    // of config 4 (profiles/r2c_cfg4_timeline.txt) had 212 us of weight gradients between 164 us of chain per network.
+    ForkJoin fj(st, 2);
+    auto lane = [&]() { ForkJoin f(st, 2); return f.lane(1); };      // behind everything queued on `st` so far
     {   // head layer 4
         LinearWgrad w{}; w.dy = dout; w.lddy = 1; w.in = plain_operand(ws->a2, l.qh, l.qh);
         w.dw = g->w4; w.ldw = l.qh; w.db = g->b4; w.M = M; w.N = 1; w.batch = 1;
-        if ((rc = linear_wgrad(w, st))) return rc;
+        if ((rc = linear_wgrad(w, lane()))) return rc;
         LinearDgrad d{}; d.dy = dout; d.lddy = 1; d.w = p->w4; d.ldw = l.qh; d.dx = dws->a2; d.lddx = l.qh;
         d.relu_src = ws->a2; d.ldrs = l.qh; d.M = M; d.N = 1; d.K = l.qh; d.batch = 1;
         if ((rc = linear_dgrad(d, st))) return rc;
@@ -165,7 +171,7 @@ static int joint_bwd(int M, const JointLayout& l, const marl_qtran_net_params* p
     {   // head layer 2
         LinearWgrad w{}; w.dy = dws->a2; w.lddy = l.qh; w.in = plain_operand(ws->a1, l.qh, l.qh);
         w.dw = g->w2; w.ldw = l.qh; w.db = g->b2; w.M = M; w.N = l.qh; w.batch = 1;
-        if ((rc = linear_wgrad(w, st))) return rc;
+        if ((rc = linear_wgrad(w, lane()))) return rc;
         LinearDgrad d{}; d.dy = dws->a2; d.lddy = l.qh; d.w = p->w2; d.ldw = l.qh; d.dx = dws->a1; d.lddx = l.qh;
         d.relu_src = ws->a1; d.ldrs = l.qh; d.M = M; d.N = l.qh; d.K = l.qh; d.batch = 1;
         if ((rc = linear_dgrad(d, st))) return rc;
@@ -173,7 +179,7 @@ static int joint_bwd(int M, const JointLayout& l, const marl_qtran_net_params* p
     {   // head layer 0 on [s | enc]: weights for both parts, data gradient only for the encoding
         LinearWgrad w{}; w.dy = dws->a1; w.lddy = l.qh; w.in = head_input(l, s, ws->enc);
         w.dw = g->w0; w.ldw = l.S + l.Din; w.db = g->b0; w.M = M; w.N = l.qh; w.batch = 1;
-        if ((rc = linear_wgrad(w, st))) return rc;
+        if ((rc = linear_wgrad(w, lane()))) return rc;
         LinearDgrad d{}; d.dy = dws->a1; d.lddy = l.qh; d.w = p->w0; d.ldw = l.S + l.Din; d.w_col0 = l.S;
         d.dx = dws->enc; d.lddx = l.Din; d.M = M; d.N = l.qh; d.K = l.Din; d.batch = 1;
         if ((rc = linear_dgrad(d, st))) return rc;
@@ -181,7 +187,7 @@ static int joint_bwd(int M, const JointLayout& l, const marl_qtran_net_params* p
     {   // encoder layer 2 (applied to the agent sum; bias counted N times)
         LinearWgrad w{}; w.dy = dws->enc; w.lddy = l.Din; w.in = plain_operand(ws->es, l.Din, l.Din);
         w.dw = g->we2; w.ldw = l.Din; w.db = g->be2; w.db_mul = (float)l.N; w.M = M; w.N = l.Din; w.batch = 1;
-        if ((rc = linear_wgrad(w, st))) return rc;
+        if ((rc = linear_wgrad(w, lane()))) return rc;
         LinearDgrad d{}; d.dy = dws->enc; d.lddy = l.Din; d.w = p->we2; d.ldw = l.Din; d.dx = dws->es; d.lddx = l.Din;
         d.M = M; d.N = l.Din; d.K = l.Din; d.batch = 1;
         if ((rc = linear_dgrad(d, st))) return rc;
@@ -195,13 +201,14 @@ static int joint_bwd(int M, const JointLayout& l, const marl_qtran_net_params* p
     {   // encoder layer 1 on [hidden | actions]
         LinearWgrad w{}; w.dy = dws->e1; w.lddy = l.Din; w.in = enc_input(l, hidden, actions);
         w.dw = g->we1; w.ldw = l.Din; w.db = g->be1; w.M = rows; w.N = l.Din; w.batch = 1;
-        if ((rc = linear_wgrad(w, st))) return rc;
+        if ((rc = linear_wgrad(w, lane()))) return rc;
         if (dhidden) {
             LinearDgrad d{}; d.dy = dws->e1; d.lddy = l.Din; d.w = p->we1; d.ldw = l.Din; d.w_col0 = 0;
             d.dx = dhidden; d.lddx = l.H; d.M = rows; d.N = l.Din; d.K = l.H; d.accumulate = accumulate_dhidden; d.batch = 1;
             if ((rc = linear_dgrad(d, st))) return rc;
         }
     }
+    fj.join();
     return MARL_OK;
 }
 
