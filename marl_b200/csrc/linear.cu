@@ -678,11 +678,16 @@ int linear_wgrad(const LinearWgrad& a, cudaStream_t st) {
     // r2c_gemm_linear.txt vs r2b_gemm_linear.txt) 153600 x 64 x 152: 165.6 -> 90.2 us, 5760 x 64 x 1232: 41.0 -> 24.4 us, but
     // 19200 x 64 x 192 (150 CTAs instead of 225): 17.7 -> 24.2 us, and config 2's fc1 (75 CTAs instead of 150) cost the step 10 us
     const int tiles_n = cdiv(a.N, UM) * cdiv(K, UN) * a.batch, tiles_s = cdiv(K, UM) * cdiv(a.N, UN) * a.batch;
-    const int ctas_s = tiles_s * max(1, min(cdiv(2 * kNumSMs, tiles_s), cdiv(a.M, 256)));
+    // rows per split of the swapped orientation (MARL_B200_WGRAD_SWAP_ROWS): 64 -- with one or two tiles the grid only fills the
+    // machine when the reduction is cut finer than the 256 rows of the default orientation; config 2's fc1 gradient (1 tile x
+    // 296 splits of 4 k-tiles instead of 2 tiles x 75 splits of 16) takes the step from 320 to 315 us (profiles/r2c_ab_swap_rows.txt)
+    static int swap_rows = -1;
+    if (swap_rows < 0) { const char* e = getenv("MARL_B200_WGRAD_SWAP_ROWS"); swap_rows = e ? atoi(e) : 64; if (swap_rows < 16) swap_rows = 64; }
+    const int ctas_s = tiles_s * max(1, min(cdiv(2 * kNumSMs, tiles_s), cdiv(a.M, swap_rows)));
     const bool swap = kMnMajor && wgrad_swap_enabled() && tiles_s < tiles_n && 2 * ctas_s >= 3 * kNumSMs;
     const int tiles = swap ? tiles_s : tiles_n;
     int splits = cdiv(2 * kNumSMs, tiles);
-    splits = max(1, min(splits, cdiv(a.M, 256)));   // 128 / 512 rows per split measured slower (r1d)
+    splits = max(1, min(splits, cdiv(a.M, swap ? swap_rows : 256)));   // 128 / 512 rows per split measured slower (r1d)
     int chunk = cdiv(cdiv(a.M, splits), UK) * UK;
     splits = cdiv(a.M, chunk);
     dim3 grid(swap ? cdiv(K, UM) : cdiv(a.N, UM), swap ? cdiv(a.N, UN) : cdiv(K, UN), a.batch * splits);
