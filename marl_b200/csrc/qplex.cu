@@ -323,6 +323,9 @@ extern "C" int marl_qplex_bwd(int M, const marl_qplex_dims* d, const marl_qplex_
         w.dw = g->w1s; w.ldw = l.S; w.db = g->b1s; w.M = M; w.N = with_adv ? l.Ws : 2 * l.he; w.batch = 1;
         if ((rc = linear_wgrad(w, st))) return rc;
     }
+    // (measured and dropped: leaving the lane forked past this call so that the last weight gradients run beside the BPTT
+    // recurrence -- a deferred join behind marl_agent_unroll_bwd; 3524 vs 3518 us at config 3, 2895 vs 2877 us with the same
+    // change in qtran.cu at config 4: what the products gain the recurrence loses to them)
     fw.join();                             // every lane above is the same side stream: one join covers them
     return MARL_OK;
 }
