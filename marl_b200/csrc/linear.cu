@@ -680,7 +680,8 @@ int linear_wgrad(const LinearWgrad& a, cudaStream_t st) {
     const int tiles_n = cdiv(a.N, UM) * cdiv(K, UN) * a.batch, tiles_s = cdiv(K, UM) * cdiv(a.N, UN) * a.batch;
     // rows per split of the swapped orientation (MARL_B200_WGRAD_SWAP_ROWS): 64 -- with one or two tiles the grid only fills the
     // machine when the reduction is cut finer than the 256 rows of the default orientation; config 2's fc1 gradient (1 tile x
-    // 296 splits of 4 k-tiles instead of 2 tiles x 75 splits of 16) takes the step from 320 to 315 us (profiles/r2c_ab_swap_rows.txt)
+    // 296 splits of 4 k-tiles instead of 2 tiles x 75 splits of 16) takes the step from 320 to 315 us (profiles/r2c_ab_swap_rows.txt;
+    // 96 / 128 rows: 313 / 319 us; 48 / 32 rows with 3 / 4 CTAs per SM: 320 us; 128-row splits of the default orientation: no change)
     static int swap_rows = -1;
     if (swap_rows < 0) { const char* e = getenv("MARL_B200_WGRAD_SWAP_ROWS"); swap_rows = e ? atoi(e) : 64; if (swap_rows < 16) swap_rows = 64; }
     const int ctas_s = tiles_s * max(1, min(cdiv(2 * kNumSMs, tiles_s), cdiv(a.M, swap_rows)));
