@@ -145,8 +145,12 @@ class QLearner:
         self.optimizer = _FlatOptimizer(self.args.optimizer, self.lr, self._flat, dev)
         self._partials = th.zeros(L.load().marl_optim_partials() if os.path.exists(L.LIB_PATH) else 148,
                                   dtype=th.float32, device=dev)
-        self._loss_out = th.zeros(2, dtype=th.float32, device=dev)
         self._loss_host = th.zeros(2, dtype=th.float32).pin_memory() if dev.type == "cuda" else th.zeros(2)
+        # (loss, gradient norm) of a step: the optimiser kernel stores them straight into the page-locked host buffer (the host
+        # pointer is the device pointer), so the read-back the reference's loss.item() implies is two posted PCIe writes at the end
+        # of the step's last kernel instead of a copy queued behind it; MARL_B200_LOSS_ZEROCOPY=0 keeps the device buffer + copy
+        zero_copy = dev.type == "cuda" and os.environ.get("MARL_B200_LOSS_ZEROCOPY", "1") != "0"
+        self._loss_out = self._loss_host if zero_copy else th.zeros(2, dtype=th.float32, device=dev)
         self._ws, self._graphs = {}, {}
 
     def _build_extra(self, args):
@@ -678,7 +682,8 @@ class QLearner:
         self._run(bt, ws, B, Lq)
         if train_step > 0 and train_step % self.args.target_update_cycle == 0:
             self._update_targets()
-        self._loss_host.copy_(self._loss_out, non_blocking=True)
+        if self._loss_out is not self._loss_host:
+            self._loss_host.copy_(self._loss_out, non_blocking=True)
         th.cuda.current_stream().synchronize()
         # hidden states as the reference leaves them ([B*N, H], q_learner.py:96-110)
         self.eval_net.hidden_states = ws["h_last"][2 if self.args.double_q else 0]
@@ -757,7 +762,8 @@ class QLearner:
         self._launch_optimizer()
         if train_step > 0 and train_step % a.target_update_cycle == 0:
             self._update_targets()
-        self._loss_host.copy_(self._loss_out, non_blocking=True)
+        if self._loss_out is not self._loss_host:
+            self._loss_host.copy_(self._loss_out, non_blocking=True)
         th.cuda.current_stream().synchronize()
         self.max_episode_len = Lq
         self.last = dict(B=B, L=Lq, q_evals=q_evals.detach(), q_tot=q_tot.detach(), a_star=a_star,
