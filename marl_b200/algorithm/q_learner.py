@@ -145,6 +145,7 @@ class QLearner:
         self.optimizer = _FlatOptimizer(self.args.optimizer, self.lr, self._flat, dev)
         self._partials = th.zeros(L.load().marl_optim_partials() if os.path.exists(L.LIB_PATH) else 148,
                                   dtype=th.float32, device=dev)
+        self._graph_key = None
         self._loss_host = th.zeros(2, dtype=th.float32).pin_memory() if dev.type == "cuda" else th.zeros(2)
         # (loss, gradient norm) of a step: the optimiser kernel stores them straight into the page-locked host buffer (the host
         # pointer is the device pointer), so the read-back the reference's loss.item() implies is two posted PCIe writes at the end
@@ -336,8 +337,9 @@ class QLearner:
         ws = self._workspace(B, int(Lq))
         src = L.EpisodeF32()
         keep, converted = [], 0
+        whole = lo == 0 and hi == B_glob               # (a slice is a new tensor object: ~1.5 us each, eleven per step)
         for k in BATCH_KEYS:
-            t = batch[k][lo:hi]
+            t = batch[k] if whole else batch[k][lo:hi]
             want = th.int64 if k == "u" else th.float32
             if t.dtype != want or not t.is_contiguous():
                 t = t.to(want).contiguous()
@@ -351,11 +353,12 @@ class QLearner:
             # per batch (the tensors are kept alive with it); past a few dozen distinct batches the copy path below
             # takes over so that the cache stays bounded.
             bt = dict(zip(BATCH_KEYS, keep))
-            key = (B, int(Lq)) + tuple(bt[k].data_ptr() for k in BATCH_KEYS)
+            key = (B, int(Lq)) + tuple(getattr(src, k) for k in BATCH_KEYS)
             if not self._use_graph or key in self._graphs or len(self._graphs) < self._max_inplace_graphs:
                 if self._use_graph:
                     self._inplace_keep[key] = bt
                 self.ingest_launches = 0
+                self._graph_key = key                  # (_run would rebuild the same tuple from eleven data_ptr() calls)
                 return bt, B, int(Lq), 1
         d = self._dims(B, int(Lq))
         dst = _episode_struct(ws["batch"])
@@ -623,7 +626,9 @@ class QLearner:
         if not self._use_graph:
             self.launches_per_step = self._device_step(bt, ws, B, Lq)
             return
-        key = (B, Lq) + tuple(bt[k].data_ptr() for k in BATCH_KEYS)
+        key, self._graph_key = self._graph_key, None
+        if key is None:
+            key = (B, Lq) + tuple(bt[k].data_ptr() for k in BATCH_KEYS)
         entry = self._graphs.get(key)
         if entry is None or isinstance(entry, int):
             # the first calls with a shape run eagerly (lazy CUDA/NCCL init must not happen in capture).  A graph is only
@@ -669,6 +674,7 @@ class QLearner:
             raise L.MarlLibraryError("QLearner.train needs a CUDA device: marl_b200 has no CPU path")
         if self._separated or getattr(self.args, "train_through_modules", False):
             return self._train_modules(batch, train_step)
+        self._graph_key = None
         if isinstance(batch, DeviceEpisodeBatch):
             bt, B, Lq, _ = self._stage_replay_batch(batch)
             ws = self._workspace(B, Lq)
