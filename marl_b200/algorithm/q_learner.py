@@ -146,6 +146,7 @@ class QLearner:
         self._partials = th.zeros(L.load().marl_optim_partials() if os.path.exists(L.LIB_PATH) else 148,
                                   dtype=th.float32, device=dev)
         self._graph_key = None
+        self._inplace_cache = {}
         self._loss_host = th.zeros(2, dtype=th.float32).pin_memory() if dev.type == "cuda" else th.zeros(2)
         # (loss, gradient norm) of a step: the optimiser kernel stores them straight into the page-locked host buffer (the host
         # pointer is the device pointer), so the read-back the reference's loss.item() implies is two posted PCIe writes at the end
@@ -326,6 +327,19 @@ class QLearner:
         set, so the captured CUDA graph never depends on the caller's addresses."""
         a = self.args
         Lq = batch.get("max_episode_len")
+        # the same dict of the same tensors at the same addresses as in an earlier call (a resident batch that is trained on again):
+        # its in-place staging is reused -- the checks below are ~3 us, the full path ~8 us of a ~285 us step
+        ent = self._inplace_cache.get(id(batch))
+        if ent is not None and ent[0] is batch and ent[2] == Lq:
+            same = True
+            for k, t, p in ent[1]:
+                v = batch[k]
+                if v is not t or v.data_ptr() != p:
+                    same = False
+                    break
+            if same:
+                self.h2d_bytes_last, self.ingest_launches, self._graph_key = 0, 0, ent[3]
+                return ent[4]
         if Lq is None:
             term = batch["terminated"].reshape(batch["terminated"].shape[0], -1)[:, :a.episode_limit] == 1
             has = term.any(dim=1)
@@ -359,6 +373,11 @@ class QLearner:
                     self._inplace_keep[key] = bt
                 self.ingest_launches = 0
                 self._graph_key = key                  # (_run would rebuild the same tuple from eleven data_ptr() calls)
+                if whole and batch.get("max_episode_len") is not None:
+                    if len(self._inplace_cache) >= 64:
+                        self._inplace_cache.clear()
+                    self._inplace_cache[id(batch)] = (batch, [(k, bt[k], bt[k].data_ptr()) for k in BATCH_KEYS],
+                                                      batch.get("max_episode_len"), key, (bt, B, int(Lq), 1))
                 return bt, B, int(Lq), 1
         d = self._dims(B, int(Lq))
         dst = _episode_struct(ws["batch"])
