@@ -147,6 +147,7 @@ class QLearner:
                                   dtype=th.float32, device=dev)
         self._graph_key = None
         self._inplace_cache = {}
+        self._ring_structs = {}
         self._loss_host = th.zeros(2, dtype=th.float32).pin_memory() if dev.type == "cuda" else th.zeros(2)
         # (loss, gradient norm) of a step: the optimiser kernel stores them straight into the page-locked host buffer (the host
         # pointer is the device pointer), so the read-back the reference's loss.item() implies is two posted PCIe writes at the end
@@ -394,13 +395,20 @@ class QLearner:
         lo, hi = self._shard(B_glob)
         B = hi - lo
         ws = self._workspace(B, Lq)
-        src = L.EpisodeF32()
-        for k in BATCH_KEYS:
-            setattr(src, k, ring[k].data_ptr())
-        T_ring = ring["o"].shape[1]
-        d = self._dims(B, Lq)
-        dst = _episode_struct(ws["batch"])
-        idx = batch.idx[lo:hi]
+        # the ring's and the working set's address structs do not change from call to call: built once (22 setattr + data_ptr calls)
+        rs = self._ring_structs.get(id(ring))
+        if rs is None or rs[0] is not ring:
+            src = L.EpisodeF32()
+            for k in BATCH_KEYS:
+                setattr(src, k, ring[k].data_ptr())
+            rs = (ring, src, ring["o"].shape[1], tuple(ring[k].data_ptr() for k in BATCH_KEYS))
+            self._ring_structs = {id(ring): rs}
+        src, T_ring = rs[1], rs[2]
+        gs = ws.get("_gather_structs")
+        if gs is None:
+            gs = ws["_gather_structs"] = (self._dims(B, Lq), _episode_struct(ws["batch"]))
+        d, dst = gs
+        idx = batch.idx if (lo == 0 and hi == B_glob) else batch.idx[lo:hi]
         L.call("marl_replay_gather_f32", C.byref(src), T_ring, idx.data_ptr(), C.byref(d), C.byref(dst), L.stream_ptr())
         self._keep_alive = idx
         self.h2d_bytes_last = 0
