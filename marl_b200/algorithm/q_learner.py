@@ -331,7 +331,7 @@ class QLearner:
         # the same dict of the same tensors at the same addresses as in an earlier call (a resident batch that is trained on again):
         # its in-place staging is reused -- the checks below are ~3 us, the full path ~8 us of a ~285 us step
         ent = self._inplace_cache.get(id(batch))
-        if ent is not None and ent[0] is batch and ent[2] == Lq:
+        if ent is not None and ent[0] is batch and Lq is not None and ent[2] == int(Lq):
             same = True
             for k, t, p in ent[1]:
                 v = batch[k]
@@ -378,7 +378,7 @@ class QLearner:
                     if len(self._inplace_cache) >= 64:
                         self._inplace_cache.clear()
                     self._inplace_cache[id(batch)] = (batch, [(k, bt[k], bt[k].data_ptr()) for k in BATCH_KEYS],
-                                                      batch.get("max_episode_len"), key, (bt, B, int(Lq), 1))
+                                                      int(Lq), key, (bt, B, int(Lq), 1))
                 return bt, B, int(Lq), 1
         d = self._dims(B, int(Lq))
         dst = _episode_struct(ws["batch"])
