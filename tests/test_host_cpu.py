@@ -155,3 +155,36 @@ def test_env_matches_reference_golden():
         assert [info[k] for k in ("n_actions", "n_agents", "state_shape", "obs_shape", "episode_limit")] == list(z[f"t{t}/env_info"])
         env.close()
         assert len(env.replay) == 1 and env.current_episode == 0
+
+
+def test_ctypes_structs_have_the_headers_layout(tmp_path):
+    """Every struct that crosses the C ABI is declared twice -- include/marl_b200.h and the ctypes mirror in marl_b200/_lib.py.
+    A tiny C program compiled against the header prints sizeof and the offset of every field; the mirror must agree (a
+    field added on one side only would shift every pointer behind it)."""
+    import shutil, subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    pairs = {"marl_dims": L.Dims, "marl_episode_f32": L.EpisodeF32, "marl_episode_f64": L.EpisodeF64,
+             "marl_agent_params": L.AgentParams, "marl_agent_grads": L.AgentGrads, "marl_unroll_stream": L.UnrollStream,
+             "marl_unroll_bwd": L.UnrollBwd, "marl_peer_group": L.PeerGroup, "marl_select_fused": L.SelectFused,
+             "marl_qmix_params": L.QmixParams, "marl_qmix_grads": L.QmixGrads, "marl_qmix_hyper2": L.QmixHyper2,
+             "marl_qmix_hyper2_grads": L.QmixHyper2Grads, "marl_qplex_dims": L.QplexDims, "marl_qplex_params": L.QplexParams,
+             "marl_qplex_grads": L.QplexGrads, "marl_qplex_ws": L.QplexWs, "marl_qtran_net_params": L.QtranNetParams,
+             "marl_qtran_net_grads": L.QtranNetGrads, "marl_qtran_net_ws": L.QtranNetWs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "marl_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    r = subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr          # (a field name that only exists in the mirror fails right here)
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
