@@ -14,4 +14,5 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --cache-co
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:"agent_front_kernel|qmix_mix_kernel|gru_unroll|linear_wgrad|linear_dgrad" -s 9 -c 9 -o gpurun_out/r2c_full python tools/prof_step.py qmix 3 > gpurun_out/ncu_full.log 2>&1
 timeout 200 python tools/early_exit_bench.py > gpurun_out/r2c_early_exit.txt 2>&1
 MARL_EARLY=1 timeout 100 python tools/config_kernel_times.py 2s3z > gpurun_out/r2c_cfg2_early_kernels.txt 2>&1
+timeout 100 python tools/host_gap.py > gpurun_out/r2c_host_gap.txt 2>&1
 ls -la gpurun_out | tail -30
